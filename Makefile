@@ -1,0 +1,36 @@
+# Builds the sm_100a shared library (C ABI) and the host CLI, in-tree.
+#   make            -> miekki_b200/libmiekki_b200.so , miekki_b200/cli/miekki
+#   make oracle     -> oracle/_build/libmiekki_oracle.so (+ oracle/_ref/Miekki when the reference is present)
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
+SRC := miekki_b200/csrc
+OBJ := build/obj
+LIB := miekki_b200/libmiekki_b200.so
+CLI := miekki_b200/cli/miekki
+CU := $(SRC)/api.cu $(SRC)/sketch.cu $(SRC)/scan.cu $(SRC)/topk.cu $(SRC)/exact.cu
+OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
+HDRS := $(SRC)/common.cuh $(SRC)/kernels.h include/miekki_b200.h
+
+all: $(LIB) $(CLI)
+
+$(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS)
+
+$(CLI): miekki_b200/cli/main.cpp miekki_b200/cli/fasta.hpp include/miekki_b200.h $(LIB)
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -fopenmp -Iinclude -o $@ miekki_b200/cli/main.cpp \
+	    -Lmiekki_b200 -lmiekki_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
+
+oracle:
+	$(MAKE) -C oracle
+	@if [ -d /root/reference ]; then $(MAKE) -C oracle ref; fi
+
+clean:
+	rm -rf build $(LIB) $(CLI)
+
+.PHONY: all oracle clean

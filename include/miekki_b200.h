@@ -1,0 +1,195 @@
+/*
+ * miekki_b200.h -- C ABI of the B200-native sketch-and-query path of Miekki.
+ *
+ * The reference (Malfoy/Miekki) has no FFI: its boundary is `class Miekki`
+ * (Miekki.h:33-137) as driven by main.cpp:184-235.  Each entry point below
+ * names the reference method it replaces.  Host code (the `miekki` CLI in
+ * miekki_b200/cli/, or any binding -- see INTEGRATION.md) keeps FASTA/gz
+ * parsing and text formatting and calls these with plain pointers and sizes.
+ *
+ * Conventions
+ *  - every call returns 0 on success, <0 on error (mk_last_error() has the text);
+ *  - the caller owns every host buffer; nothing returned points into the library
+ *    except the error string;
+ *  - one mk_ctx drives one GPU (one process per GPU in multi-GPU runs: each rank
+ *    owns a contiguous ascending range of genome ids, see mk_set_shard);
+ *  - calls on one ctx are serialised internally, so host parser threads may call
+ *    concurrently; work is enqueued on the ctx's CUDA stream and every call
+ *    returns after its results are in the caller's buffers;
+ *  - there is no CPU fallback: without a CUDA device mk_create fails.
+ */
+#ifndef MIEKKI_B200_H
+#define MIEKKI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MK_ABI_VERSION 1
+
+enum {
+    MK_OK = 0,
+    MK_ERR_ARG = -1,       /* bad argument (see mk_last_error)                     */
+    MK_ERR_CUDA = -2,      /* CUDA runtime error                                    */
+    MK_ERR_NOMEM = -3,     /* host or device allocation failed                      */
+    MK_ERR_UNSUPPORTED = -4, /* e.g. -f other than 3: reference prints "not implemented" (Miekki.cpp:236) */
+    MK_ERR_STATE = -5      /* call not valid in this state                          */
+};
+
+typedef struct mk_ctx mk_ctx;
+
+/* == similarity_score, Miekki.h:27-31 (24 bytes, same field order) */
+typedef struct mk_hit {
+    uint32_t genome;        /* insertion id (list order), not a file name */
+    uint32_t matches;       /* shared fingerprints                        */
+    double jaccard;         /* matches / sketch_size[genome]              */
+    double intersection;    /* jaccard * genome_size[genome]              */
+} mk_hit;
+
+typedef struct mk_batch mk_batch;   /* sequences resident in HBM */
+
+/* ---- lifetime -------------------------------------------------------------- */
+
+/* Miekki::Miekki(k, h, bits_per_min, bits_mantis, 0, out, b, threshold, t), Miekki.h:66.
+ * bits_per_min must be 8 (the -f 3 default; quirk G12) and bits_mantis 5.
+ * k in [2,31] (Miekki.h:76-77), h in [1,24], bloom_log2 in [32,40] (smaller values
+ * index out of bounds in the reference, Miekki.cpp:124).  device = CUDA ordinal. */
+int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_mantis,
+              uint32_t bloom_log2, uint32_t threshold, int device, mk_ctx **out);
+void mk_destroy(mk_ctx *ctx);
+const char *mk_last_error(const mk_ctx *ctx);   /* ctx may be NULL: last mk_create error */
+int mk_abi_version(void);
+
+/* Run all later work of this ctx on an existing CUDA stream (a cudaStream_t passed as
+ * void*, e.g. torch.cuda.current_stream().cuda_stream).  NULL restores the ctx's own. */
+int mk_set_stream(mk_ctx *ctx, void *cuda_stream);
+
+/* Genome-sharded runs: this ctx holds global ids
+ * [first_id, first_id + mk_index_size).  Hits carry global ids. */
+int mk_set_shard(mk_ctx *ctx, uint32_t first_id);
+
+/* parameters as stored in a dump header (Miekki.cpp:651-661) */
+int mk_get_params(const mk_ctx *ctx, uint32_t *k, uint32_t *h, uint32_t *bits_per_min,
+                  uint32_t *bits_mantis, uint32_t *bloom_log2, uint32_t *threshold);
+
+/* ---- sequences in HBM ------------------------------------------------------ */
+
+/* Copies n ASCII sequences (any bytes; no terminator needed) to the device. */
+int mk_batch_upload(mk_ctx *ctx, const char *const *seqs, const uint64_t *lens, uint32_t n,
+                    mk_batch **out);
+/* Same, from one contiguous host buffer: sequence i is data[offsets[i] .. offsets[i+1]). */
+int mk_batch_upload_flat(mk_ctx *ctx, const char *data, const uint64_t *offsets, uint32_t n,
+                         mk_batch **out);
+/* Bench/test tooling: n synthetic genomes of `len` bases generated on the device with the
+ * counter-based generator of miekki_b200/synth.py:cb_bases (ids first_g .. first_g+n-1). */
+int mk_batch_synth(mk_ctx *ctx, uint64_t seed, uint32_t first_g, uint32_t n, uint64_t len,
+                   mk_batch **out);
+int mk_batch_download(mk_ctx *ctx, const mk_batch *b, uint32_t i, char *dst, uint64_t cap);
+uint32_t mk_batch_size(const mk_batch *b);
+uint64_t mk_batch_bases(const mk_batch *b);
+void mk_batch_free(mk_ctx *ctx, mk_batch *b);
+
+/* ---- build ----------------------------------------------------------------- */
+
+/* Pre-size the bucket-major matrix for n_genomes columns (optional; it grows). */
+int mk_index_reserve(mk_ctx *ctx, uint32_t n_genomes);
+
+/* Miekki::insert_sequences, Miekki.cpp:277-314.  Appends n genomes; ids are assigned in
+ * call order (== `-t 1` list order).  Sequences shorter than k are an error, as the
+ * reference's callers filter them (Miekki.cpp:569). */
+int mk_index_add(mk_ctx *ctx, const char *const *seqs, const uint64_t *lens, uint32_t n);
+int mk_index_add_batch(mk_ctx *ctx, const mk_batch *genomes);   /* same, input already in HBM */
+
+int mk_index_size(const mk_ctx *ctx, uint32_t *n_genomes);
+/* sketch_size (Miekki.h:59) and genome_size (Miekki.h:60) of ids [first, first+n) (local ids) */
+int mk_index_stats(mk_ctx *ctx, uint32_t first, uint32_t n, uint32_t *sketch_size,
+                   uint64_t *genome_size);
+
+/* Payload of Miekki::dump_disk, Miekki.cpp:665-676: rows is 2^h x N bucket-major (row b =
+ * N bytes in id order, no padding); bloom receives bloom_bytes (= 2^b / 8) bytes.  Any
+ * pointer may be NULL to skip that part. */
+int mk_index_export(mk_ctx *ctx, uint8_t *rows, uint64_t *genome_size, uint8_t *bloom,
+                    uint64_t bloom_bytes, uint32_t *sketch_size);
+/* Loader ctor Miekki::Miekki(const string&), Miekki.cpp:682-719 (after the header was
+ * parsed and passed to mk_create).  Replaces the index content.  rows_stride is the
+ * distance in bytes between consecutive bucket rows in `rows` (>= n). */
+int mk_index_import(mk_ctx *ctx, uint32_t n, const uint8_t *rows, uint64_t rows_stride,
+                    const uint64_t *genome_size, const uint8_t *bloom, uint64_t bloom_bytes,
+                    const uint32_t *sketch_size);
+
+/* Bloom bytes only (multi-GPU merge): the window the device keeps is the
+ * first mk_bloom_window() bytes of the 2^b/8-byte table; bytes past it are never touched
+ * for this k.  merge: dst byte = (dst != 0) ? dst : src  ("lowest rank wins"). */
+uint64_t mk_bloom_window(const mk_ctx *ctx);
+int mk_bloom_get(mk_ctx *ctx, uint8_t *dst, uint64_t n);
+int mk_bloom_merge(mk_ctx *ctx, const uint8_t *src, uint64_t n);
+
+/* ---- query ----------------------------------------------------------------- */
+
+/* Miekki::query_sequences + filter_results, Miekki.cpp:344-372 + :376-422.
+ * hits: n * nresults entries, read i at hits[i*nresults ..], nhits[i] valid ones, sorted
+ * like std::sort_heap leaves them (descending intersection; libstdc++ tie order).
+ * Reads shorter than k get nhits = 0 (the reference's callers skip them, :465).
+ * `-a` uses (10, 10, 0.5*threshold), `-e` (5, 10, threshold). */
+int mk_query(mk_ctx *ctx, const char *const *seqs, const uint64_t *lens, uint32_t n,
+             uint32_t nresults, uint32_t min_score, double min_intersection,
+             mk_hit *hits, uint32_t *nhits);
+/* Same with reads already in HBM; hits/nhits are host buffers (NULL: leave on device). */
+int mk_query_batch(mk_ctx *ctx, const mk_batch *reads, uint32_t nresults, uint32_t min_score,
+                   double min_intersection, mk_hit *hits, uint32_t *nhits);
+
+/* Sharded top-k (SURVEY.md 7 hard part 1): ranks are chained in ascending genome-id order.
+ * heap_io: n * nresults mk_hit, len_io: n lengths -- the bounded heap of Miekki.cpp:386-393
+ * as the previous shard left it (len 0 for the first shard).  finalize != 0 on the last
+ * shard applies std::sort_heap (:396). */
+int mk_query_chain(mk_ctx *ctx, const mk_batch *reads, uint32_t nresults, uint32_t min_score,
+                   double min_intersection, mk_hit *heap_io, uint32_t *len_io, int finalize);
+
+/* Test hook: raw shared-fingerprint counts, the matrix Miekki::query_sequences returns
+ * (Miekki.cpp:352): counts[i * N + g].  surviving (may be NULL) receives A(q), the number of
+ * query buckets that are non-empty and pass the Bloom check. */
+int mk_query_counts(mk_ctx *ctx, const char *const *seqs, const uint64_t *lens, uint32_t n,
+                    uint32_t *counts, uint32_t *surviving);
+
+/* Test hook: Miekki::minhash_sketch_partition, Miekki.cpp:150-197.  fp[2^h], anc[2^h]. */
+int mk_sketch(mk_ctx *ctx, const char *seq, uint64_t len, uint8_t *fp, uint64_t *anc,
+              uint32_t *active);
+
+/* ---- exact mode (-e) ------------------------------------------------------- */
+
+/* Miekki::ground_truth_batch, Miekki.cpp:792-859, for one genome file: `records` are the
+ * strings whose k-mers form set B (the host applies the record rules of :803-822), reads
+ * the candidates grouped on that genome.  Per read: nb_inter = |A n B|,
+ * nb_union = |B| + |A \ B| over distinct canonical k-mers (str2num, utils.cpp:276). */
+int mk_exact(mk_ctx *ctx, const char *const *records, const uint64_t *rec_lens, uint32_t n_records,
+             const char *const *reads, const uint64_t *read_lens, uint32_t n_reads,
+             uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct);
+
+/* ---- measurement ----------------------------------------------------------- */
+
+/* Device-side timings (CUDA events on the ctx stream) and work counters accumulated since
+ * the last mk_stats_reset.  Times in milliseconds. */
+typedef struct mk_stats {
+    double sketch_ms;          /* encode + sketch + finalize kernels (build)             */
+    double read_sketch_ms;     /* query-side sketch + Bloom mask                         */
+    double scan_ms;            /* fingerprint scan kernel                                */
+    double topk_ms;            /* threshold + bounded-heap kernel                        */
+    double exact_ms;
+    uint64_t scan_launches;
+    uint64_t scan_row_bytes;   /* algorithmic bytes: sum_q A(q) * N_shard                */
+    uint64_t scan_rows;        /* sum_q A(q)                                             */
+    uint64_t bases_sketched;   /* genome bases through the build kernels                 */
+    uint64_t bases_queried;    /* read bases through the query kernels                   */
+    uint64_t kernel_launches;  /* every kernel this library launched                     */
+    uint64_t h2d_bytes, d2h_bytes;
+} mk_stats;
+int mk_stats_get(mk_ctx *ctx, mk_stats *out);
+int mk_stats_reset(mk_ctx *ctx);
+int mk_sync(mk_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIEKKI_B200_H */

@@ -1,0 +1,1098 @@
+// api.cu -- the C ABI (include/miekki_b200.h): context, HBM layout, orchestration.
+//
+// HBM layout of one context (one GPU, one genome shard):
+//   rows        2^h x stride bytes, bucket-major, stride % 128 == 0, columns >= n hold 255
+//               (== vector<string> index, Miekki.h:54, with the genome axis contiguous)
+//   sketch_size u32[cap], genome_size u64[cap]                       (Miekki.h:59-60)
+//   bloom       the first `window` bytes of the 2^b/8-byte table      (Miekki.h:56)
+//   owner       u32[window]: scratch for the order-exact Bloom insert (all ~0 between calls)
+// plus grow-only scratch for sequence planes, bucket keys, query lists and count tiles.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/miekki_b200.h"
+#include "kernels.h"
+
+using namespace mk;
+
+static_assert(sizeof(mk_hit) == 24 && sizeof(HitDev) == 24, "mk_hit layout");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum Phase { PH_SKETCH = 0, PH_READ_SKETCH, PH_SCAN, PH_TOPK, PH_EXACT, PH_COUNT };
+
+struct PendingEvent {
+    cudaEvent_t a, b;
+    int phase;
+};
+
+}  // namespace
+
+struct mk_batch {
+    uint8_t* chars = nullptr;     // device; sequence i at chars + h_coff[i] (16-byte aligned)
+    uint64_t* d_coff = nullptr;   // device copies of the two arrays below
+    uint64_t* d_len = nullptr;
+    std::vector<uint64_t> h_coff, h_len;
+    uint32_t n = 0;
+    uint64_t bytes = 0;           // padded size of chars
+    uint64_t bases = 0, max_len = 0;
+};
+
+struct mk_ctx {
+    uint32_t k, h, nbm, nbmant, b, threshold;
+    uint64_t B;
+    int device = 0, sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::mutex mu;
+    std::string err;
+
+    uint8_t* rows = nullptr;
+    uint64_t stride = 0;
+    uint32_t n = 0, cap = 0, first_id = 0;
+    uint32_t* d_sketch_size = nullptr;
+    uint64_t* d_genome_size = nullptr;
+    std::vector<uint32_t> h_sketch_size;
+    std::vector<uint64_t> h_genome_size;
+    uint8_t* bloom = nullptr;
+    uint32_t* owner = nullptr;
+    uint64_t window = 0;          // bytes, multiple of 16
+
+    DevBuf planeF, planeR, keys, fp, meta, list, list_len, counts, heap, heap_len, misc;
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+    uint32_t* d_work = nullptr;
+
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<PendingEvent> ev_pending;
+    mk_stats stats{};
+
+    SketchParams sp() const { return SketchParams{(int)k, (int)h, b, window}; }
+};
+
+namespace {
+
+int fail(mk_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? MK_ERR_NOMEM : MK_ERR_CUDA,      \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+#define TRY(expr)                  \
+    do {                           \
+        int r_ = (expr);           \
+        if (r_ != MK_OK) return r_; \
+    } while (0)
+
+int reserve(mk_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return MK_OK;
+    if (b.p) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&b.p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        CU(cudaMalloc(&b.p, want));
+    }
+    b.cap = want;
+    return MK_OK;
+}
+
+int reserve_pinned(mk_ctx* c, size_t bytes) {
+    if (bytes <= c->pinned_cap) return MK_OK;
+    if (c->pinned) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFreeHost(c->pinned));
+        c->pinned = nullptr;
+        c->pinned_cap = 0;
+    }
+    CU(cudaMallocHost(&c->pinned, bytes + bytes / 4));
+    c->pinned_cap = bytes + bytes / 4;
+    return MK_OK;
+}
+
+// ---- device timing ---------------------------------------------------------------
+cudaEvent_t get_event(mk_ctx* c) {
+    if (!c->ev_pool.empty()) {
+        cudaEvent_t e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct PhaseTimer {
+    mk_ctx* c;
+    PendingEvent pe;
+    PhaseTimer(mk_ctx* ctx, int phase) : c(ctx) {
+        pe.a = get_event(c);
+        pe.b = get_event(c);
+        pe.phase = phase;
+        cudaEventRecord(pe.a, c->stream);
+    }
+    ~PhaseTimer() {
+        cudaEventRecord(pe.b, c->stream);
+        c->ev_pending.push_back(pe);
+    }
+};
+void resolve_events(mk_ctx* c) {
+    for (auto& pe : c->ev_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+            double* slot[PH_COUNT] = {&c->stats.sketch_ms, &c->stats.read_sketch_ms, &c->stats.scan_ms,
+                                      &c->stats.topk_ms, &c->stats.exact_ms};
+            *slot[pe.phase] += ms;
+        }
+        c->ev_pool.push_back(pe.a);
+        c->ev_pool.push_back(pe.b);
+    }
+    c->ev_pending.clear();
+}
+int sync(mk_ctx* c) {
+    CU(cudaStreamSynchronize(c->stream));
+    resolve_events(c);
+    return MK_OK;
+}
+
+// ---- index storage ---------------------------------------------------------------
+int ensure_capacity(mk_ctx* c, uint32_t need) {
+    if (need <= c->cap) return MK_OK;
+    uint32_t ncap = std::max<uint32_t>(need, c->cap ? c->cap * 2 : 128);
+    ncap = (ncap + 127) / 128 * 128;
+    uint8_t* nrows = nullptr;
+    const uint64_t bytes = c->B * (uint64_t)ncap;
+    if (cudaMalloc(&nrows, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ncap = (need + 127) / 128 * 128;       // retry without the growth slack
+        CU(cudaMalloc(&nrows, c->B * (uint64_t)ncap));
+    }
+    CU(cudaMemsetAsync(nrows, 0xFF, c->B * (uint64_t)ncap, c->stream));
+    uint32_t* nss = nullptr;
+    uint64_t* ngs = nullptr;
+    CU(cudaMalloc(&nss, (size_t)ncap * 4));
+    CU(cudaMalloc(&ngs, (size_t)ncap * 8));
+    CU(cudaMemsetAsync(nss, 0, (size_t)ncap * 4, c->stream));
+    CU(cudaMemsetAsync(ngs, 0, (size_t)ncap * 8, c->stream));
+    if (c->n) {
+        CU(cudaMemcpy2DAsync(nrows, ncap, c->rows, c->stride, c->n, c->B, cudaMemcpyDeviceToDevice,
+                             c->stream));
+        CU(cudaMemcpyAsync(nss, c->d_sketch_size, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(ngs, c->d_genome_size, (size_t)c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->rows) CU(cudaFree(c->rows));
+    if (c->d_sketch_size) CU(cudaFree(c->d_sketch_size));
+    if (c->d_genome_size) CU(cudaFree(c->d_genome_size));
+    c->rows = nrows;
+    c->d_sketch_size = nss;
+    c->d_genome_size = ngs;
+    c->cap = ncap;
+    c->stride = ncap;
+    return MK_OK;
+}
+
+// ---- batches ---------------------------------------------------------------------
+void batch_layout(mk_batch* b, const uint64_t* lens, uint32_t n) {
+    b->n = n;
+    b->h_coff.resize((size_t)n + 1);
+    b->h_len.assign(lens, lens + n);
+    uint64_t off = 0;
+    b->bases = 0;
+    b->max_len = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        b->h_coff[i] = off;
+        off += (lens[i] + 15) / 16 * 16;
+        b->bases += lens[i];
+        b->max_len = std::max(b->max_len, lens[i]);
+    }
+    b->h_coff[n] = off;
+    b->bytes = off + 64;          // kernels may read one 16-byte word past a sequence
+}
+
+int batch_alloc(mk_ctx* c, mk_batch* b) {
+    CU(cudaMalloc(&b->chars, b->bytes));
+    CU(cudaMalloc(&b->d_coff, ((size_t)b->n + 1) * 8));
+    CU(cudaMalloc(&b->d_len, std::max<size_t>(1, b->n) * 8));
+    CU(cudaMemcpyAsync(b->d_coff, b->h_coff.data(), ((size_t)b->n + 1) * 8, cudaMemcpyHostToDevice,
+                       c->stream));
+    if (b->n)
+        CU(cudaMemcpyAsync(b->d_len, b->h_len.data(), (size_t)b->n * 8, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += ((size_t)b->n * 2 + 1) * 8;
+    return MK_OK;
+}
+
+void batch_release(mk_batch* b) {
+    if (!b) return;
+    if (b->chars) cudaFree(b->chars);
+    if (b->d_coff) cudaFree(b->d_coff);
+    if (b->d_len) cudaFree(b->d_len);
+    delete b;
+}
+
+// gathers sequences [first, first+n) of (seqs, lens) into a new device batch
+int upload_range(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, mk_batch** out) {
+    mk_batch* b = new mk_batch();
+    batch_layout(b, lens, n);
+    int r = batch_alloc(c, b);
+    if (r != MK_OK) { batch_release(b); return r; }
+    // zero the alignment gaps once so that padding bytes are deterministic
+    cudaError_t e = cudaMemsetAsync(b->chars, 0, b->bytes, c->stream);
+    if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
+    const bool big = n && (b->bases / n) >= (1u << 20);
+    if (big) {
+        // few long sequences (genomes): copy each straight from the caller's memory
+        for (uint32_t i = 0; i < n; ++i) {
+            if (!lens[i]) continue;
+            e = cudaMemcpyAsync(b->chars + b->h_coff[i], seqs[i], lens[i], cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
+        }
+    } else if (n) {
+        // many short sequences (reads): pack into pinned staging, one copy
+        r = reserve_pinned(c, b->h_coff[n] + 64);
+        if (r != MK_OK) { batch_release(b); return r; }
+        char* st = static_cast<char*>(c->pinned);
+        for (uint32_t i = 0; i < n; ++i) {
+            memcpy(st + b->h_coff[i], seqs[i], lens[i]);
+            const uint64_t pad = b->h_coff[i + 1] - b->h_coff[i] - lens[i];
+            if (pad) memset(st + b->h_coff[i] + lens[i], 0, pad);
+        }
+        e = cudaMemcpyAsync(b->chars, st, b->h_coff[n], cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
+        // the staging buffer is reused by the next call: wait for the copy
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    c->stats.h2d_bytes += b->bases;
+    *out = b;
+    return MK_OK;
+}
+
+// a view on sequences [first, first+n) of an existing batch (shares chars)
+struct BatchView {
+    const uint8_t* chars;
+    const uint64_t* d_coff;
+    const uint64_t* d_len;
+    const uint64_t* h_len;
+    uint32_t n;
+    uint64_t max_len, bases;
+};
+BatchView view_of(const mk_batch* b, uint32_t first, uint32_t n) {
+    BatchView v{b->chars, b->d_coff + first, b->d_len + first, b->h_len.data() + first, n, 0, 0};
+    for (uint32_t i = 0; i < n; ++i) {
+        v.max_len = std::max(v.max_len, v.h_len[i]);
+        v.bases += v.h_len[i];
+    }
+    return v;
+}
+
+// ---- dense sketch of a view: planes + keys -> fp / anc ------------------------------
+// leaves: c->keys = anc[n][B], c->fp = fp[n][B], c->meta = {woff[n+1] | active[n] | ssum[n]}
+struct DenseOut {
+    uint64_t* d_woff;
+    uint32_t* d_active;
+    unsigned long long* d_ssum;
+};
+int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out) {
+    const uint32_t n = v.n;
+    std::vector<uint64_t> woff((size_t)n + 1);
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        woff[i] = w;
+        w += (v.h_len[i] + 15) / 16 + 2;
+    }
+    woff[n] = w;
+    TRY(reserve(c, c->planeF, (w + 4) * 4));
+    TRY(reserve(c, c->planeR, (w + 4) * 4));
+    TRY(reserve(c, c->keys, (size_t)n * c->B * 8));
+    TRY(reserve(c, c->fp, (size_t)n * c->B));
+    const size_t meta_bytes = ((size_t)n + 1) * 8 + (size_t)n * 8 + (size_t)n * 8;
+    TRY(reserve(c, c->meta, meta_bytes));
+    uint64_t* d_woff = static_cast<uint64_t*>(c->meta.p);
+    unsigned long long* d_ssum = reinterpret_cast<unsigned long long*>(d_woff + n + 1);
+    uint32_t* d_active = reinterpret_cast<uint32_t*>(d_ssum + n);
+    CU(cudaMemcpyAsync(d_woff, woff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_ssum, 0, (size_t)n * 16, c->stream));
+    auto* keys = static_cast<unsigned long long*>(c->keys.p);
+    launch_fill_u64(keys, (uint64_t)n * c->B, ~0ull, c->stream);
+    launch_encode_planes(v.chars, v.d_coff, v.d_len, d_woff, n, v.max_len, (int)c->k,
+                         static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeR.p), c->stream);
+    launch_sketch_dense(static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeR.p), v.d_len,
+                        d_woff, n, v.max_len, (int)c->k, (int)c->h, keys, c->stream);
+    launch_resolve(keys, static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeR.p), d_woff, n,
+                   c->sp(), static_cast<uint8_t*>(c->fp.p), d_active, d_ssum, c->bloom,
+                   bloom_insert ? c->owner : nullptr, c->stream);
+    c->stats.kernel_launches += 4;
+    CU(cudaGetLastError());
+    out->d_woff = d_woff;
+    out->d_active = d_active;
+    out->d_ssum = d_ssum;
+    return MK_OK;
+}
+
+// genomes per dense chunk: bounded by the Bloom owner key (5 + h + 3 bits <= 32) and memory
+uint32_t dense_chunk(const mk_ctx* c) {
+    uint32_t by_key = c->h <= 24 ? (1u << std::min<uint32_t>(29 - c->h, 6)) : 1;
+    uint64_t by_mem = (1ull << 30) / (c->B * 9) ;        // keys + fp <= 1 GiB
+    uint32_t ch = (uint32_t)std::min<uint64_t>(by_key, std::max<uint64_t>(1, by_mem));
+    return std::max<uint32_t>(1, std::min<uint32_t>(ch, 32));
+}
+
+// Miekki.cpp:303-311 on the host, from the device's exact integer statistics
+uint64_t genome_size_of(uint32_t active, unsigned long long ssum31, uint64_t len) {
+    const double S = std::ldexp((double)ssum31, -31);            // sum of 2^-(fp>>3), exact
+    const uint32_t sq = active * active;                          // uint32 wrap: quirk G2
+    const double card = (0.72134 * (double)sq) / S;
+    if (card > (double)len) return len;
+    return (uint64_t)card;
+}
+
+int index_add_view(mk_ctx* c, const mk_batch* b) {
+    for (uint32_t i = 0; i < b->n; ++i)
+        if (b->h_len[i] < c->k)
+            return fail(c, MK_ERR_ARG, "mk_index_add: sequence shorter than k (the reference's callers skip these, Miekki.cpp:569)");
+    const uint32_t chunk = dense_chunk(c);
+    TRY(ensure_capacity(c, c->n + b->n));
+    for (uint32_t first = 0; first < b->n; first += chunk) {
+        const uint32_t n = std::min(chunk, b->n - first);
+        BatchView v = view_of(b, first, n);
+        DenseOut d{};
+        {
+            PhaseTimer t(c, PH_SKETCH);
+            TRY(dense_sketch(c, v, true, &d));
+            launch_bloom_commit(static_cast<unsigned long long*>(c->keys.p), static_cast<uint8_t*>(c->fp.p), n,
+                                c->sp(), c->bloom, c->owner, c->stream);
+            launch_scatter_rows(static_cast<uint8_t*>(c->fp.p), n, (int)c->h, c->rows, c->stride, c->n, c->stream);
+            c->stats.kernel_launches += 2;
+        }
+        std::vector<uint32_t> act(n);
+        std::vector<unsigned long long> ssum(n);
+        CU(cudaMemcpyAsync(act.data(), d.d_active, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(ssum.data(), d.d_ssum, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        std::vector<uint64_t> gs(n);
+        for (uint32_t i = 0; i < n; ++i) gs[i] = genome_size_of(act[i], ssum[i], v.h_len[i]);
+        CU(cudaMemcpyAsync(c->d_sketch_size + c->n, act.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_genome_size + c->n, gs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->h_sketch_size.insert(c->h_sketch_size.end(), act.begin(), act.end());
+        c->h_genome_size.insert(c->h_genome_size.end(), gs.begin(), gs.end());
+        c->n += n;
+        c->stats.bases_sketched += v.bases;
+        c->stats.d2h_bytes += (size_t)n * 12;
+        c->stats.h2d_bytes += (size_t)n * 12 + ((size_t)n + 1) * 8;
+    }
+    return sync(c);
+}
+
+// ---- query: reads -> (bucket << 8 | fp) lists ----------------------------------------
+struct Lists {
+    uint32_t* list;
+    uint64_t* list_off;     // device, n+1
+    uint32_t* list_len;     // device, n
+};
+constexpr uint64_t SPARSE_MAX_KMERS = 12288;   // 16384-slot table at load <= 0.75
+
+int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
+    const uint32_t n = b->n;
+    std::vector<uint64_t> off((size_t)n + 1);
+    std::vector<uint32_t> sparse_ids, dense_ids;
+    uint64_t total = 0, sparse_max = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        off[i] = total;
+        const uint64_t len = b->h_len[i];
+        const uint64_t nk = len > c->k ? len - c->k : 0;
+        // a list can hold at most one entry per k-mer and per bucket
+        total += std::min<uint64_t>(nk, c->B);
+        if (nk == 0) continue;                       // empty sketch (len <= k), empty list
+        if (nk <= SPARSE_MAX_KMERS) {
+            sparse_ids.push_back(i);
+            sparse_max = std::max(sparse_max, len);
+        } else {
+            dense_ids.push_back(i);
+        }
+    }
+    off[n] = total;
+    TRY(reserve(c, c->list, (total + 4) * 4));
+    // list_len | list_off | read ids, all in one small buffer
+    const size_t ll_bytes = ((size_t)n * 4 + 15) / 16 * 16;
+    const size_t lo_bytes = ((size_t)n + 1) * 8;
+    const size_t id_bytes = (size_t)n * 4 + 16;
+    TRY(reserve(c, c->list_len, ll_bytes + lo_bytes + id_bytes));
+    uint8_t* base = static_cast<uint8_t*>(c->list_len.p);
+    uint32_t* d_len = reinterpret_cast<uint32_t*>(base);
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(base + ll_bytes);
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(base + ll_bytes + lo_bytes);
+    CU(cudaMemsetAsync(d_len, 0, ll_bytes, c->stream));
+    CU(cudaMemcpyAsync(d_off, off.data(), lo_bytes, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += lo_bytes;
+    std::vector<uint32_t> ids(sparse_ids);
+    ids.insert(ids.end(), dense_ids.begin(), dense_ids.end());
+    if (!ids.empty()) {
+        CU(cudaMemcpyAsync(d_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += ids.size() * 4;
+    }
+    auto* list = static_cast<uint32_t*>(c->list.p);
+    PhaseTimer t(c, PH_READ_SKETCH);
+    if (!sparse_ids.empty()) {
+        int r = launch_sketch_reads(b->chars, b->d_coff, b->d_len, d_ids, (uint32_t)sparse_ids.size(),
+                                    sparse_max, c->sp(), c->bloom, d_off, list, d_len, c->stream);
+        if (r != 0) return fail(c, MK_ERR_CUDA, "sketch_reads launch configuration failed");
+        c->stats.kernel_launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (!dense_ids.empty()) {
+        // long reads: dense sketch of gathered views, a few at a time
+        const uint32_t chunk = dense_chunk(c);
+        for (size_t first = 0; first < dense_ids.size(); first += chunk) {
+            const uint32_t m = (uint32_t)std::min<size_t>(chunk, dense_ids.size() - first);
+            // gather per-read offsets/lengths for this chunk
+            std::vector<uint64_t> coff(m), len(m);
+            uint64_t max_len = 0, bases = 0;
+            for (uint32_t i = 0; i < m; ++i) {
+                const uint32_t rid = dense_ids[first + i];
+                coff[i] = b->h_coff[rid];
+                len[i] = b->h_len[rid];
+                max_len = std::max(max_len, len[i]);
+                bases += len[i];
+            }
+            TRY(reserve(c, c->misc, (size_t)m * 16));
+            uint64_t* d_c = static_cast<uint64_t*>(c->misc.p);
+            uint64_t* d_l = d_c + m;
+            CU(cudaMemcpyAsync(d_c, coff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_l, len.data(), (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));   // coff/len are stack vectors
+            BatchView v{b->chars, d_c, d_l, len.data(), m, max_len, bases};
+            DenseOut d{};
+            TRY(dense_sketch(c, v, false, &d));
+            launch_compact_list(static_cast<unsigned long long*>(c->keys.p), static_cast<uint8_t*>(c->fp.p), m,
+                                c->sp(), c->bloom, d_ids + sparse_ids.size() + first, d_off, list, d_len,
+                                c->stream);
+            c->stats.kernel_launches += 1;
+            CU(cudaGetLastError());
+        }
+    }
+    out->list = list;
+    out->list_off = d_off;
+    out->list_len = d_len;
+    c->stats.bases_queried += b->bases;
+    return MK_OK;
+}
+
+// reads per scan launch: bounded by the count tile buffer
+uint32_t scan_batch_reads(const mk_ctx* c, uint32_t n_reads) {
+    const uint64_t n_pad = (c->n + 15) / 16 * 16;
+    const uint64_t budget = 1ull << 30;
+    uint64_t q = budget / (n_pad * 4);
+    q = std::max<uint64_t>(1, std::min<uint64_t>(q, n_reads));
+    return (uint32_t)q;
+}
+
+// scans reads [q0, q0+nq) into c->counts
+int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPlan& plan) {
+    PhaseTimer t(c, PH_SCAN);
+    CU(cudaMemsetAsync(c->d_work, 0, 4, c->stream));
+    int r = launch_scan(plan, c->rows, c->stride, c->n, L.list, L.list_off + q0, L.list_len + q0, nq,
+                        static_cast<uint32_t*>(c->counts.p), c->d_work, c->stream);
+    if (r != 0) return fail(c, MK_ERR_CUDA, "scan launch configuration failed");
+    c->stats.kernel_launches += 1;
+    c->stats.scan_launches += 1;
+    CU(cudaGetLastError());
+    return MK_OK;
+}
+
+// accumulates A(q) statistics from the device list lengths
+int account_lists(mk_ctx* c, const Lists& L, uint32_t n, uint32_t* surviving) {
+    std::vector<uint32_t> ll(n);
+    if (n) CU(cudaMemcpyAsync(ll.data(), L.list_len, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint64_t rows = 0;
+    for (uint32_t i = 0; i < n; ++i) rows += ll[i];
+    c->stats.scan_rows += rows;
+    c->stats.scan_row_bytes += rows * c->n;
+    c->stats.d2h_bytes += (size_t)n * 4;
+    if (surviving) memcpy(surviving, ll.data(), (size_t)n * 4);
+    return MK_OK;
+}
+
+// full query of a device batch; heap state in/out through host buffers (may be NULL)
+int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, double min_int,
+                 mk_hit* heap_io, uint32_t* len_io, bool chain_in, int finalize) {
+    if (K < 1 || K > 64) return fail(c, MK_ERR_ARG, "nresults must be in [1, 64]");
+    const uint32_t n = b->n;
+    if (n == 0) return MK_OK;
+    TRY(reserve(c, c->heap, (size_t)n * K * sizeof(HitDev)));
+    TRY(reserve(c, c->heap_len, (size_t)n * 4));
+    auto* d_heap = static_cast<HitDev*>(c->heap.p);
+    auto* d_hlen = static_cast<uint32_t*>(c->heap_len.p);
+    if (chain_in) {
+        if (!heap_io || !len_io) return fail(c, MK_ERR_ARG, "mk_query_chain needs heap_io and len_io");
+        CU(cudaMemcpyAsync(d_heap, heap_io, (size_t)n * K * sizeof(HitDev), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_hlen, len_io, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (size_t)n * (K * sizeof(HitDev) + 4);
+    } else {
+        CU(cudaMemsetAsync(d_hlen, 0, (size_t)n * 4, c->stream));
+    }
+    Lists L{};
+    TRY(build_lists(c, b, &L));
+    if (c->n > 0) {
+        ScanPlan plan{};
+        if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
+            return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
+        const uint32_t qb = scan_batch_reads(c, n);
+        const uint64_t n_pad = (c->n + 15) / 16 * 16;
+        TRY(reserve(c, c->counts, (size_t)qb * n_pad * 4));
+        for (uint32_t q0 = 0; q0 < n; q0 += qb) {
+            const uint32_t nq = std::min(qb, n - q0);
+            TRY(scan_reads(c, L, q0, nq, plan));
+            PhaseTimer t(c, PH_TOPK);
+            launch_topk(static_cast<uint32_t*>(c->counts.p), nq, c->n, c->first_id, c->d_sketch_size,
+                        c->d_genome_size, K, min_score, min_int, d_heap + (size_t)q0 * K, d_hlen + q0,
+                        finalize, c->stream);
+            c->stats.kernel_launches += 1;
+            CU(cudaGetLastError());
+        }
+    }
+    if (heap_io) {
+        CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (size_t)n * K * sizeof(HitDev);
+    }
+    if (len_io) {
+        CU(cudaMemcpyAsync(len_io, d_hlen, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (size_t)n * 4;
+    }
+    TRY(account_lists(c, L, n, nullptr));
+    return sync(c);
+}
+
+struct Guard {
+    std::lock_guard<std::mutex> lk;
+    explicit Guard(mk_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+}  // namespace
+
+// ======================================================================================
+extern "C" {
+
+int mk_abi_version(void) { return MK_ABI_VERSION; }
+
+const char* mk_last_error(const mk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_mantis, uint32_t bloom_log2,
+              uint32_t threshold, int device, mk_ctx** out) {
+    mk_ctx* c = nullptr;
+    if (!out) return fail(c, MK_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (bits_per_min != 8 || bits_mantis != 5)
+        return fail(c, MK_ERR_UNSUPPORTED, "not implemented: only 8-bit fingerprints (-f 3) with a 5-bit exponent (Miekki.cpp:236, quirk G12)");
+    if (k < 2 || k > 31) return fail(c, MK_ERR_ARG, "k must be in [2, 31] (Miekki.h:76-77)");
+    if (h < 1 || h > 24) return fail(c, MK_ERR_ARG, "h must be in [1, 24]");
+    if (bloom_log2 < 32 || bloom_log2 > 40)
+        return fail(c, MK_ERR_ARG, "bloom_log2 must be in [32, 40]: below 32 the reference indexes out of bounds (Miekki.cpp:124)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(c, MK_ERR_CUDA, "no CUDA device: miekki_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(c, MK_ERR_ARG, "bad device ordinal");
+    cudaDeviceProp prop{};
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(c, MK_ERR_CUDA, "cudaSetDevice failed");
+    if (prop.major < 10)
+        return fail(c, MK_ERR_UNSUPPORTED, "miekki_b200 is built for sm_100a (B200) only");
+    mk_ctx* ctx = new mk_ctx();
+    ctx->k = k; ctx->h = h; ctx->nbm = bits_per_min; ctx->nbmant = bits_mantis; ctx->b = bloom_log2;
+    ctx->threshold = threshold;
+    ctx->B = 1ull << h;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    c = ctx;
+    // Bloom window: canonical k-mer < 4^k, the probe term adds < 1024 (utils.cpp:197-199)
+    const uint64_t top = (1ull << (2 * k)) + 1023;
+    uint64_t window = ((top >> bloom_log2) >> 3) + 1;
+    window = std::min<uint64_t>(window, (1ull << bloom_log2) / 8);
+    ctx->window = (window + 15) / 16 * 16;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->bloom, ctx->window);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->owner, ctx->window * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work, 16);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("mk_create: ") + cudaGetErrorString(e);
+        mk_destroy(ctx);
+        return fail(nullptr, MK_ERR_CUDA, msg);
+    }
+    ctx->stream = ctx->own_stream;
+    cudaMemsetAsync(ctx->bloom, 0, ctx->window, ctx->stream);
+    launch_fill_u32(ctx->owner, ctx->window, 0xFFFFFFFFu, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return MK_OK;
+}
+
+void mk_destroy(mk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
+                      &c->heap, &c->heap_len, &c->misc})
+        if (b->p) cudaFree(b->p);
+    for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->bloom,
+                    (void*)c->owner, (void*)c->d_work})
+        if (p) cudaFree(p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto& pe : c->ev_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int mk_set_stream(mk_ctx* c, void* cuda_stream) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    CU(cudaStreamSynchronize(c->stream));
+    resolve_events(c);
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return MK_OK;
+}
+
+int mk_set_shard(mk_ctx* c, uint32_t first_id) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    c->first_id = first_id;
+    return MK_OK;
+}
+
+int mk_get_params(const mk_ctx* c, uint32_t* k, uint32_t* h, uint32_t* bits_per_min, uint32_t* bits_mantis,
+                  uint32_t* bloom_log2, uint32_t* threshold) {
+    if (!c) return MK_ERR_ARG;
+    if (k) *k = c->k;
+    if (h) *h = c->h;
+    if (bits_per_min) *bits_per_min = c->nbm;
+    if (bits_mantis) *bits_mantis = c->nbmant;
+    if (bloom_log2) *bloom_log2 = c->b;
+    if (threshold) *threshold = c->threshold;
+    return MK_OK;
+}
+
+// ---- batches -------------------------------------------------------------------------
+
+int mk_batch_upload(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, mk_batch** out) {
+    if (!c || !out || (n && (!seqs || !lens))) return fail(c, MK_ERR_ARG, "mk_batch_upload: NULL argument");
+    Guard g(c);
+    TRY(upload_range(c, seqs, lens, n, out));
+    return sync(c);
+}
+
+int mk_batch_upload_flat(mk_ctx* c, const char* data, const uint64_t* offsets, uint32_t n, mk_batch** out) {
+    if (!c || !out || (n && (!data || !offsets))) return fail(c, MK_ERR_ARG, "mk_batch_upload_flat: NULL argument");
+    Guard g(c);
+    std::vector<uint64_t> lens(n);
+    bool aligned = true;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail(c, MK_ERR_ARG, "offsets must be non-decreasing");
+        lens[i] = offsets[i + 1] - offsets[i];
+        aligned = aligned && (offsets[i] % 16 == 0);
+    }
+    mk_batch* b = new mk_batch();
+    batch_layout(b, lens.data(), n);
+    int r = batch_alloc(c, b);
+    if (r != MK_OK) { batch_release(b); return r; }
+    cudaError_t e = cudaSuccess;
+    if (aligned && n && offsets[0] == 0 && b->h_coff[n] >= offsets[n] &&
+        std::equal(b->h_coff.begin(), b->h_coff.begin() + n, offsets)) {
+        // the caller's layout already is ours (every start 16-byte aligned): one copy
+        e = cudaMemsetAsync(b->chars + offsets[n], 0, b->bytes - offsets[n], c->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(b->chars, data, offsets[n], cudaMemcpyHostToDevice, c->stream);
+    } else {
+        e = cudaMemsetAsync(b->chars, 0, b->bytes, c->stream);
+        for (uint32_t i = 0; i < n && e == cudaSuccess; ++i)
+            if (lens[i])
+                e = cudaMemcpyAsync(b->chars + b->h_coff[i], data + offsets[i], lens[i], cudaMemcpyHostToDevice,
+                                    c->stream);
+    }
+    if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
+    c->stats.h2d_bytes += b->bases;
+    *out = b;
+    return sync(c);
+}
+
+int mk_batch_synth(mk_ctx* c, uint64_t seed, uint32_t first_g, uint32_t n, uint64_t len, mk_batch** out) {
+    if (!c || !out) return fail(c, MK_ERR_ARG, "mk_batch_synth: NULL argument");
+    Guard g(c);
+    std::vector<uint64_t> lens(n, len);
+    mk_batch* b = new mk_batch();
+    batch_layout(b, lens.data(), n);
+    int r = batch_alloc(c, b);
+    if (r != MK_OK) { batch_release(b); return r; }
+    cudaMemsetAsync(b->chars + b->h_coff[n], 0, b->bytes - b->h_coff[n], c->stream);
+    launch_synth(b->chars, b->d_coff, seed, first_g, n, len, c->stream);
+    c->stats.kernel_launches += 1;
+    *out = b;
+    return sync(c);
+}
+
+int mk_batch_download(mk_ctx* c, const mk_batch* b, uint32_t i, char* dst, uint64_t cap) {
+    if (!c || !b || !dst || i >= b->n) return fail(c, MK_ERR_ARG, "mk_batch_download: bad argument");
+    Guard g(c);
+    const uint64_t m = std::min<uint64_t>(cap, b->h_len[i]);
+    CU(cudaMemcpyAsync(dst, b->chars + b->h_coff[i], m, cudaMemcpyDeviceToHost, c->stream));
+    return sync(c);
+}
+
+uint32_t mk_batch_size(const mk_batch* b) { return b ? b->n : 0; }
+uint64_t mk_batch_bases(const mk_batch* b) { return b ? b->bases : 0; }
+
+void mk_batch_free(mk_ctx* c, mk_batch* b) {
+    if (!b) return;
+    if (c) {
+        Guard g(c);
+        cudaStreamSynchronize(c->stream);
+        batch_release(b);
+    } else {
+        batch_release(b);
+    }
+}
+
+// ---- build ---------------------------------------------------------------------------
+
+int mk_index_reserve(mk_ctx* c, uint32_t n_genomes) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    return ensure_capacity(c, n_genomes);
+}
+
+int mk_index_add_batch(mk_ctx* c, const mk_batch* genomes) {
+    if (!c || !genomes) return fail(c, MK_ERR_ARG, "mk_index_add_batch: NULL argument");
+    Guard g(c);
+    return index_add_view(c, genomes);
+}
+
+int mk_index_add(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n) {
+    if (!c || (n && (!seqs || !lens))) return fail(c, MK_ERR_ARG, "mk_index_add: NULL argument");
+    Guard g(c);
+    for (uint32_t i = 0; i < n; ++i)
+        if (lens[i] < c->k) return fail(c, MK_ERR_ARG, "mk_index_add: sequence shorter than k");
+    // upload in slices of bounded size so that staging memory stays small
+    const uint64_t slice_bytes = 1ull << 30;
+    uint32_t first = 0;
+    while (first < n) {
+        uint64_t bytes = 0;
+        uint32_t m = 0;
+        while (first + m < n && (m == 0 || bytes + lens[first + m] <= slice_bytes) && m < 1024) {
+            bytes += lens[first + m];
+            ++m;
+        }
+        mk_batch* b = nullptr;
+        TRY(upload_range(c, seqs + first, lens + first, m, &b));
+        int r = index_add_view(c, b);
+        cudaStreamSynchronize(c->stream);
+        batch_release(b);
+        if (r != MK_OK) return r;
+        first += m;
+    }
+    return MK_OK;
+}
+
+int mk_index_size(const mk_ctx* c, uint32_t* n_genomes) {
+    if (!c || !n_genomes) return MK_ERR_ARG;
+    *n_genomes = c->n;
+    return MK_OK;
+}
+
+int mk_index_stats(mk_ctx* c, uint32_t first, uint32_t n, uint32_t* sketch_size, uint64_t* genome_size) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    if ((uint64_t)first + n > c->n) return fail(c, MK_ERR_ARG, "mk_index_stats: range exceeds the index");
+    if (sketch_size) memcpy(sketch_size, c->h_sketch_size.data() + first, (size_t)n * 4);
+    if (genome_size) memcpy(genome_size, c->h_genome_size.data() + first, (size_t)n * 8);
+    return MK_OK;
+}
+
+int mk_index_export(mk_ctx* c, uint8_t* rows, uint64_t* genome_size, uint8_t* bloom, uint64_t bloom_bytes,
+                    uint32_t* sketch_size) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    if (rows && c->n) {
+        CU(cudaMemcpy2DAsync(rows, c->n, c->rows, c->stride, c->n, c->B, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += c->B * c->n;
+    }
+    if (bloom) {
+        const uint64_t m = std::min<uint64_t>(bloom_bytes, c->window);
+        CU(cudaMemcpyAsync(bloom, c->bloom, m, cudaMemcpyDeviceToHost, c->stream));
+        if (bloom_bytes > m) memset(bloom + m, 0, bloom_bytes - m);   // never touched for this k
+        c->stats.d2h_bytes += m;
+    }
+    if (genome_size) memcpy(genome_size, c->h_genome_size.data(), (size_t)c->n * 8);
+    if (sketch_size) memcpy(sketch_size, c->h_sketch_size.data(), (size_t)c->n * 4);
+    return sync(c);
+}
+
+int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_stride, const uint64_t* genome_size,
+                    const uint8_t* bloom, uint64_t bloom_bytes, const uint32_t* sketch_size) {
+    if (!c || (n && (!rows || !genome_size || !sketch_size)))
+        return fail(c, MK_ERR_ARG, "mk_index_import: NULL argument");
+    Guard g(c);
+    if (n && rows_stride < n) return fail(c, MK_ERR_ARG, "mk_index_import: rows_stride < n");
+    c->n = 0;
+    c->h_sketch_size.clear();
+    c->h_genome_size.clear();
+    TRY(ensure_capacity(c, std::max<uint32_t>(n, 1)));
+    CU(cudaMemsetAsync(c->rows, 0xFF, c->B * c->stride, c->stream));
+    if (n) {
+        CU(cudaMemcpy2DAsync(c->rows, c->stride, rows, rows_stride, n, c->B, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_sketch_size, sketch_size, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_genome_size, genome_size, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += c->B * n + (size_t)n * 12;
+    }
+    CU(cudaMemsetAsync(c->bloom, 0, c->window, c->stream));
+    if (bloom && bloom_bytes) {
+        const uint64_t m = std::min<uint64_t>(bloom_bytes, c->window);
+        CU(cudaMemcpyAsync(c->bloom, bloom, m, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += m;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->h_sketch_size.assign(sketch_size, sketch_size + n);
+    c->h_genome_size.assign(genome_size, genome_size + n);
+    c->n = n;
+    return MK_OK;
+}
+
+uint64_t mk_bloom_window(const mk_ctx* c) { return c ? c->window : 0; }
+
+int mk_bloom_get(mk_ctx* c, uint8_t* dst, uint64_t n) {
+    if (!c || !dst) return MK_ERR_ARG;
+    Guard g(c);
+    if (n > c->window) return fail(c, MK_ERR_ARG, "mk_bloom_get: n exceeds the window");
+    CU(cudaMemcpyAsync(dst, c->bloom, n, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += n;
+    return sync(c);
+}
+
+int mk_bloom_merge(mk_ctx* c, const uint8_t* src, uint64_t n) {
+    if (!c || !src) return MK_ERR_ARG;
+    Guard g(c);
+    if (n > c->window || n % 16) return fail(c, MK_ERR_ARG, "mk_bloom_merge: n must be a multiple of 16 within the window");
+    TRY(reserve(c, c->misc, n));
+    CU(cudaMemcpyAsync(c->misc.p, src, n, cudaMemcpyHostToDevice, c->stream));
+    launch_bloom_merge(c->bloom, static_cast<uint8_t*>(c->misc.p), n, c->stream);
+    c->stats.kernel_launches += 1;
+    c->stats.h2d_bytes += n;
+    return sync(c);
+}
+
+// ---- query ---------------------------------------------------------------------------
+
+int mk_query_batch(mk_ctx* c, const mk_batch* reads, uint32_t nresults, uint32_t min_score,
+                   double min_intersection, mk_hit* hits, uint32_t* nhits) {
+    if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_query_batch: NULL argument");
+    Guard g(c);
+    return query_device(c, reads, nresults, min_score, min_intersection, hits, nhits, false, 1);
+}
+
+int mk_query(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, uint32_t nresults,
+             uint32_t min_score, double min_intersection, mk_hit* hits, uint32_t* nhits) {
+    if (!c || (n && (!seqs || !lens || !hits || !nhits))) return fail(c, MK_ERR_ARG, "mk_query: NULL argument");
+    Guard g(c);
+    mk_batch* b = nullptr;
+    TRY(upload_range(c, seqs, lens, n, &b));
+    int r = query_device(c, b, nresults, min_score, min_intersection, hits, nhits, false, 1);
+    cudaStreamSynchronize(c->stream);
+    batch_release(b);
+    return r;
+}
+
+int mk_query_chain(mk_ctx* c, const mk_batch* reads, uint32_t nresults, uint32_t min_score,
+                   double min_intersection, mk_hit* heap_io, uint32_t* len_io, int finalize) {
+    if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_query_chain: NULL argument");
+    Guard g(c);
+    return query_device(c, reads, nresults, min_score, min_intersection, heap_io, len_io, true, finalize);
+}
+
+int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, uint32_t* counts,
+                    uint32_t* surviving) {
+    if (!c || (n && (!seqs || !lens || !counts))) return fail(c, MK_ERR_ARG, "mk_query_counts: NULL argument");
+    Guard g(c);
+    if (n == 0) return MK_OK;
+    mk_batch* b = nullptr;
+    TRY(upload_range(c, seqs, lens, n, &b));
+    auto body = [&]() -> int {
+        Lists L{};
+        TRY(build_lists(c, b, &L));
+        if (c->n) {
+            ScanPlan plan{};
+            if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
+                return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
+            const uint32_t qb = scan_batch_reads(c, n);
+            const uint64_t n_pad = (c->n + 15) / 16 * 16;
+            TRY(reserve(c, c->counts, (size_t)qb * n_pad * 4));
+            for (uint32_t q0 = 0; q0 < n; q0 += qb) {
+                const uint32_t nq = std::min(qb, n - q0);
+                TRY(scan_reads(c, L, q0, nq, plan));
+                CU(cudaMemcpy2DAsync(counts + (size_t)q0 * c->n, (size_t)c->n * 4, c->counts.p, n_pad * 4,
+                                     (size_t)c->n * 4, nq, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                c->stats.d2h_bytes += (size_t)nq * c->n * 4;
+            }
+        }
+        TRY(account_lists(c, L, n, surviving));
+        return sync(c);
+    };
+    int r = body();
+    cudaStreamSynchronize(c->stream);
+    batch_release(b);
+    return r;
+}
+
+int mk_sketch(mk_ctx* c, const char* seq, uint64_t len, uint8_t* fp, uint64_t* anc, uint32_t* active) {
+    if (!c || (len && !seq)) return fail(c, MK_ERR_ARG, "mk_sketch: NULL argument");
+    Guard g(c);
+    mk_batch* b = nullptr;
+    const char* seqs[1] = {seq};
+    TRY(upload_range(c, seqs, &len, 1, &b));
+    auto body = [&]() -> int {
+        BatchView v = view_of(b, 0, 1);
+        DenseOut d{};
+        {
+            PhaseTimer t(c, PH_SKETCH);
+            TRY(dense_sketch(c, v, false, &d));
+        }
+        if (fp) CU(cudaMemcpyAsync(fp, c->fp.p, c->B, cudaMemcpyDeviceToHost, c->stream));
+        if (anc) CU(cudaMemcpyAsync(anc, c->keys.p, c->B * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (active) CU(cudaMemcpyAsync(active, d.d_active, 4, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += c->B * 9 + 4;
+        return sync(c);
+    };
+    int r = body();
+    cudaStreamSynchronize(c->stream);
+    batch_release(b);
+    return r;
+}
+
+// ---- exact mode ----------------------------------------------------------------------
+
+int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, uint32_t n_records,
+             const char* const* reads, const uint64_t* read_lens, uint32_t n_reads, uint64_t* nb_inter,
+             uint64_t* nb_union, uint64_t* genome_distinct) {
+    if (!c || (n_records && (!records || !rec_lens)) || (n_reads && (!reads || !read_lens || !nb_inter || !nb_union)))
+        return fail(c, MK_ERR_ARG, "mk_exact: NULL argument");
+    Guard g(c);
+    mk_batch *gb = nullptr, *rb = nullptr;
+    unsigned long long *tableB = nullptr, *rtable = nullptr, *d_cnt = nullptr;
+    uint64_t* d_toff = nullptr;
+    auto body = [&]() -> int {
+        TRY(upload_range(c, records, rec_lens, n_records, &gb));
+        TRY(upload_range(c, reads, read_lens, n_reads, &rb));
+        const uint32_t k = c->k;
+        uint64_t wins = 0;
+        for (uint32_t i = 0; i < n_records; ++i)
+            if (rec_lens[i] >= k) wins += rec_lens[i] - k + 1;
+        const uint64_t slotsB = std::max<uint64_t>(16, wins * 2);
+        std::vector<uint64_t> toff((size_t)n_reads + 1);
+        uint64_t tt = 0;
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            toff[i] = tt;
+            tt += read_lens[i] >= k ? std::max<uint64_t>(4, (read_lens[i] - k + 1) * 2) : 1;
+        }
+        toff[n_reads] = tt;
+        CU(cudaMalloc(&tableB, slotsB * 8));
+        CU(cudaMalloc(&rtable, std::max<uint64_t>(1, tt) * 8));
+        CU(cudaMalloc(&d_cnt, (1 + 2 * (size_t)n_reads) * 8));
+        CU(cudaMalloc(&d_toff, ((size_t)n_reads + 1) * 8));
+        PhaseTimer t(c, PH_EXACT);
+        launch_fill_u64(tableB, slotsB, ~0ull, c->stream);
+        launch_fill_u64(rtable, tt, ~0ull, c->stream);
+        CU(cudaMemsetAsync(d_cnt, 0, (1 + 2 * (size_t)n_reads) * 8, c->stream));
+        CU(cudaMemcpyAsync(d_toff, toff.data(), ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        c->stats.kernel_launches += 2;
+        const uint32_t YMAX = 32768;
+        for (uint32_t f = 0; f < n_records; f += YMAX) {
+            const uint32_t m = std::min(YMAX, n_records - f);
+            BatchView v = view_of(gb, f, m);
+            launch_exact_insert(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, tableB, slotsB, d_cnt, c->stream);
+            c->stats.kernel_launches += 1;
+        }
+        unsigned long long* d_inter = d_cnt + 1;
+        unsigned long long* d_dist = d_cnt + 1 + n_reads;
+        for (uint32_t f = 0; f < n_reads; f += YMAX) {
+            const uint32_t m = std::min(YMAX, n_reads - f);
+            BatchView v = view_of(rb, f, m);
+            launch_exact_reads(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, rtable, d_toff + f, tableB, slotsB,
+                               d_inter + f, d_dist + f, c->stream);
+            c->stats.kernel_launches += 1;
+        }
+        CU(cudaGetLastError());
+        std::vector<unsigned long long> cnt(1 + 2 * (size_t)n_reads);
+        CU(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += cnt.size() * 8;
+        if (genome_distinct) *genome_distinct = cnt[0];
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            nb_inter[i] = cnt[1 + i];
+            nb_union[i] = cnt[0] + (cnt[1 + n_reads + i] - cnt[1 + i]);   // |B| + |A \ B|
+        }
+        return MK_OK;
+    };
+    int r = body();
+    cudaStreamSynchronize(c->stream);
+    resolve_events(c);
+    if (tableB) cudaFree(tableB);
+    if (rtable) cudaFree(rtable);
+    if (d_cnt) cudaFree(d_cnt);
+    if (d_toff) cudaFree(d_toff);
+    batch_release(gb);
+    batch_release(rb);
+    return r;
+}
+
+// ---- measurement ---------------------------------------------------------------------
+
+int mk_stats_get(mk_ctx* c, mk_stats* out) {
+    if (!c || !out) return MK_ERR_ARG;
+    Guard g(c);
+    TRY(sync(c));
+    *out = c->stats;
+    return MK_OK;
+}
+
+int mk_stats_reset(mk_ctx* c) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    TRY(sync(c));
+    c->stats = mk_stats{};
+    return MK_OK;
+}
+
+int mk_sync(mk_ctx* c) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    return sync(c);
+}
+
+}  // extern "C"

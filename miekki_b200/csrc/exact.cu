@@ -1,0 +1,163 @@
+// exact.cu -- exact mode (-e): true k-mer intersection of candidate hits, sm_100a.
+//
+// Replaces Miekki::ground_truth_batch (Miekki.cpp:792-859): set B = distinct canonical
+// k-mers of the genome's records, and per read A = its distinct canonical k-mers,
+// nb_inter = |A n B|, nb_union = |B| + |A \ B|.  Canonical k-mer = str2num
+// (utils.cpp:276-278): min(str2numstrand(w), str2numstrand(revComp(w))), case-insensitive,
+// and 0 for any window holding a byte outside ACGTacgt (str2numstrand returns 0, revComp
+// maps the byte to 'T', so the minimum is 0).  Every window 0 .. len-k is included
+// (unlike the sketch loop, quirk G1).
+//
+// The reference uses std::unordered_set; here both sets are exact open-addressing hash
+// sets of 64-bit keys in HBM/L2 (insert-if-absent with atomicCAS, empty = ~0, which is not
+// a k-mer for k <= 31).  |B| is the number of successful inserts.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mk {
+
+namespace {
+
+constexpr unsigned long long EMPTY = ~0ull;
+constexpr int RUN = 64;      // windows per thread in the genome kernel
+
+// digit (0..3) of str2numstrand, 4 for a byte it rejects (utils.cpp:252-272)
+__device__ __forceinline__ uint32_t ci_code(uint32_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+    }
+    return 4;
+}
+
+// insert-if-absent; true when the key was new
+__device__ __forceinline__ bool set_insert(unsigned long long* table, uint64_t slots, uint64_t v) {
+    uint64_t i = __umul64hi(revhash64(v ^ 0x5851F42D4C957F2Dull), slots);
+    for (;;) {
+        unsigned long long cur = table[i];
+        if (cur == v) return false;
+        if (cur == EMPTY) {
+            cur = atomicCAS(table + i, EMPTY, (unsigned long long)v);
+            if (cur == EMPTY) return true;
+            if (cur == v) return false;
+        }
+        if (++i == slots) i = 0;
+    }
+}
+__device__ __forceinline__ bool set_contains(const unsigned long long* __restrict__ table,
+                                             uint64_t slots, uint64_t v) {
+    uint64_t i = __umul64hi(revhash64(v ^ 0x5851F42D4C957F2Dull), slots);
+    for (;;) {
+        const unsigned long long cur = table[i];
+        if (cur == v) return true;
+        if (cur == EMPTY) return false;
+        if (++i == slots) i = 0;
+    }
+}
+
+// genome records -> set B.  One thread rolls over RUN consecutive windows.
+__global__ void __launch_bounds__(256)
+exact_insert_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
+                    const uint64_t* __restrict__ len, int k, unsigned long long* __restrict__ table,
+                    uint64_t slots, unsigned long long* __restrict__ distinct) {
+    const uint32_t s = blockIdx.y;
+    const uint64_t n = len[s];
+    uint32_t fresh = 0;
+    if (n >= (uint64_t)k) {
+        const uint64_t nwin = n - k + 1;                       // Miekki.cpp:807
+        const uint8_t* seq = chars + coff[s];
+        const uint64_t kmask = (1ull << (2 * k)) - 1;
+        for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * RUN; i0 < nwin;
+             i0 += (uint64_t)gridDim.x * blockDim.x * RUN) {
+            const uint64_t iend = (i0 + RUN < nwin) ? i0 + RUN : nwin;
+            uint64_t fwd = 0, rc = 0;
+            int64_t last_bad = -1;
+            for (uint64_t t = i0; t < iend + k - 1; ++t) {
+                uint32_t c = ci_code(seq[t]);
+                if (c > 3) { last_bad = (int64_t)t; c = 0; }
+                fwd = ((fwd << 2) | c) & kmask;
+                rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * k - 2));
+                if (t + 1 >= i0 + k) {
+                    const uint64_t i = t + 1 - k;
+                    const uint64_t v = (last_bad >= (int64_t)i) ? 0ull : (fwd < rc ? fwd : rc);
+                    fresh += set_insert(table, slots, v) ? 1u : 0u;
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(distinct, (unsigned long long)fresh);
+}
+
+// reads: thread per window; per-read set A lives in rtable[toff[r] .. toff[r] + tslots[r])
+__global__ void __launch_bounds__(256)
+exact_reads_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
+                   const uint64_t* __restrict__ len, int k, unsigned long long* __restrict__ rtable,
+                   const uint64_t* __restrict__ toff, const unsigned long long* __restrict__ tableB,
+                   uint64_t slotsB, unsigned long long* __restrict__ inter,
+                   unsigned long long* __restrict__ distinctA) {
+    const uint32_t r = blockIdx.y;
+    const uint64_t n = len[r];
+    uint32_t n_new = 0, n_in = 0;
+    if (n >= (uint64_t)k) {
+        const uint64_t nwin = n - k + 1;                       // Miekki.cpp:832
+        const uint8_t* seq = chars + coff[r];
+        unsigned long long* setA = rtable + toff[r];
+        const uint64_t slotsA = toff[r + 1] - toff[r];
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwin;
+             i += (uint64_t)gridDim.x * blockDim.x) {
+            uint64_t fwd = 0, rc = 0;
+            bool bad = false;
+            for (int t = 0; t < k; ++t) {
+                uint32_t c = ci_code(seq[i + t]);
+                if (c > 3) { bad = true; c = 0; }
+                fwd = (fwd << 2) | c;
+                rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * k - 2));
+            }
+            const uint64_t v = bad ? 0ull : (fwd < rc ? fwd : rc);
+            if (set_insert(setA, slotsA, v)) {                 // :834 first time in A
+                ++n_new;
+                if (set_contains(tableB, slotsB, v)) ++n_in;   // :835
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
+        n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_new) atomicAdd(distinctA + r, (unsigned long long)n_new);
+        if (n_in) atomicAdd(inter + r, (unsigned long long)n_in);
+    }
+}
+
+}  // namespace
+
+void launch_exact_insert(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                         uint32_t n_seq, uint64_t max_len, int k, unsigned long long* table,
+                         uint64_t slots, unsigned long long* distinct, cudaStream_t st) {
+    if (!n_seq || max_len < (uint64_t)k) return;
+    const uint64_t threads = (max_len - k + 1 + RUN - 1) / RUN;
+    uint64_t bx = (threads + 255) / 256;
+    if (bx > 148 * 16) bx = 148 * 16;
+    dim3 grid((unsigned)bx, n_seq);
+    exact_insert_kernel<<<grid, 256, 0, st>>>(chars, coff, len, k, table, slots, distinct);
+}
+
+void launch_exact_reads(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                        uint32_t n_reads, uint64_t max_len, int k, unsigned long long* rtable,
+                        const uint64_t* toff, const unsigned long long* tableB, uint64_t slotsB,
+                        unsigned long long* inter, unsigned long long* distinctA, cudaStream_t st) {
+    if (!n_reads || max_len < (uint64_t)k) return;
+    uint64_t bx = (max_len - k + 1 + 255) / 256;
+    if (bx > 148 * 4) bx = 148 * 4;
+    dim3 grid((unsigned)bx, n_reads);
+    exact_reads_kernel<<<grid, 256, 0, st>>>(chars, coff, len, k, rtable, toff, tableB, slotsB, inter,
+                                             distinctA);
+}
+
+}  // namespace mk

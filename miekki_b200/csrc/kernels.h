@@ -1,0 +1,91 @@
+// kernels.h -- host-side launchers of the sm_100a kernels (one .cu per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mk {
+
+struct SketchParams {
+    int k, h;
+    uint32_t bloom_log2;
+    uint64_t bloom_window;      // bytes of the Bloom table kept on the device
+};
+
+// ---- sketch.cu ------------------------------------------------------------------
+// Dense path (genomes, long reads): sequences -> 2-bit planes -> per-bucket min key.
+//   chars     : concatenated ASCII, sequence s at chars + coff[s] (16-byte aligned)
+//   woff[s]   : first plane word of sequence s (each sequence owns ceil(len/16)+2 words)
+//   keys      : n_seq x 2^h u64, pre-set to ~0; afterwards fp << 56 | first position
+void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                          const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k,
+                          uint32_t* planeF, uint32_t* planeR, cudaStream_t st);
+void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const uint64_t* len,
+                         const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k, int h,
+                         unsigned long long* keys, cudaStream_t st);
+// keys -> fp[s][b] (u8) and anc written over keys[s][b]; per-sequence active count and
+// S = sum 2^(31 - (fp >> 3)).  If owner != nullptr, also registers Bloom candidates
+// (pass A of the order-exact insert) with key (seq_in_batch, bucket, probe).
+void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const uint32_t* planeR,
+                    const uint64_t* woff, uint32_t n_seq, SketchParams p, uint8_t* fp,
+                    uint32_t* active, unsigned long long* ssum, const uint8_t* bloom,
+                    uint32_t* owner, cudaStream_t st);
+// pass B: the smallest (genome, bucket, probe) key of every still-zero Bloom byte writes it.
+void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
+                         SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st);
+// fp[s][b] -> rows[b * stride + col0 + s]
+void launch_scatter_rows(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
+                         uint32_t col0, cudaStream_t st);
+// dense read sketch -> (bucket << 8 | fp) list of buckets that are non-empty and pass Bloom
+void launch_compact_list(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
+                         SketchParams p, const uint8_t* bloom, const uint32_t* read_ids,
+                         const uint64_t* list_off, uint32_t* list, uint32_t* list_len,
+                         cudaStream_t st);
+// Sparse path (reads with at most max_kmers k-mers): one CTA per read, smem hash table.
+//   read_ids  : indices (into coff/len/list_off/list_len) of the reads to process
+size_t sketch_reads_smem(uint64_t max_len, int k, uint32_t* slots_out);
+int launch_sketch_reads(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                        const uint32_t* read_ids, uint32_t n_ids, uint64_t max_len, SketchParams p,
+                        const uint8_t* bloom, const uint64_t* list_off, uint32_t* list,
+                        uint32_t* list_len, cudaStream_t st);
+void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);
+void launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st);
+void launch_synth(uint8_t* chars, const uint64_t* coff, uint64_t seed, uint32_t first_g,
+                  uint32_t n, uint64_t len, cudaStream_t st);
+void launch_bloom_merge(uint8_t* dst, const uint8_t* src, uint64_t n, cudaStream_t st);
+
+// ---- scan.cu --------------------------------------------------------------------
+struct ScanPlan {
+    int threads;        // consumer threads (multiple of 32)
+    int J;              // 16-byte column groups per thread
+    uint32_t tile_w;    // genomes per tile (multiple of 16, <= 16 * threads * J)
+    uint32_t n_tiles;   // genome tiles per row
+    int stages;         // smem ring depth
+    size_t smem;
+    int grid;
+};
+int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out);
+// counts[q * n_genomes + g] = #{entries e of read q : rows[bucket(e)][g] == fp(e)}
+int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes,
+                const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len,
+                uint32_t n_reads, uint32_t* counts, uint32_t* work_counter, cudaStream_t st);
+
+// ---- topk.cu --------------------------------------------------------------------
+struct HitDev { uint32_t genome, matches; double jaccard, intersection; };
+// heap: n_reads x nresults HitDev, len: n_reads.  chained across shards (first_id offsets).
+void launch_topk(const uint32_t* counts, uint32_t n_reads, uint32_t n_genomes, uint32_t first_id,
+                 const uint32_t* sketch_size, const uint64_t* genome_size, uint32_t nresults,
+                 uint32_t min_score, double min_intersection, HitDev* heap, uint32_t* len,
+                 int finalize, cudaStream_t st);
+
+// ---- exact.cu -------------------------------------------------------------------
+// open-addressing exact sets of canonical k-mers (utils.cpp:276 str2num); tables pre-set to ~0
+void launch_exact_insert(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                         uint32_t n_seq, uint64_t max_len, int k, unsigned long long* table,
+                         uint64_t slots, unsigned long long* distinct, cudaStream_t st);
+// per read r: set A in rtable[toff[r] .. toff[r+1]); inter[r] += |A n B|, distinctA[r] += |A|
+void launch_exact_reads(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                        uint32_t n_reads, uint64_t max_len, int k, unsigned long long* rtable,
+                        const uint64_t* toff, const unsigned long long* tableB, uint64_t slotsB,
+                        unsigned long long* inter, unsigned long long* distinctA, cudaStream_t st);
+
+}  // namespace mk

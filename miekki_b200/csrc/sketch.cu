@@ -1,0 +1,525 @@
+// sketch.cu -- partitioned min-hash sketch kernels (genomes and reads), sm_100a.
+//
+// Replaces Miekki::minhash_sketch_partition (Miekki.cpp:150-197), the per-genome part of
+// insert_sequences (Miekki.cpp:287-311) and the Bloom filter (Miekki.cpp:121-146).
+//
+// Reference semantics reproduced here:
+//   * n - k k-mers per sequence (loop "i + k < n", Miekki.cpp:162);
+//   * per bucket the minimum fingerprint, and as `anc` the hash of the FIRST k-mer that
+//     attains it (strict "<", Miekki.cpp:172): a 64-bit atomicMin on (fp << 56 | position);
+//   * a fingerprint of 255 never registers (Miekki.cpp:172 with res[] preset to 255);
+//   * Bloom bytes: the byte value belongs to the smallest (genome, bucket, probe) that maps
+//     to it (order-independent restatement of Miekki.cpp:295-299).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mk {
+
+// ---- character codes -------------------------------------------------------------
+// bits 0-1 nuc2int (utils.cpp:31-49), bits 2-3 nuc2intrc (utils.cpp:107-125),
+// bits 4-5 str2numstrand digit (utils.cpp:252-272), bit 6 "valid for str2numstrand".
+__device__ __forceinline__ uint32_t char_code(uint32_t c) {
+    uint32_t f = c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u;
+    uint32_t r = c == 'A' ? 3u : c == 'C' ? 2u : c == 'G' ? 1u : 0u;
+    uint32_t u = c & 0xDFu;  // fold case for the four letters only
+    bool letter = (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z');
+    uint32_t pc = 0, pv = 0;
+    if (letter && (u == 'A' || u == 'C' || u == 'G' || u == 'T')) {
+        pv = 1;
+        pc = u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 0u;
+    }
+    return f | (r << 2) | (pc << 4) | (pv << 6);
+}
+
+__device__ __forceinline__ void fill_lut(uint8_t* lut) {
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) lut[c] = (uint8_t)char_code((uint32_t)c);
+}
+
+// all of the first min(k-1, n) characters valid for str2numstrand?  (else the prefix is 0)
+__device__ __forceinline__ bool prefix_valid(const uint8_t* __restrict__ s, uint64_t n, int k,
+                                             const uint8_t* lut) {
+    const int m = (uint64_t)(k - 1) < n ? (k - 1) : (int)n;
+    bool ok = true;
+    for (int i = 0; i < m; ++i) ok = ok && ((lut[s[i]] >> 6) & 1u);
+    return ok;
+}
+
+// encode characters [16w, 16w+16) of a sequence into one F word and one R word
+__device__ __forceinline__ void encode_word(const uint8_t* __restrict__ s, uint64_t n, uint64_t w,
+                                            int k, bool pvalid, const uint8_t* lut, uint32_t& F,
+                                            uint32_t& R) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(s + 16 * w);  // start is 16-byte aligned
+    const uint32_t q[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t f = 0, r = 0;
+    #pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint64_t pos = 16 * w + i;
+        const uint32_t c = (q[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        const uint32_t code = lut[c];
+        uint32_t fd, rd;
+        if (pos < (uint64_t)(k - 1)) {           // prefix digits: str2numstrand, then rcb
+            fd = pvalid ? ((code >> 4) & 3u) : 0u;
+            rd = 3u - fd;
+        } else {
+            fd = code & 3u;
+            rd = (code >> 2) & 3u;
+        }
+        if (pos >= n) { fd = 0; rd = 0; }
+        f |= fd << (30 - 2 * i);
+        r |= rd << (2 * i);
+    }
+    F = f;
+    R = r;
+}
+
+// ---- dense path ------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+encode_planes_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
+                     const uint64_t* __restrict__ len, const uint64_t* __restrict__ woff, int k,
+                     uint32_t* __restrict__ planeF, uint32_t* __restrict__ planeR) {
+    __shared__ uint8_t lut[256];
+    fill_lut(lut);
+    __syncthreads();
+    const uint32_t s = blockIdx.y;
+    const uint64_t n = len[s];
+    const uint64_t nw = (n + 15) / 16 + 2;       // two zero words of padding
+    const uint8_t* seq = chars + coff[s];
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t F = 0, R = 0;
+        if (16 * w < n) {
+            const bool pv = (16 * w < (uint64_t)(k - 1)) ? prefix_valid(seq, n, k, lut) : true;
+            encode_word(seq, n, w, k, pv, lut, F, R);
+        }
+        planeF[woff[s] + w] = F;
+        planeR[woff[s] + w] = R;
+    }
+}
+
+// one thread = 16 consecutive k-mer start positions (one plane word + two neighbours)
+__global__ void __launch_bounds__(256)
+sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restrict__ planeR,
+                    const uint64_t* __restrict__ len, const uint64_t* __restrict__ woff, int k, int h,
+                    unsigned long long* __restrict__ keys) {
+    const uint32_t s = blockIdx.y;
+    const uint64_t n = len[s];
+    if (n <= (uint64_t)k) return;
+    const uint64_t nk = n - k;                    // quirk G1: the last k-mer is not visited
+    const uint64_t nwk = (nk + 15) / 16;
+    const uint64_t kmask = (1ull << (2 * k)) - 1;
+    const uint64_t pmask = (1ull << (64 - h)) - 1;
+    const uint32_t* F = planeF + woff[s];
+    const uint32_t* R = planeR + woff[s];
+    unsigned long long* kz = keys + ((uint64_t)s << h);
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwk;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t f0 = F[w], f1 = F[w + 1], f2 = F[w + 2];
+        const uint32_t r0 = R[w], r1 = R[w + 1], r2 = R[w + 2];
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint64_t pos = 16 * w + j;
+            if (pos < nk) {
+                const uint64_t x = kmer_hash(f0, f1, f2, r0, r1, r2, j, k, kmask);
+                const uint32_t fp = mantis(x & pmask, h);
+                if (fp != EMPTY_FP)
+                    atomicMin(kz + (x >> (64 - h)), ((unsigned long long)fp << POS_BITS) | pos);
+            }
+        }
+    }
+}
+
+// hash of the k-mer starting at `pos`, from the planes in global memory
+__device__ __forceinline__ uint64_t hash_at(const uint32_t* __restrict__ F,
+                                            const uint32_t* __restrict__ R, uint64_t pos, int k) {
+    const uint64_t w = pos >> 4;
+    const int j = (int)(pos & 15);
+    return kmer_hash(F[w], F[w + 1], F[w + 2], R[w], R[w + 1], R[w + 2], j, k,
+                     (1ull << (2 * k)) - 1);
+}
+
+// key = (seq_in_batch, bucket, probe) packed so that u32 order == lexicographic order
+__device__ __forceinline__ uint32_t owner_key(uint32_t s, uint32_t bucket, uint32_t i, int h) {
+    return (((s << h) | bucket) << 3) | i;
+}
+
+__global__ void __launch_bounds__(256)
+resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __restrict__ planeF,
+               const uint32_t* __restrict__ planeR, const uint64_t* __restrict__ woff, SketchParams p,
+               uint8_t* __restrict__ fp_out, uint32_t* __restrict__ active,
+               unsigned long long* __restrict__ ssum, const uint8_t* __restrict__ bloom,
+               uint32_t* __restrict__ owner) {
+    const uint32_t s = blockIdx.y;
+    const uint32_t B = 1u << p.h;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t act = 0;
+    unsigned long long sum = 0;
+    if (b < B) {
+        const uint64_t idx = ((uint64_t)s << p.h) + b;
+        const unsigned long long key = keys_anc[idx];
+        const uint32_t fp = (uint32_t)(key >> POS_BITS);
+        unsigned long long anc = EMPTY_ANC;
+        if (fp != EMPTY_FP) {
+            anc = hash_at(planeF + woff[s], planeR + woff[s], key & POS_MASK, p.k);
+            act = 1;
+            sum = 1ull << (31 - (fp >> 3));       // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
+            if (owner != nullptr) {               // Bloom pass A (Miekki.cpp:295-299)
+                BloomProbe pr(anc);
+                #pragma unroll
+                for (uint32_t i = 0; i < 5; ++i) {
+                    const uint64_t byte = pr.slot(i, p.bloom_log2) >> 3;
+                    if (byte < p.bloom_window && bloom[byte] == 0)
+                        atomicMin(owner + byte, owner_key(s, b, i, p.h));
+                }
+            }
+        }
+        keys_anc[idx] = anc;
+        fp_out[idx] = (uint8_t)fp;
+    }
+    // per-sequence statistics: warp reduce, one atomic per warp
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        act += __shfl_xor_sync(0xffffffffu, act, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && act) {
+        atomicAdd(active + s, act);
+        atomicAdd(ssum + s, sum);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint8_t* __restrict__ fp,
+                    SketchParams p, uint8_t* __restrict__ bloom, uint32_t* __restrict__ owner) {
+    const uint32_t s = blockIdx.y;
+    const uint32_t B = 1u << p.h;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint64_t idx = ((uint64_t)s << p.h) + b;
+    if (fp[idx] == EMPTY_FP) return;
+    BloomProbe pr(anc[idx]);
+    #pragma unroll
+    for (uint32_t i = 0; i < 5; ++i) {
+        const uint64_t slot = pr.slot(i, p.bloom_log2);
+        const uint64_t byte = slot >> 3;
+        if (byte < p.bloom_window && owner[byte] == owner_key(s, b, i, p.h)) {
+            bloom[byte] = (uint8_t)(1u << (slot & 7));   // Miekki.cpp:128
+            owner[byte] = 0xFFFFFFFFu;                   // the winner also clears its claim
+        }
+    }
+}
+
+// fp[s][b] -> rows[b][col0 + s] through a 32 x 32 shared-memory transpose, so that both the
+// reads (along b) and the writes (along the genome axis) are contiguous.
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const uint8_t* __restrict__ fp, uint32_t n_seq, int h, uint8_t* __restrict__ rows,
+                    uint64_t stride, uint32_t col0) {
+    __shared__ uint8_t tile[32][33];
+    const uint32_t B = 1u << h;
+    const uint32_t b0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (uint32_t r = ty; r < 32; r += 8) {
+        const uint32_t s = s0 + r, b = b0 + tx;
+        tile[r][tx] = (s < n_seq && b < B) ? fp[((uint64_t)s << h) + b] : (uint8_t)EMPTY_FP;
+    }
+    __syncthreads();
+    for (uint32_t r = ty; r < 32; r += 8) {
+        const uint32_t b = b0 + r, s = s0 + tx;
+        if (s < n_seq && b < B) rows[(uint64_t)b * stride + col0 + s] = tile[tx][r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+compact_list_kernel(const unsigned long long* __restrict__ anc, const uint8_t* __restrict__ fp,
+                    SketchParams p, const uint8_t* __restrict__ bloom,
+                    const uint32_t* __restrict__ read_ids, const uint64_t* __restrict__ list_off,
+                    uint32_t* __restrict__ list, uint32_t* __restrict__ list_len) {
+    const uint32_t s = blockIdx.y;
+    const uint32_t B = 1u << p.h;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    uint32_t f = EMPTY_FP;
+    if (b < B) {
+        const uint64_t idx = ((uint64_t)s << p.h) + b;
+        f = fp[idx];
+        // Miekki.cpp:216-219: a bucket whose anc fails check_bloom is masked to 255
+        keep = f != EMPTY_FP && bloom_check(bloom, p.bloom_window, p.bloom_log2, anc[idx]);
+    }
+    const uint32_t rid = read_ids[s];
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(list_len + rid, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[list_off[rid] + base + __popc(m & ((1u << lane) - 1))] = (b << 8) | f;
+}
+
+// ---- sparse path: one CTA per read ------------------------------------------------
+// shared memory: lut[256] | F words | R words | hash table (u64 slots) | counter
+//   slot = bucket << 40 | fp << 32 | position ; ~0 = empty.  Linear probing; a slot is claimed
+//   by its bucket with atomicCAS and then lowered with atomicMin, which orders (fp, position)
+//   because the bucket bits above them are equal.
+__global__ void __launch_bounds__(128)
+sketch_reads_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
+                    const uint64_t* __restrict__ len, const uint32_t* __restrict__ read_ids,
+                    uint32_t n_ids, uint32_t max_words, uint32_t slots, SketchParams p,
+                    const uint8_t* __restrict__ bloom, const uint64_t* __restrict__ list_off,
+                    uint32_t* __restrict__ list, uint32_t* __restrict__ list_len) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* lut = smem;
+    uint32_t* F = reinterpret_cast<uint32_t*>(smem + 256);
+    uint32_t* R = F + max_words;
+    unsigned long long* table =
+        reinterpret_cast<unsigned long long*>(smem + 256 + ((2ull * max_words * 4 + 15) & ~15ull));
+    __shared__ uint32_t cnt;
+    fill_lut(lut);
+    const int k = p.k, h = p.h;
+    const uint64_t kmask = (1ull << (2 * k)) - 1;
+    const uint64_t pmask = (1ull << (64 - h)) - 1;
+    const uint32_t smask = slots - 1;
+
+    for (uint32_t it = blockIdx.x; it < n_ids; it += gridDim.x) {
+        const uint32_t rid = read_ids[it];
+        const uint64_t n = len[rid];
+        const uint8_t* seq = chars + coff[rid];
+        __syncthreads();                          // lut ready / previous read finished
+        if (threadIdx.x == 0) cnt = 0;
+        const uint32_t nw = (uint32_t)((n + 15) / 16);
+        const uint32_t nk = n > (uint64_t)k ? (uint32_t)(n - k) : 0;
+        // table only as large as this read needs (power of two, load <= 0.75)
+        uint32_t my_slots = 64;
+        while ((uint64_t)my_slots * 3 < (uint64_t)nk * 4) my_slots <<= 1;
+        if (my_slots > slots) my_slots = slots;
+        const uint32_t my_mask = my_slots - 1;
+        (void)smask;
+        const bool pv = prefix_valid(seq, n, k, lut);
+        for (uint32_t w = threadIdx.x; w < nw + 2; w += blockDim.x) {
+            uint32_t f = 0, r = 0;
+            if (w < nw) encode_word(seq, n, w, k, pv, lut, f, r);
+            F[w] = f;
+            R[w] = r;
+        }
+        for (uint32_t i = threadIdx.x; i < my_slots; i += blockDim.x) table[i] = EMPTY_KEY;
+        __syncthreads();
+
+        for (uint32_t pos = threadIdx.x; pos < nk; pos += blockDim.x) {
+            const uint32_t w = pos >> 4;
+            const int j = (int)(pos & 15);
+            const uint64_t x = kmer_hash(F[w], F[w + 1], F[w + 2], R[w], R[w + 1], R[w + 2], j, k, kmask);
+            const uint32_t fp = mantis(x & pmask, h);
+            if (fp == EMPTY_FP) continue;
+            const uint32_t bucket = (uint32_t)(x >> (64 - h));
+            const unsigned long long key = ((unsigned long long)bucket << 40) |
+                                           ((unsigned long long)fp << 32) | pos;
+            uint32_t slot = (bucket * 0x9E3779B1u) >> 7 & my_mask;
+            for (;;) {
+                unsigned long long cur = table[slot];
+                if (cur == EMPTY_KEY) {
+                    cur = atomicCAS(table + slot, EMPTY_KEY, key);
+                    if (cur == EMPTY_KEY) break;
+                }
+                if ((uint32_t)(cur >> 40) == bucket) {
+                    atomicMin(table + slot, key);
+                    break;
+                }
+                slot = (slot + 1) & my_mask;
+            }
+        }
+        __syncthreads();
+
+        const uint64_t out0 = list_off[rid];
+        for (uint32_t i = threadIdx.x; i < my_slots; i += blockDim.x) {
+            const unsigned long long e = table[i];
+            if (e == EMPTY_KEY) continue;
+            const uint32_t pos = (uint32_t)e;
+            const uint32_t w = pos >> 4;
+            const int j = (int)(pos & 15);
+            const uint64_t x = kmer_hash(F[w], F[w + 1], F[w + 2], R[w], R[w + 1], R[w + 2], j, k, kmask);
+            if (!bloom_check(bloom, p.bloom_window, p.bloom_log2, x)) continue;   // Miekki.cpp:217
+            const uint32_t o = atomicAdd(&cnt, 1u);
+            list[out0 + o] = ((uint32_t)(e >> 40) << 8) | ((uint32_t)(e >> 32) & 0xFFu);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) list_len[rid] = cnt;
+    }
+}
+
+// ---- small utilities ---------------------------------------------------------------
+
+__global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+__global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// counter-based synthetic genomes (mirrors miekki_b200/synth.py:cb_bases)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+synth_kernel(uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff, uint64_t seed,
+             uint32_t first_g, uint64_t len) {
+    const uint32_t s = blockIdx.y;
+    const uint64_t base = seed + ((uint64_t)(first_g + s) << 40);
+    uint8_t* dst = chars + coff[s];
+    const uint64_t nq = (len + 15) / 16;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq;
+         q += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint64_t pos = 16 * q + i;
+            const uint32_t c = pos < len ? (uint32_t)("ACGT"[splitmix64(base + pos) >> 62]) : 0u;
+            w[i >> 2] |= c << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4*>(dst + 16 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// multi-GPU Bloom merge: a byte set by a lower rank wins
+__global__ void bloom_merge_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                   uint64_t n16) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 d = reinterpret_cast<uint4*>(dst)[i];
+        const uint4 s = reinterpret_cast<const uint4*>(src)[i];
+        uint32_t* dp = &d.x;
+        const uint32_t* sp = &s.x;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            // per byte: keep d where d != 0, else take s
+            uint32_t nz = dp[w] | (dp[w] >> 4);
+            nz |= nz >> 2;
+            nz |= nz >> 1;
+            nz &= 0x01010101u;                 // 1 per non-zero byte of d
+            const uint32_t keep = nz * 0xFFu;  // 0xFF per non-zero byte
+            dp[w] = (dp[w] & keep) | (sp[w] & ~keep);
+        }
+        reinterpret_cast<uint4*>(dst)[i] = d;
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------
+
+static inline unsigned blocks_for(uint64_t items, unsigned per_block, unsigned cap) {
+    uint64_t b = (items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (unsigned)(b > cap ? cap : b);
+}
+
+void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                          const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k,
+                          uint32_t* planeF, uint32_t* planeR, cudaStream_t st) {
+    if (!n_seq) return;
+    const uint64_t nw = (max_len + 15) / 16 + 2;
+    dim3 grid(blocks_for(nw, 256, 148 * 16), n_seq);
+    encode_planes_kernel<<<grid, 256, 0, st>>>(chars, coff, len, woff, k, planeF, planeR);
+}
+
+void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const uint64_t* len,
+                         const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k, int h,
+                         unsigned long long* keys, cudaStream_t st) {
+    if (!n_seq || max_len <= (uint64_t)k) return;
+    const uint64_t nwk = (max_len - k + 15) / 16;
+    dim3 grid(blocks_for(nwk, 256, 148 * 16), n_seq);
+    sketch_dense_kernel<<<grid, 256, 0, st>>>(planeF, planeR, len, woff, k, h, keys);
+}
+
+void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const uint32_t* planeR,
+                    const uint64_t* woff, uint32_t n_seq, SketchParams p, uint8_t* fp,
+                    uint32_t* active, unsigned long long* ssum, const uint8_t* bloom,
+                    uint32_t* owner, cudaStream_t st) {
+    if (!n_seq) return;
+    dim3 grid(((1u << p.h) + 255) / 256, n_seq);
+    resolve_kernel<<<grid, 256, 0, st>>>(keys_anc, planeF, planeR, woff, p, fp, active, ssum, bloom, owner);
+}
+
+void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
+                         SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st) {
+    if (!n_seq) return;
+    dim3 grid(((1u << p.h) + 255) / 256, n_seq);
+    bloom_commit_kernel<<<grid, 256, 0, st>>>(anc, fp, p, bloom, owner);
+}
+
+void launch_scatter_rows(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
+                         uint32_t col0, cudaStream_t st) {
+    if (!n_seq) return;
+    dim3 grid(((1u << h) + 31) / 32, (n_seq + 31) / 32);
+    scatter_rows_kernel<<<grid, 256, 0, st>>>(fp, n_seq, h, rows, stride, col0);
+}
+
+void launch_compact_list(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
+                         SketchParams p, const uint8_t* bloom, const uint32_t* read_ids,
+                         const uint64_t* list_off, uint32_t* list, uint32_t* list_len,
+                         cudaStream_t st) {
+    if (!n_seq) return;
+    dim3 grid(((1u << p.h) + 255) / 256, n_seq);
+    compact_list_kernel<<<grid, 256, 0, st>>>(anc, fp, p, bloom, read_ids, list_off, list, list_len);
+}
+
+// reads with more k-mers than this take the dense path
+static constexpr uint32_t SPARSE_MAX_SLOTS = 16384;
+
+size_t sketch_reads_smem(uint64_t max_len, int k, uint32_t* slots_out) {
+    const uint64_t nk = max_len > (uint64_t)k ? max_len - k : 0;
+    uint32_t slots = 64;
+    while ((uint64_t)slots * 3 < nk * 4 && slots < (1u << 30)) slots <<= 1;
+    if (slots_out) *slots_out = slots;
+    const uint64_t words = (max_len + 15) / 16 + 2;
+    return 256 + ((2 * words * 4 + 15) & ~15ull) + (size_t)slots * 8;
+}
+
+int launch_sketch_reads(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
+                        const uint32_t* read_ids, uint32_t n_ids, uint64_t max_len, SketchParams p,
+                        const uint8_t* bloom, const uint64_t* list_off, uint32_t* list,
+                        uint32_t* list_len, cudaStream_t st) {
+    if (!n_ids) return 0;
+    uint32_t slots = 0;
+    const size_t smem = sketch_reads_smem(max_len, p.k, &slots);
+    if (slots > SPARSE_MAX_SLOTS) return -1;     // caller routes such reads to the dense path
+    const uint32_t words = (uint32_t)((max_len + 15) / 16 + 2);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(sketch_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return -2;
+        configured = smem;
+    }
+    const unsigned grid = n_ids < 148u * 32u ? n_ids : 148u * 32u;
+    sketch_reads_kernel<<<grid, 128, smem, st>>>(chars, coff, len, read_ids, n_ids, words, slots, p,
+                                                 bloom, list_off, list, list_len);
+    return 0;
+}
+
+void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st) {
+    if (!n) return;
+    fill_u64_kernel<<<blocks_for(n, 256 * 8, 148 * 8), 256, 0, st>>>(p, n, v);
+}
+void launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st) {
+    if (!n) return;
+    fill_u32_kernel<<<blocks_for(n, 256 * 8, 148 * 8), 256, 0, st>>>(p, n, v);
+}
+
+void launch_synth(uint8_t* chars, const uint64_t* coff, uint64_t seed, uint32_t first_g, uint32_t n,
+                  uint64_t len, cudaStream_t st) {
+    if (!n || !len) return;
+    dim3 grid(blocks_for((len + 15) / 16, 256, 148 * 8), n);
+    synth_kernel<<<grid, 256, 0, st>>>(chars, coff, seed, first_g, len);
+}
+
+void launch_bloom_merge(uint8_t* dst, const uint8_t* src, uint64_t n, cudaStream_t st) {
+    if (!n) return;
+    bloom_merge_kernel<<<blocks_for(n / 16, 256 * 4, 148 * 8), 256, 0, st>>>(dst, src, n / 16);
+}
+
+}  // namespace mk

