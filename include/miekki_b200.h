@@ -79,9 +79,11 @@ int mk_get_params(const mk_ctx *ctx, uint32_t *k, uint32_t *h, uint32_t *bits_pe
 /* Copies n ASCII sequences (any bytes; no terminator needed) to the device. */
 int mk_batch_upload(mk_ctx *ctx, const char *const *seqs, const uint64_t *lens, uint32_t n,
                     mk_batch **out);
-/* Same, from one contiguous host buffer: sequence i is data[offsets[i] .. offsets[i+1]). */
-int mk_batch_upload_flat(mk_ctx *ctx, const char *data, const uint64_t *offsets, uint32_t n,
-                         mk_batch **out);
+/* Same, from one contiguous host buffer (ideally pinned): sequence i is
+ * data[offsets[i] .. offsets[i] + lens[i]).  When every offset is the previous one plus the
+ * length rounded up to 16 (offsets[0] == 0) the whole buffer goes over in a single copy. */
+int mk_batch_upload_flat(mk_ctx *ctx, const char *data, const uint64_t *offsets,
+                         const uint64_t *lens, uint32_t n, mk_batch **out);
 /* Bench/test tooling: n synthetic genomes of `len` bases generated on the device with the
  * counter-based generator of miekki_b200/synth.py:cb_bases (ids first_g .. first_g+n-1). */
 int mk_batch_synth(mk_ctx *ctx, uint64_t seed, uint32_t first_g, uint32_t n, uint64_t len,
@@ -125,6 +127,8 @@ int mk_index_import(mk_ctx *ctx, uint32_t n, const uint8_t *rows, uint64_t rows_
 uint64_t mk_bloom_window(const mk_ctx *ctx);
 int mk_bloom_get(mk_ctx *ctx, uint8_t *dst, uint64_t n);
 int mk_bloom_merge(mk_ctx *ctx, const uint8_t *src, uint64_t n);
+int mk_bloom_set(mk_ctx *ctx, const uint8_t *src, uint64_t n);   /* replace the first n bytes */
+/* dst/src of the three calls above may be host or device pointers (unified addressing). */
 
 /* ---- query ----------------------------------------------------------------- */
 
@@ -146,6 +150,16 @@ int mk_query_batch(mk_ctx *ctx, const mk_batch *reads, uint32_t nresults, uint32
  * shard applies std::sort_heap (:396). */
 int mk_query_chain(mk_ctx *ctx, const mk_batch *reads, uint32_t nresults, uint32_t min_score,
                    double min_intersection, mk_hit *heap_io, uint32_t *len_io, int finalize);
+
+/* The two halves of mk_query_chain, so that shards scan concurrently and only the cheap
+ * top-k step is chained: mk_scan sketches the reads and scans this shard, keeping the
+ * count matrix (n x N u32) in HBM; mk_topk then applies Miekki.cpp:376-397 to it.
+ * chain_in != 0: heap_io/len_io hold the previous shard's state.  heap_io/len_io may be
+ * host or device pointers.  mk_scan fails with MK_ERR_ARG when n x N counts exceed 16 GiB
+ * (split the reads). */
+int mk_scan(mk_ctx *ctx, const mk_batch *reads);
+int mk_topk(mk_ctx *ctx, uint32_t nresults, uint32_t min_score, double min_intersection,
+            mk_hit *heap_io, uint32_t *len_io, int chain_in, int finalize);
 
 /* Test hook: raw shared-fingerprint counts, the matrix Miekki::query_sequences returns
  * (Miekki.cpp:352): counts[i * N + g].  surviving (may be NULL) receives A(q), the number of

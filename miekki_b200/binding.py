@@ -53,7 +53,7 @@ SIGNATURES = {
     "mk_set_shard": (_i, [_vp, _u32]),
     "mk_get_params": (_i, [_vp] + [C.POINTER(_u32)] * 6),
     "mk_batch_upload": (_i, [_vp, _vp, _vp, _u32, _pp]),
-    "mk_batch_upload_flat": (_i, [_vp, _vp, _vp, _u32, _pp]),
+    "mk_batch_upload_flat": (_i, [_vp, _vp, _vp, _vp, _u32, _pp]),
     "mk_batch_synth": (_i, [_vp, _u64, _u32, _u32, _u64, _pp]),
     "mk_batch_download": (_i, [_vp, _vp, _u32, _vp, _u64]),
     "mk_batch_size": (_u32, [_vp]),
@@ -69,6 +69,9 @@ SIGNATURES = {
     "mk_bloom_window": (_u64, [_vp]),
     "mk_bloom_get": (_i, [_vp, _vp, _u64]),
     "mk_bloom_merge": (_i, [_vp, _vp, _u64]),
+    "mk_bloom_set": (_i, [_vp, _vp, _u64]),
+    "mk_scan": (_i, [_vp, _vp]),
+    "mk_topk": (_i, [_vp, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_query": (_i, [_vp, _vp, _vp, _u32, _u32, _u32, _d, _vp, _vp]),
     "mk_query_batch": (_i, [_vp, _vp, _u32, _u32, _d, _vp, _vp]),
     "mk_query_chain": (_i, [_vp, _vp, _u32, _u32, _d, _vp, _vp, _i]),
@@ -180,19 +183,16 @@ class Miekki:
         self._ck(lib().mk_batch_upload(self._ctx, arr, _ptr(lens), len(seqs), C.byref(h)))
         return Batch(self, h)
 
-    def upload_flat(self, data: np.ndarray, offsets: np.ndarray) -> Batch:
-        """data: uint8 array (ideally pinned), offsets: uint64[n+1]."""
-        h = C.c_void_p()
-        offsets = np.ascontiguousarray(offsets, np.uint64)
-        self._ck(lib().mk_batch_upload_flat(self._ctx, C.c_void_p(data.ctypes.data), _ptr(offsets),
-                                            len(offsets) - 1, C.byref(h)))
-        return Batch(self, h)
+    def upload_flat(self, data: np.ndarray, offsets, lens) -> Batch:
+        """data: uint8 array (ideally pinned); read i = data[offsets[i] : offsets[i] + lens[i]]."""
+        return self.upload_flat_ptr(data.ctypes.data, offsets, lens)
 
-    def upload_flat_ptr(self, ptr: int, offsets: np.ndarray) -> Batch:
+    def upload_flat_ptr(self, ptr: int, offsets, lens) -> Batch:
         h = C.c_void_p()
         offsets = np.ascontiguousarray(offsets, np.uint64)
-        self._ck(lib().mk_batch_upload_flat(self._ctx, C.c_void_p(ptr), _ptr(offsets),
-                                            len(offsets) - 1, C.byref(h)))
+        lens = np.ascontiguousarray(lens, np.uint64)
+        self._ck(lib().mk_batch_upload_flat(self._ctx, C.c_void_p(ptr), _ptr(offsets), _ptr(lens),
+                                            len(lens), C.byref(h)))
         return Batch(self, h)
 
     def synth(self, seed: int, first_g: int, n: int, length: int) -> Batch:
@@ -235,6 +235,16 @@ class Miekki:
     def bloom_merge(self, src: np.ndarray):
         src = np.ascontiguousarray(src, np.uint8)
         self._ck(lib().mk_bloom_merge(self._ctx, _ptr(src), len(src)))
+
+    def bloom_set(self, src: np.ndarray):
+        src = np.ascontiguousarray(src, np.uint8)
+        self._ck(lib().mk_bloom_set(self._ctx, _ptr(src), len(src)))
+
+    def bloom_get_ptr(self, ptr: int, n: int):
+        self._ck(lib().mk_bloom_get(self._ctx, C.c_void_p(ptr), n))
+
+    def bloom_set_ptr(self, ptr: int, n: int):
+        self._ck(lib().mk_bloom_set(self._ctx, C.c_void_p(ptr), n))
 
     def export(self, rows=True, bloom_bytes: int | None = None):
         """-> dict(rows[B,n], genome_size, bloom, sketch_size): dump_disk payload."""
@@ -289,6 +299,23 @@ class Miekki:
         assert heap.dtype == HIT_DTYPE and heap.flags.c_contiguous and lens.dtype == np.uint32
         self._ck(lib().mk_query_chain(self._ctx, batch._h, nresults, min_score, float(min_intersection),
                                       _ptr(heap), _ptr(lens), 1 if finalize else 0))
+
+    def scan(self, batch: Batch):
+        """Sketch the reads and scan this shard; the counts stay in HBM for topk()."""
+        self._ck(lib().mk_scan(self._ctx, batch._h))
+
+    def topk_ptr(self, heap_ptr: int, len_ptr: int, nresults=10, min_score=10, min_intersection=None,
+                 chain_in=False, finalize=True):
+        """Bounded-heap step on the stored counts; pointers may be host or device memory."""
+        if min_intersection is None:
+            min_intersection = 0.5 * self.threshold
+        self._ck(lib().mk_topk(self._ctx, nresults, min_score, float(min_intersection),
+                               C.c_void_p(heap_ptr), C.c_void_p(len_ptr), 1 if chain_in else 0,
+                               1 if finalize else 0))
+
+    def topk(self, heap: np.ndarray, lens: np.ndarray, **kw):
+        assert heap.dtype == HIT_DTYPE and heap.flags.c_contiguous and lens.dtype == np.uint32
+        self.topk_ptr(heap.ctypes.data, lens.ctypes.data, nresults=heap.shape[1], **kw)
 
     def query_counts(self, seqs):
         """-> (counts[n_reads, n_genomes] u32, surviving[n_reads] u32)."""

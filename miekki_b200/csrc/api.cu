@@ -74,6 +74,7 @@ struct mk_ctx {
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint32_t* d_work = nullptr;
+    uint32_t scanned_reads = 0;   // rows of `counts` left by mk_scan
 
     std::vector<cudaEvent_t> ev_pool;
     std::vector<PendingEvent> ev_pending;
@@ -589,6 +590,58 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     return sync(c);
 }
 
+// sketch + scan of a whole batch with the counts kept in HBM (for the chained top-k)
+int scan_all(mk_ctx* c, const mk_batch* b) {
+    const uint32_t n = b->n;
+    c->scanned_reads = 0;
+    if (n == 0) return MK_OK;
+    const uint64_t n_pad = (c->n + 15) / 16 * 16;
+    if ((uint64_t)n * std::max<uint64_t>(n_pad, 16) * 4 > (16ull << 30))
+        return fail(c, MK_ERR_ARG, "mk_scan: count matrix would exceed 16 GiB, split the reads");
+    Lists L{};
+    TRY(build_lists(c, b, &L));
+    if (c->n > 0) {
+        ScanPlan plan{};
+        if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
+            return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
+        TRY(reserve(c, c->counts, (size_t)n * n_pad * 4));
+        TRY(scan_reads(c, L, 0, n, plan));
+    }
+    TRY(account_lists(c, L, n, nullptr));
+    c->scanned_reads = n;
+    return sync(c);
+}
+
+int topk_stored(mk_ctx* c, uint32_t K, uint32_t min_score, double min_int, mk_hit* heap_io,
+                uint32_t* len_io, bool chain_in, int finalize) {
+    if (K < 1 || K > 64) return fail(c, MK_ERR_ARG, "nresults must be in [1, 64]");
+    const uint32_t n = c->scanned_reads;
+    if (n == 0) return MK_OK;
+    if (!heap_io || !len_io) return fail(c, MK_ERR_ARG, "mk_topk needs heap_io and len_io");
+    TRY(reserve(c, c->heap, (size_t)n * K * sizeof(HitDev)));
+    TRY(reserve(c, c->heap_len, (size_t)n * 4));
+    auto* d_heap = static_cast<HitDev*>(c->heap.p);
+    auto* d_hlen = static_cast<uint32_t*>(c->heap_len.p);
+    if (chain_in) {
+        CU(cudaMemcpyAsync(d_heap, heap_io, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, c->stream));
+        CU(cudaMemcpyAsync(d_hlen, len_io, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    } else {
+        CU(cudaMemsetAsync(d_hlen, 0, (size_t)n * 4, c->stream));
+    }
+    if (c->n > 0) {
+        PhaseTimer t(c, PH_TOPK);
+        launch_topk(static_cast<uint32_t*>(c->counts.p), n, c->n, c->first_id, c->d_sketch_size,
+                    c->d_genome_size, K, min_score, min_int, d_heap, d_hlen, finalize, c->stream);
+        c->stats.kernel_launches += 1;
+        CU(cudaGetLastError());
+    } else if (finalize) {
+        return fail(c, MK_ERR_STATE, "mk_topk: the finalizing shard must hold at least one genome");
+    }
+    CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(len_io, d_hlen, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    return sync(c);
+}
+
 struct Guard {
     std::lock_guard<std::mutex> lk;
     explicit Guard(mk_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
@@ -709,27 +762,27 @@ int mk_batch_upload(mk_ctx* c, const char* const* seqs, const uint64_t* lens, ui
     return sync(c);
 }
 
-int mk_batch_upload_flat(mk_ctx* c, const char* data, const uint64_t* offsets, uint32_t n, mk_batch** out) {
-    if (!c || !out || (n && (!data || !offsets))) return fail(c, MK_ERR_ARG, "mk_batch_upload_flat: NULL argument");
+int mk_batch_upload_flat(mk_ctx* c, const char* data, const uint64_t* offsets, const uint64_t* lens, uint32_t n,
+                         mk_batch** out) {
+    if (!c || !out || (n && (!data || !offsets || !lens)))
+        return fail(c, MK_ERR_ARG, "mk_batch_upload_flat: NULL argument");
     Guard g(c);
-    std::vector<uint64_t> lens(n);
-    bool aligned = true;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (offsets[i + 1] < offsets[i]) return fail(c, MK_ERR_ARG, "offsets must be non-decreasing");
-        lens[i] = offsets[i + 1] - offsets[i];
-        aligned = aligned && (offsets[i] % 16 == 0);
-    }
     mk_batch* b = new mk_batch();
-    batch_layout(b, lens.data(), n);
+    batch_layout(b, lens, n);
     int r = batch_alloc(c, b);
     if (r != MK_OK) { batch_release(b); return r; }
     cudaError_t e = cudaSuccess;
-    if (aligned && n && offsets[0] == 0 && b->h_coff[n] >= offsets[n] &&
-        std::equal(b->h_coff.begin(), b->h_coff.begin() + n, offsets)) {
-        // the caller's layout already is ours (every start 16-byte aligned): one copy
-        e = cudaMemsetAsync(b->chars + offsets[n], 0, b->bytes - offsets[n], c->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(b->chars, data, offsets[n], cudaMemcpyHostToDevice, c->stream);
+    uint64_t span = 0;
+    bool same = n > 0;
+    for (uint32_t i = 0; i < n && same; ++i) {
+        same = offsets[i] == b->h_coff[i];
+        span = offsets[i] + lens[i];
+    }
+    if (same) {
+        // the caller's layout already is ours (every start 16-byte aligned, packed): one copy.
+        // Gap bytes come from the caller's buffer; kernels never interpret bytes past a length.
+        e = cudaMemsetAsync(b->chars + span, 0, b->bytes - span, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->chars, data, span, cudaMemcpyHostToDevice, c->stream);
     } else {
         e = cudaMemsetAsync(b->chars, 0, b->bytes, c->stream);
         for (uint32_t i = 0; i < n && e == cudaSuccess; ++i)
@@ -890,8 +943,17 @@ int mk_bloom_get(mk_ctx* c, uint8_t* dst, uint64_t n) {
     if (!c || !dst) return MK_ERR_ARG;
     Guard g(c);
     if (n > c->window) return fail(c, MK_ERR_ARG, "mk_bloom_get: n exceeds the window");
-    CU(cudaMemcpyAsync(dst, c->bloom, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(dst, c->bloom, n, cudaMemcpyDefault, c->stream));
     c->stats.d2h_bytes += n;
+    return sync(c);
+}
+
+int mk_bloom_set(mk_ctx* c, const uint8_t* src, uint64_t n) {
+    if (!c || !src) return MK_ERR_ARG;
+    Guard g(c);
+    if (n > c->window) return fail(c, MK_ERR_ARG, "mk_bloom_set: n exceeds the window");
+    CU(cudaMemcpyAsync(c->bloom, src, n, cudaMemcpyDefault, c->stream));
+    c->stats.h2d_bytes += n;
     return sync(c);
 }
 
@@ -900,7 +962,7 @@ int mk_bloom_merge(mk_ctx* c, const uint8_t* src, uint64_t n) {
     Guard g(c);
     if (n > c->window || n % 16) return fail(c, MK_ERR_ARG, "mk_bloom_merge: n must be a multiple of 16 within the window");
     TRY(reserve(c, c->misc, n));
-    CU(cudaMemcpyAsync(c->misc.p, src, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->misc.p, src, n, cudaMemcpyDefault, c->stream));
     launch_bloom_merge(c->bloom, static_cast<uint8_t*>(c->misc.p), n, c->stream);
     c->stats.kernel_launches += 1;
     c->stats.h2d_bytes += n;
@@ -933,6 +995,19 @@ int mk_query_chain(mk_ctx* c, const mk_batch* reads, uint32_t nresults, uint32_t
     if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_query_chain: NULL argument");
     Guard g(c);
     return query_device(c, reads, nresults, min_score, min_intersection, heap_io, len_io, true, finalize);
+}
+
+int mk_scan(mk_ctx* c, const mk_batch* reads) {
+    if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_scan: NULL argument");
+    Guard g(c);
+    return scan_all(c, reads);
+}
+
+int mk_topk(mk_ctx* c, uint32_t nresults, uint32_t min_score, double min_intersection, mk_hit* heap_io,
+            uint32_t* len_io, int chain_in, int finalize) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    return topk_stored(c, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
 }
 
 int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, uint32_t* counts,

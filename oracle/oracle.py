@@ -338,5 +338,6 @@ class RefBinary:
     @staticmethod
     def elapsed(stdout: str) -> list[float]:
         """The two 'elapsed time: Xs' lines (main.cpp:211,234): build, query."""
-        return [float(l.split(":")[1].strip().rstrip("s")) for l in stdout.splitlines()
-                if l.startswith("elapsed time:")]
+        import re
+        # progress ticks ("-", no newline) may precede the text on the same line
+        return [float(x) for x in re.findall(r"elapsed time: ([0-9.eE+-]+)s", stdout)]
