@@ -2,7 +2,7 @@
 #   make            -> miekki_b200/libmiekki_b200.so , miekki_b200/cli/miekki
 #   make oracle     -> oracle/_build/libmiekki_oracle.so (+ oracle/_ref/Miekki when the reference is present)
 NVCC ?= /usr/local/cuda/bin/nvcc
-CXX ?= g++
+CXX := $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
 SRC := miekki_b200/csrc

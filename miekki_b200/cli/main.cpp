@@ -1,0 +1,440 @@
+// miekki -- command line of the B200-native sketch-and-query path.
+//
+// Drop-in for the reference's main.cpp:125-238 on the flags -l -a -o -d -i -h -k -s -f -b
+// -e -t: same getopt string, same defaults (h=17, t=8, k=31, b=33, f=3, s=200, out.txt), same
+// hit-line format (Miekki.cpp:438-445), exact-line format (Miekki.cpp:853) and gz index dump
+// (Miekki.cpp:649-719).  The host keeps file parsing (plain/gz FASTA) and text formatting;
+// sketching, scoring, filtering and the exact intersection run on the GPU through the C ABI
+// in include/miekki_b200.h.  Genome ids are list order (the reference's `-t 1` order) for any
+// -t; -t only sets the number of host parser threads.
+#include <getopt.h>
+#include <omp.h>
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "fasta.hpp"
+#include "miekki_b200.h"
+
+using namespace std;
+
+namespace {
+
+bool exists_test(const string& name) {
+    struct stat buffer;
+    return stat(name.c_str(), &buffer) == 0;
+}
+
+// utils.cpp:145-157 intToString (thousands separators) -- banner only
+string int_to_string(uint64_t n) {
+    if (n < 1000) return to_string(n);
+    string end(to_string(n % 1000));
+    if (end.size() == 3) return int_to_string(n / 1000) + "," + end;
+    if (end.size() == 2) return int_to_string(n / 1000) + ",0" + end;
+    return int_to_string(n / 1000) + ",00" + end;
+}
+
+void help() {   // main.cpp:102-121
+    cout << "This is a help message" << endl;
+    cout << "Input " << endl;
+    cout << "-i load a constructed index from disk" << endl;
+    cout << "-l construct an index from a list of file" << endl;
+    cout << "-a query a fasta file" << endl;
+    cout << "\nOutput " << endl;
+    cout << "-o output file name (out.txt)" << endl;
+    cout << "-d dump the index on disk" << endl;
+    cout << "\nPerformances " << endl;
+    cout << "-h use 2^h minimizers per sequence (17)" << endl;
+    cout << "-k kmer size (31)" << endl;
+    cout << "-s minimal estimated intersection to be reported (200)" << endl;
+    cout << "-t host thread number (8)" << endl;
+    cout << "\nAdvanced usage " << endl;
+    cout << "-f fingerprint size " << endl;
+    cout << "-b 2^b bits used for the bloom filter  " << endl;
+    cout << "-e exact mode, real intersection will be computed on hits" << endl;
+    cout << "\nB200 " << endl;
+    cout << "--device N  CUDA device ordinal (0)" << endl;
+}
+
+[[noreturn]] void die(mk_ctx* ctx, const char* what) {
+    cerr << "miekki: " << what << ": " << mk_last_error(ctx) << endl;
+    exit(1);
+}
+
+struct Index {
+    mk_ctx* ctx = nullptr;
+    uint32_t k = 31, h = 17, nbm = 8, nbmant = 5, b = 33, threshold = 200;
+    bool compressed_flag = false;        // header byte 38
+    vector<string> file_names;           // Miekki.h:58; not part of the dump (quirk G4)
+    ofstream* out = nullptr;
+    int threads = 8;
+};
+
+// ---- build: Miekki::index_file_of_file, Miekki.cpp:540-588 ----------------------------------
+void index_file_of_file(Index& ix, const string& list) {
+    if (!exists_test(list)) {
+        cout << "Missed file of file: " << list << endl;
+        return;
+    }
+    vector<string> names;
+    {
+        mkcli::LineReader in(list);
+        string name;
+        while (!in.eof()) {
+            in.getline(name);
+            if (name.size() > 3) names.push_back(name);          // :555
+        }
+    }
+    // parse `wave` files in parallel, then insert in list order so that ids are deterministic
+    const size_t wave = max<size_t>(32, 4 * (size_t)ix.threads);
+    for (size_t w0 = 0; w0 < names.size(); w0 += wave) {
+        const size_t m = min(wave, names.size() - w0);
+        vector<string> seqs(m);
+        vector<char> ok(m, 0);
+        #pragma omp parallel for num_threads(ix.threads) schedule(dynamic, 1)
+        for (size_t i = 0; i < m; ++i) {
+            const string& fn = names[w0 + i];
+            if (!exists_test(fn)) {
+                #pragma omp critical(msg)
+                cout << "Missed file: " << fn << endl;           // :557
+                continue;
+            }
+            seqs[i] = mkcli::read_genome_concat(fn);
+            ok[i] = seqs[i].size() >= ix.k;                      // :569
+        }
+        vector<const char*> ptr;
+        vector<uint64_t> len;
+        for (size_t i = 0; i < m; ++i) {
+            if (!ok[i]) continue;
+            ptr.push_back(seqs[i].data());
+            len.push_back(seqs[i].size());
+            ix.file_names.push_back(names[w0 + i]);              // :303
+            cout << "-" << flush;                                // :575
+        }
+        if (!ptr.empty() && mk_index_add(ix.ctx, ptr.data(), len.data(), (uint32_t)ptr.size()) != MK_OK)
+            die(ix.ctx, "mk_index_add");
+    }
+    uint32_t n = 0;
+    mk_index_size(ix.ctx, &n);
+    cout << endl;
+    cout << "Reference indexed: " << n << endl;                  // :583
+    cout << "BF size:" << int_to_string(1ull << ix.b) << endl;   // :585
+}
+
+// ---- dump / load: Miekki.cpp:649-719, SURVEY.md Appendix C -----------------------------------
+void dump_disk(Index& ix, const string& path) {
+    uint32_t n = 0;
+    mk_index_size(ix.ctx, &n);
+    const uint64_t B = 1ull << ix.h;
+    const uint64_t bloom_bits = 1ull << ix.b;
+    vector<uint8_t> rows(B * (uint64_t)n), bloom(bloom_bits / 8);
+    vector<uint64_t> gs(n);
+    vector<uint32_t> ss(n);
+    if (mk_index_export(ix.ctx, rows.data(), gs.data(), bloom.data(), bloom.size(), ss.data()) != MK_OK)
+        die(ix.ctx, "mk_index_export");
+    mkcli::GzWriter w(path);
+    const uint8_t jaccard_estimation = 0;       // uninitialised in the reference (quirk G7)
+    const uint8_t containment_estimation = 0;
+    const uint8_t compressed = ix.compressed_flag ? 1 : 0;
+    w.write(&ix.k, 4);
+    w.write(&ix.h, 4);
+    w.write(&ix.nbm, 4);
+    w.write(&ix.nbmant, 4);
+    w.write(&n, 4);
+    w.write(&ix.b, 4);
+    w.write(&bloom_bits, 8);
+    w.write(&jaccard_estimation, 1);
+    w.write(&containment_estimation, 1);
+    w.write(&ix.threshold, 4);
+    w.write(&compressed, 1);
+    w.write(rows.data(), rows.size());
+    w.write(gs.data(), gs.size() * 8);
+    w.write(bloom.data(), bloom.size());
+    w.write(ss.data(), ss.size() * 4);
+    w.close();
+}
+
+bool load_disk(Index& ix, const string& path, int device) {
+    if (!exists_test(path)) {
+        cout << "File problem" << endl;                          // :683-686
+        return false;
+    }
+    mkcli::LineReader in(path);
+    unsigned char head[39];
+    if (in.read(head, 39) != 39) {
+        cerr << "miekki: truncated index dump" << endl;
+        return false;
+    }
+    uint32_t n;
+    uint64_t bloom_bits;
+    memcpy(&ix.k, head + 0, 4);
+    memcpy(&ix.h, head + 4, 4);
+    memcpy(&ix.nbm, head + 8, 4);
+    memcpy(&ix.nbmant, head + 12, 4);
+    memcpy(&n, head + 16, 4);
+    memcpy(&ix.b, head + 20, 4);
+    memcpy(&bloom_bits, head + 24, 8);
+    memcpy(&ix.threshold, head + 34, 4);
+    if (mk_create(ix.k, ix.h, ix.nbm, ix.nbmant, ix.b, ix.threshold, device, &ix.ctx) != MK_OK) {
+        cerr << "miekki: " << mk_last_error(nullptr) << endl;
+        exit(1);
+    }
+    const uint64_t B = 1ull << ix.h;
+    vector<uint8_t> rows(B * (uint64_t)n), bloom(bloom_bits / 8);
+    vector<uint64_t> gs(n);
+    vector<uint32_t> ss(n);
+    bool ok = in.read(rows.data(), rows.size()) == rows.size();
+    ok = ok && in.read(gs.data(), gs.size() * 8) == gs.size() * 8;
+    if (bloom_bits != 0) ok = ok && in.read(bloom.data(), bloom.size()) == bloom.size();
+    ok = ok && in.read(ss.data(), ss.size() * 4) == ss.size() * 4;
+    if (!ok) {
+        cerr << "miekki: truncated index dump" << endl;
+        return false;
+    }
+    if (mk_index_import(ix.ctx, n, rows.data(), n, gs.data(), bloom.data(), bloom.size(), ss.data()) != MK_OK)
+        die(ix.ctx, "mk_index_import");
+    ix.compressed_flag = false;                                   // :705
+    return true;
+}
+
+// ---- query: Miekki::query_file, Miekki.cpp:426-483 -------------------------------------------
+struct ReadBatch {
+    vector<string> heads, seqs;
+    void clear() { heads.clear(); seqs.clear(); }
+    size_t size() const { return seqs.size(); }
+};
+
+// the 2-line record loop of :458-475; fills up to `cap` reads, false when the file is done
+bool next_reads(mkcli::LineReader& in, uint32_t k, size_t cap, ReadBatch& b, bool exact_filter) {
+    b.clear();
+    string head, ref;
+    while (!in.eof() && b.size() < cap) {
+        in.getline(head);
+        in.getline(ref);
+        if (ref.size() < k) continue;                            // :465
+        if (exact_filter) {                                      // :736
+            const char c = ref[0];
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') continue;
+        }
+        b.heads.push_back(head);
+        b.seqs.push_back(ref);
+    }
+    return b.size() > 0;
+}
+
+void run_query(Index& ix, ReadBatch& b, uint32_t nresults, uint32_t min_score, double min_int,
+               vector<mk_hit>& hits, vector<uint32_t>& nhits) {
+    const size_t n = b.size();
+    vector<const char*> ptr(n);
+    vector<uint64_t> len(n);
+    for (size_t i = 0; i < n; ++i) {
+        ptr[i] = b.seqs[i].data();
+        len[i] = b.seqs[i].size();
+    }
+    hits.assign(n * nresults, mk_hit{});
+    nhits.assign(n, 0);
+    if (mk_query(ix.ctx, ptr.data(), len.data(), (uint32_t)n, nresults, min_score, min_int, hits.data(),
+                 nhits.data()) != MK_OK)
+        die(ix.ctx, "mk_query");
+}
+
+void query_file(Index& ix, const string& path) {
+    if (!exists_test(path)) {
+        cout << "File problem" << endl;
+        return;
+    }
+    mkcli::LineReader in(path);
+    ReadBatch b;
+    vector<mk_hit> hits;
+    vector<uint32_t> nhits;
+    const size_t cap = 1 << 16;
+    while (next_reads(in, ix.k, cap, b, false)) {
+        cout << "-" << flush;                                    // :345
+        run_query(ix, b, 10, 10, 0.5 * ix.threshold, hits, nhits);   // :437
+        vector<string> lines(b.size());
+        #pragma omp parallel for num_threads(ix.threads) schedule(static)
+        for (size_t i = 0; i < b.size(); ++i) {
+            string& s = lines[i];
+            s = b.heads[i] + ":";                                // :440
+            for (uint32_t j = 0; j < nhits[i]; ++j) {
+                const mk_hit& sim = hits[i * 10 + j];            // :442
+                s += to_string(sim.genome) + "\t" + to_string(sim.matches) + "\t" +
+                     to_string((unsigned)sim.intersection) + "\t" + to_string(sim.jaccard) + ";";
+            }
+            s += "\n";
+        }
+        for (const string& s : lines) *ix.out << s;
+    }
+    *ix.out << flush;
+}
+
+// ---- exact mode: Miekki::query_file_exact + ground_truth_batch, Miekki.cpp:723-759, 792-859 ---
+struct Candidate {
+    string seq, head;
+    double jaccard, intersection;
+};
+
+void ground_truth(Index& ix, const string& file, vector<Candidate>& v) {
+    if (v.empty()) return;
+    if (!exists_test(file)) {
+        cout << "File problem: " << file << endl;                // :796-799
+        return;
+    }
+    vector<string> recs = mkcli::read_genome_records(file, ix.k);
+    vector<const char*> rp(recs.size()), qp(v.size());
+    vector<uint64_t> rl(recs.size()), ql(v.size());
+    for (size_t i = 0; i < recs.size(); ++i) { rp[i] = recs[i].data(); rl[i] = recs[i].size(); }
+    for (size_t i = 0; i < v.size(); ++i) { qp[i] = v[i].seq.data(); ql[i] = v[i].seq.size(); }
+    vector<uint64_t> inter(v.size()), uni(v.size());
+    uint64_t nB = 0;
+    if (mk_exact(ix.ctx, rp.data(), rl.data(), (uint32_t)recs.size(), qp.data(), ql.data(), (uint32_t)v.size(),
+                 inter.data(), uni.data(), &nB) != MK_OK)
+        die(ix.ctx, "mk_exact");
+    for (size_t i = 0; i < v.size(); ++i) {
+        const double nb_inter = (double)inter[i], nb_union = (double)uni[i];
+        if (nb_inter > 0) {                                      // :843
+            const double real_jax = nb_inter / nb_union;         // :845-846
+            *ix.out << real_jax << "\t" << v[i].jaccard << "\t" << nb_inter << "\t" << v[i].intersection
+                    << "\t" << v[i].head << "\t" << file << "\n";   // :853
+        }
+    }
+}
+
+void query_file_exact(Index& ix, const string& path) {
+    if (!exists_test(path)) {
+        cout << "File problem" << endl;
+        return;
+    }
+    if (ix.file_names.empty()) {
+        // the reference segfaults here (file_names is not in the dump, quirk G4)
+        cerr << "miekki: exact mode needs the genome list (-l) in the same run" << endl;
+        return;
+    }
+    mkcli::LineReader in(path);
+    ReadBatch b;
+    vector<mk_hit> hits;
+    vector<uint32_t> nhits;
+    map<uint32_t, vector<Candidate>> per_genome;
+    size_t held = 0;
+    auto flush_all = [&]() {
+        for (auto& kv : per_genome) ground_truth(ix, ix.file_names[kv.first], kv.second);
+        per_genome.clear();
+        held = 0;
+    };
+    while (next_reads(in, ix.k, 1 << 14, b, true)) {
+        run_query(ix, b, 5, 10, (double)ix.threshold, hits, nhits);   // :741
+        for (size_t i = 0; i < b.size(); ++i)
+            for (uint32_t j = 0; j < nhits[i]; ++j) {
+                const mk_hit& sim = hits[i * 5 + j];
+                per_genome[sim.genome].push_back({b.seqs[i], b.heads[i], sim.jaccard, sim.intersection});
+                ++held;
+            }
+        if (held > (1u << 20)) flush_all();      // the reference flushes per genome at 100 (:745)
+    }
+    flush_all();
+    *ix.out << flush;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        help();
+        exit(0);
+    }
+    string index_file, list_file, query_fa, query_list, output_file("out.txt"), index_dump;
+    uint64_t H = 17, core_number = 8, kmer_size = 31, bloom_size = 33, fingerprint_size = 3;
+    double threshold = 200;
+    bool exact_mode = false;
+    int device = 0;
+    static const option longopts[] = {{"device", required_argument, nullptr, 1000}, {nullptr, 0, nullptr, 0}};
+    int c;
+    while ((c = getopt_long(argc, argv, "i:l:a:h:t:f:k:s:b:o:ed:A:", longopts, nullptr)) != -1) {
+        switch (c) {
+            case 'i': index_file = optarg; break;
+            case 'l': list_file = optarg; break;
+            case 'a': query_fa = optarg; break;
+            case 'A': query_list = optarg; break;
+            case 'o': output_file = optarg; break;
+            case 'h': H = stoi(optarg); break;
+            case 't': core_number = stoi(optarg); break;
+            case 'k': kmer_size = stoi(optarg); break;
+            case 's': threshold = stof(optarg); break;
+            case 'f': fingerprint_size = stoi(optarg); break;
+            case 'b': bloom_size = stoi(optarg); break;
+            case 'e': exact_mode = true; break;
+            case 'd': index_dump = optarg; break;
+            case 1000: device = stoi(optarg); break;
+        }
+    }
+    const uint32_t bit_per_min = (uint32_t)(5 + fingerprint_size);
+    cout << "Using " << bit_per_min << " bits per minimizer, " << int_to_string(1ull << H) << " minimizers so "
+         << int_to_string((uint64_t)bit_per_min * (1ull << H)) << " bits per sequences" << endl;   // main.cpp:186
+    auto start = chrono::system_clock::now();
+    Index ix;
+    ix.threads = (int)max<uint64_t>(1, core_number);
+    if (!index_file.empty()) {
+        if (!load_disk(ix, index_file, device)) return 1;
+        ix.out = new ofstream(output_file.c_str());
+        cout << "I output results in " << output_file << endl;
+        cout << "Load sucessful" << endl;                        // main.cpp:193 (sic)
+    } else if (!list_file.empty()) {
+        ix.k = (uint32_t)kmer_size;
+        ix.h = (uint32_t)H;
+        ix.nbm = bit_per_min;
+        ix.b = (uint32_t)bloom_size;
+        ix.threshold = (uint32_t)threshold;                      // double -> uint32_t, Miekki.h:66
+        if (bit_per_min != 8) {
+            cout << "not implemented" << endl;                   // Miekki.cpp:236-237 (quirk G12)
+            exit(0);
+        }
+        if (mk_create(ix.k, ix.h, ix.nbm, 5, ix.b, ix.threshold, device, &ix.ctx) != MK_OK) {
+            cerr << "miekki: " << mk_last_error(nullptr) << endl;
+            return 1;
+        }
+        ix.out = new ofstream(output_file.c_str());
+        cout << "I output results in " << output_file << endl;   // Miekki.h:75
+        index_file_of_file(ix, list_file);
+        ix.compressed_flag = true;      // the reference has run compress_index(1) here (main.cpp:198)
+    } else {
+        cout << "What am I supposed to index ? use either -i or -l options please" << endl;
+        help();
+        exit(0);
+    }
+    if (!index_dump.empty()) {
+        cout << "I write this index on the disk for later" << endl;
+        dump_disk(ix, index_dump);
+    }
+    auto end_index = chrono::system_clock::now();
+    chrono::duration<double> elapsed = end_index - start;
+    cout << "elapsed time: " << elapsed.count() << "s\n";
+    if (!query_fa.empty()) {
+        if (exact_mode) {
+            cout << "running in exact mode, actual intersection will be computed on hits found by the index" << endl;
+            query_file_exact(ix, query_fa);
+        } else {
+            cout << "running in approx mode, intersection is estimated by the index" << endl;
+            query_file(ix, query_fa);
+        }
+    } else if (!query_list.empty()) {
+        cout << "-A (whole-file queries) is not part of this build; see DESIGN.md, out of scope" << endl;
+    } else {
+        cout << "No query file, No queries" << endl;
+    }
+    auto end_query = chrono::system_clock::now();
+    elapsed = end_query - end_index;
+    cout << "elapsed time: " << elapsed.count() << "s\n";
+    cout << "The end" << endl;
+    if (ix.out) ix.out->close();
+    mk_destroy(ix.ctx);
+    return 0;
+}

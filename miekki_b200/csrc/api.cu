@@ -42,8 +42,9 @@ struct PendingEvent {
 
 struct mk_batch {
     uint8_t* chars = nullptr;     // device; sequence i at chars + h_coff[i] (16-byte aligned)
-    uint64_t* d_coff = nullptr;   // device copies of the two arrays below
+    uint64_t* d_coff = nullptr;   // device copies of the two arrays below (same allocation)
     uint64_t* d_len = nullptr;
+    cudaStream_t stream = nullptr;   // stream the allocation is ordered on
     std::vector<uint64_t> h_coff, h_len;
     uint32_t n = 0;
     uint64_t bytes = 0;           // padded size of chars
@@ -200,8 +201,12 @@ int ensure_capacity(mk_ctx* c, uint32_t need) {
     CU(cudaMemsetAsync(nss, 0, (size_t)ncap * 4, c->stream));
     CU(cudaMemsetAsync(ngs, 0, (size_t)ncap * 8, c->stream));
     if (c->n) {
-        CU(cudaMemcpy2DAsync(nrows, ncap, c->rows, c->stride, c->n, c->B, cudaMemcpyDeviceToDevice,
+        // a row is [half 0 | half 1]: each half moves to its place in the wider row
+        const size_t used = (size_t)((c->n + 31) / 32) * 16;     // bytes in use per half
+        CU(cudaMemcpy2DAsync(nrows, ncap, c->rows, c->stride, used, c->B, cudaMemcpyDeviceToDevice,
                              c->stream));
+        CU(cudaMemcpy2DAsync(nrows + ncap / 2, ncap, c->rows + c->stride / 2, c->stride, used, c->B,
+                             cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(nss, c->d_sketch_size, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(ngs, c->d_genome_size, (size_t)c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -235,10 +240,17 @@ void batch_layout(mk_batch* b, const uint64_t* lens, uint32_t n) {
     b->bytes = off + 64;          // kernels may read one 16-byte word past a sequence
 }
 
+// Per-call buffers come from the stream-ordered pool (release threshold raised in
+// mk_create): cudaMalloc/cudaFree per query batch cost up to hundreds of ms on a GPU
+// that holds a multi-GB index.
 int batch_alloc(mk_ctx* c, mk_batch* b) {
-    CU(cudaMalloc(&b->chars, b->bytes));
-    CU(cudaMalloc(&b->d_coff, ((size_t)b->n + 1) * 8));
-    CU(cudaMalloc(&b->d_len, std::max<size_t>(1, b->n) * 8));
+    b->stream = c->stream;
+    // one allocation: chars | coff[n+1] | len[n]
+    const size_t chars_bytes = (b->bytes + 255) / 256 * 256;
+    const size_t total = chars_bytes + ((size_t)b->n + 1) * 8 + std::max<size_t>(1, b->n) * 8;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&b->chars), total, c->stream));
+    b->d_coff = reinterpret_cast<uint64_t*>(b->chars + chars_bytes);
+    b->d_len = b->d_coff + b->n + 1;
     CU(cudaMemcpyAsync(b->d_coff, b->h_coff.data(), ((size_t)b->n + 1) * 8, cudaMemcpyHostToDevice,
                        c->stream));
     if (b->n)
@@ -249,9 +261,7 @@ int batch_alloc(mk_ctx* c, mk_batch* b) {
 
 void batch_release(mk_batch* b) {
     if (!b) return;
-    if (b->chars) cudaFree(b->chars);
-    if (b->d_coff) cudaFree(b->d_coff);
-    if (b->d_len) cudaFree(b->d_len);
+    if (b->chars) cudaFreeAsync(b->chars, b->stream);
     delete b;
 }
 
@@ -387,7 +397,7 @@ int index_add_view(mk_ctx* c, const mk_batch* b) {
             TRY(dense_sketch(c, v, true, &d));
             launch_bloom_commit(static_cast<unsigned long long*>(c->keys.p), static_cast<uint8_t*>(c->fp.p), n,
                                 c->sp(), c->bloom, c->owner, c->stream);
-            launch_scatter_rows(static_cast<uint8_t*>(c->fp.p), n, (int)c->h, c->rows, c->stride, c->n, c->stream);
+            launch_scatter_planes(static_cast<uint8_t*>(c->fp.p), n, (int)c->h, c->rows, c->stride, c->n, c->stream);
             c->stats.kernel_launches += 2;
         }
         std::vector<uint32_t> act(n);
@@ -506,7 +516,7 @@ int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
 
 // reads per scan launch: bounded by the count tile buffer
 uint32_t scan_batch_reads(const mk_ctx* c, uint32_t n_reads) {
-    const uint64_t n_pad = (c->n + 15) / 16 * 16;
+    const uint64_t n_pad = (c->n + 31) / 32 * 32;
     const uint64_t budget = 1ull << 30;
     uint64_t q = budget / (n_pad * 4);
     q = std::max<uint64_t>(1, std::min<uint64_t>(q, n_reads));
@@ -565,7 +575,7 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
         if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
             return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
         const uint32_t qb = scan_batch_reads(c, n);
-        const uint64_t n_pad = (c->n + 15) / 16 * 16;
+        const uint64_t n_pad = (c->n + 31) / 32 * 32;
         TRY(reserve(c, c->counts, (size_t)qb * n_pad * 4));
         for (uint32_t q0 = 0; q0 < n; q0 += qb) {
             const uint32_t nq = std::min(qb, n - q0);
@@ -595,7 +605,7 @@ int scan_all(mk_ctx* c, const mk_batch* b) {
     const uint32_t n = b->n;
     c->scanned_reads = 0;
     if (n == 0) return MK_OK;
-    const uint64_t n_pad = (c->n + 15) / 16 * 16;
+    const uint64_t n_pad = (c->n + 31) / 32 * 32;
     if ((uint64_t)n * std::max<uint64_t>(n_pad, 16) * 4 > (16ull << 30))
         return fail(c, MK_ERR_ARG, "mk_scan: count matrix would exceed 16 GiB, split the reads");
     Lists L{};
@@ -691,6 +701,14 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     uint64_t window = ((top >> bloom_log2) >> 3) + 1;
     window = std::min<uint64_t>(window, (1ull << bloom_log2) / 8);
     ctx->window = (window + 15) / 16 * 16;
+    {   // keep freed per-call buffers in the stream-ordered pool instead of returning them
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->bloom, ctx->window);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->owner, ctx->window * 4);
@@ -893,7 +911,16 @@ int mk_index_export(mk_ctx* c, uint8_t* rows, uint64_t* genome_size, uint8_t* bl
     if (!c) return MK_ERR_ARG;
     Guard g(c);
     if (rows && c->n) {
-        CU(cudaMemcpy2DAsync(rows, c->n, c->rows, c->stride, c->n, c->B, cudaMemcpyDeviceToHost, c->stream));
+        // bit-plane rows -> the dump's dense byte rows, a slab of buckets at a time
+        const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / c->n);
+        TRY(reserve(c, c->misc, std::min<uint64_t>(slab, c->B) * c->n));
+        for (uint64_t r0 = 0; r0 < c->B; r0 += slab) {
+            const uint64_t nr = std::min<uint64_t>(slab, c->B - r0);
+            launch_planes_to_bytes(c->rows, c->stride, r0, nr, c->n, static_cast<uint8_t*>(c->misc.p), c->stream);
+            CU(cudaMemcpyAsync(rows + r0 * c->n, c->misc.p, nr * c->n, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            c->stats.kernel_launches += 1;
+        }
         c->stats.d2h_bytes += c->B * c->n;
     }
     if (bloom) {
@@ -919,7 +946,17 @@ int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_st
     TRY(ensure_capacity(c, std::max<uint32_t>(n, 1)));
     CU(cudaMemsetAsync(c->rows, 0xFF, c->B * c->stride, c->stream));
     if (n) {
-        CU(cudaMemcpy2DAsync(c->rows, c->stride, rows, rows_stride, n, c->B, cudaMemcpyHostToDevice, c->stream));
+        // dense byte rows (dump layout) -> bit-plane rows, a slab of buckets at a time
+        const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / n);
+        TRY(reserve(c, c->misc, std::min<uint64_t>(slab, c->B) * n));
+        for (uint64_t r0 = 0; r0 < c->B; r0 += slab) {
+            const uint64_t nr = std::min<uint64_t>(slab, c->B - r0);
+            CU(cudaMemcpy2DAsync(c->misc.p, n, rows + r0 * rows_stride, rows_stride, n, nr, cudaMemcpyHostToDevice,
+                                 c->stream));
+            launch_bytes_to_planes(static_cast<uint8_t*>(c->misc.p), n, r0, nr, n, c->rows, c->stride, c->stream);
+            CU(cudaStreamSynchronize(c->stream));
+            c->stats.kernel_launches += 1;
+        }
         CU(cudaMemcpyAsync(c->d_sketch_size, sketch_size, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_genome_size, genome_size, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += c->B * n + (size_t)n * 12;
@@ -1025,7 +1062,7 @@ int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, ui
             if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
                 return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
             const uint32_t qb = scan_batch_reads(c, n);
-            const uint64_t n_pad = (c->n + 15) / 16 * 16;
+            const uint64_t n_pad = (c->n + 31) / 32 * 32;
             TRY(reserve(c, c->counts, (size_t)qb * n_pad * 4));
             for (uint32_t q0 = 0; q0 < n; q0 += qb) {
                 const uint32_t nq = std::min(qb, n - q0);
@@ -1096,10 +1133,10 @@ int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, ui
             tt += read_lens[i] >= k ? std::max<uint64_t>(4, (read_lens[i] - k + 1) * 2) : 1;
         }
         toff[n_reads] = tt;
-        CU(cudaMalloc(&tableB, slotsB * 8));
-        CU(cudaMalloc(&rtable, std::max<uint64_t>(1, tt) * 8));
-        CU(cudaMalloc(&d_cnt, (1 + 2 * (size_t)n_reads) * 8));
-        CU(cudaMalloc(&d_toff, ((size_t)n_reads + 1) * 8));
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&tableB), slotsB * 8, c->stream));
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&rtable), std::max<uint64_t>(1, tt) * 8, c->stream));
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), (1 + 2 * (size_t)n_reads) * 8, c->stream));
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&d_toff), ((size_t)n_reads + 1) * 8, c->stream));
         PhaseTimer t(c, PH_EXACT);
         launch_fill_u64(tableB, slotsB, ~0ull, c->stream);
         launch_fill_u64(rtable, tt, ~0ull, c->stream);
@@ -1137,10 +1174,10 @@ int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, ui
     int r = body();
     cudaStreamSynchronize(c->stream);
     resolve_events(c);
-    if (tableB) cudaFree(tableB);
-    if (rtable) cudaFree(rtable);
-    if (d_cnt) cudaFree(d_cnt);
-    if (d_toff) cudaFree(d_toff);
+    if (tableB) cudaFreeAsync(tableB, c->stream);
+    if (rtable) cudaFreeAsync(rtable, c->stream);
+    if (d_cnt) cudaFreeAsync(d_cnt, c->stream);
+    if (d_toff) cudaFreeAsync(d_toff, c->stream);
     batch_release(gb);
     batch_release(rb);
     return r;

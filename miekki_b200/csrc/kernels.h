@@ -32,9 +32,14 @@ void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const 
 // pass B: the smallest (genome, bucket, probe) key of every still-zero Bloom byte writes it.
 void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
                          SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st);
-// fp[s][b] -> rows[b * stride + col0 + s]
-void launch_scatter_rows(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
-                         uint32_t col0, cudaStream_t st);
+// fp[s][b] -> bit-plane rows (layout: scan.cu), genome column col0 + s
+void launch_scatter_planes(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
+                           uint32_t col0, cudaStream_t st);
+// bit-plane rows [row0, row0+nrows) <-> dense bucket-major bytes (the dump's layout)
+void launch_planes_to_bytes(const uint8_t* rows, uint64_t stride, uint64_t row0, uint64_t nrows, uint32_t n,
+                            uint8_t* out, cudaStream_t st);
+void launch_bytes_to_planes(const uint8_t* in, uint64_t in_stride, uint64_t row0, uint64_t nrows, uint32_t n,
+                            uint8_t* rows, uint64_t stride, cudaStream_t st);
 // dense read sketch -> (bucket << 8 | fp) list of buckets that are non-empty and pass Bloom
 void launch_compact_list(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
                          SketchParams p, const uint8_t* bloom, const uint32_t* read_ids,
@@ -56,8 +61,8 @@ void launch_bloom_merge(uint8_t* dst, const uint8_t* src, uint64_t n, cudaStream
 // ---- scan.cu --------------------------------------------------------------------
 struct ScanPlan {
     int threads;        // consumer threads (multiple of 32)
-    int J;              // 16-byte column groups per thread
-    uint32_t tile_w;    // genomes per tile (multiple of 16, <= 16 * threads * J)
+    int J;              // 32-genome groups per thread
+    uint32_t tile_w;    // genomes per tile (multiple of 32, <= 32 * threads * J)
     uint32_t n_tiles;   // genome tiles per row
     int stages;         // smem ring depth
     size_t smem;

@@ -4,18 +4,26 @@
 // Miekki::query_sequence (:323-337):
 //     count[q][g] = #{ (bucket, fp) of read q : rows[bucket][g] == fp }.
 //
-// Layout: rows is the bucket-major matrix, 2^h rows of `stride` bytes (stride % 128 == 0),
-// one byte per genome.  A read arrives as a list of (bucket << 8 | fp) words: only buckets
-// that are non-empty and passed the Bloom check.
+// HBM layout (see DESIGN.md "index layout"): bucket-major, one byte per (bucket, genome),
+// but inside a row the eight bits of 32 consecutive genomes are stored as eight 32-bit
+// bit-planes: row b = [half 0 | half 1], each half stride/2 bytes; group j (genomes
+// 32j..32j+31) keeps planes 0-3 at half0 + 16j and planes 4-7 at half1 + 16j; bit i of plane p
+// is bit p of the fingerprint of genome 32j+i.  One row still costs N bytes of HBM traffic,
+// but "fingerprint == f" for 32 genomes is eight 3-input logic ops
+//     e = AND_p (plane_p XOR m_p),   m_p = (f bit p) ? 0 : ~0,
+// and the 1-bit results are summed with carry-save adders (vertical counters) instead of
+// 32 byte compares + 32 adds: ~10 integer ops per 32 genome-rows.  That takes the integer
+// pipe out of the way so the kernel runs at DRAM speed.
 //
-// Kernel: persistent, one CTA per SM.  A producer warp walks the work items
-// (read, genome tile), and for every list entry issues ONE bulk async copy
-// (cp.async.bulk, SASS UBLKCP) of the row segment rows[bucket][g0 .. g0+w) into a ring of
-// shared-memory stages guarded by mbarriers; its fingerprint and the item boundaries travel
-// in a 16-byte per-stage descriptor.  Consumer threads own 16-byte column groups: they
-// compare 4 genomes per 32-bit op (SWAR byte equality), accumulate in packed 8-bit counters
-// that are spilled into 32-bit registers every 255 rows, and write the finished counters of
-// an item with 16-byte stores.  Algorithmic bytes = sum_q A(q) * N (one byte per compare).
+// Kernel: persistent, one CTA per SM.  A producer warp walks the work items (read, genome
+// tile); for every R = 4 list entries it issues 2 x R bulk async copies (cp.async.bulk, SASS
+// UBLKCP) of row-tile halves into one stage of a shared-memory ring guarded by mbarriers; the
+// XOR masks of the R fingerprints and the item boundaries travel in a per-stage descriptor.
+// Consumer threads own J groups of 32 genomes; per stage they fold R rows into the vertical
+// counters; at the end of an item the planes are bit-transposed into 32 counts per group and
+// written with 16-byte stores.  Algorithmic bytes = sum_q A(q) * N (one byte per compare).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,15 +31,19 @@ namespace mk {
 
 namespace {
 
-constexpr uint32_t F_FIRST = 1, F_LAST = 2, F_ROW = 4, F_END = 8;
+constexpr uint32_t F_FIRST = 1, F_LAST = 2, F_END = 8, F_ACCUM = 16;
+constexpr int R = 4;                 // rows per stage
 constexpr int MAX_J = 4;
-constexpr int MAX_STAGES = 64;
+constexpr int MAX_STAGES = 48;
+constexpr int TOP = 16;              // counter planes: counts up to 65535 per chunk
+constexpr uint32_t CHUNK_ROWS = 65532;   // rows per chunk, multiple of R, < 2^16
 
 struct __align__(16) StageMeta {
-    uint32_t splat;     // fp * 0x01010101
     uint32_t flags;
+    uint32_t nrows;     // rows in this stage (1..R), 0 for an empty item
     uint32_t read;
-    uint32_t g0;        // first genome of the tile
+    uint32_t grp0;      // first 32-genome group of the tile
+    uint32_t mask[R][8];   // mask[r][p] = (fp_r bit p) ? 0 : ~0
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -70,21 +82,88 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
-// 0x01 in every byte of x that is zero
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
-    uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;   // bit 7 set iff low 7 bits non-zero
-    t = ~(t | x) & 0x80808080u;                      // bit 7 set iff the whole byte is zero
-    return t >> 7;
+// carry-save adder: (carry, sum) of three bit-planes
+__device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
+}
+
+// Vertical counters of one 32-genome group: value = ones + 2 twos + sum_l 2^l (c[l] + pend[l]),
+// l = 2..TOP-1; pend[l] is occupied iff bit (l-2) of the number of R-row blocks folded so far.
+struct Counters {
+    uint32_t ones, twos;
+    uint32_t c[TOP], pend[TOP];     // indices 0,1 unused (kept for static indexing)
+    __device__ __forceinline__ void reset() {
+        ones = twos = 0;
+        #pragma unroll
+        for (int l = 0; l < TOP; ++l) { c[l] = 0; pend[l] = 0; }
+    }
+    // fold four 1-bit planes (one R-row block); nblk = blocks folded before this one
+    __device__ __forceinline__ void add4(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t nblk) {
+        uint32_t ta, tb, carry;
+        csa(ta, ones, ones, e0, e1);
+        csa(tb, ones, ones, e2, e3);
+        csa(carry, twos, twos, ta, tb);          // carry has weight 4
+        // binary counter with one pending slot per level: amortised ~2 CSAs per block
+        bool go = true;
+        #pragma unroll
+        for (int l = 2; l < TOP; ++l) {
+            if (go) {
+                if ((nblk >> (l - 2)) & 1u) {    // slot occupied: combine, carry on
+                    uint32_t nc;
+                    csa(nc, c[l], c[l], pend[l], carry);
+                    carry = nc;
+                } else {                          // slot free: park the carry here
+                    pend[l] = carry;
+                    go = false;
+                }
+            }
+        }
+    }
+    // resolve pending slots and return the TOP planes (plane l has weight 2^l)
+    __device__ __forceinline__ void planes(uint32_t nblk, uint32_t (&P)[32]) {
+        uint32_t carry = 0;
+        P[0] = ones;
+        P[1] = twos;
+        #pragma unroll
+        for (int l = 2; l < TOP; ++l) {
+            const uint32_t x = ((nblk >> (l - 2)) & 1u) ? pend[l] : 0u;
+            uint32_t nc, s;
+            csa(nc, s, c[l], x, carry);
+            P[l] = s;
+            carry = nc;
+        }
+        #pragma unroll
+        for (int l = TOP; l < 32; ++l) P[l] = 0;
+    }
+};
+
+// 32 x 32 bit-matrix transpose (LSB-first): out[g] bit l = in[l] bit g
+__device__ __forceinline__ void transpose32(uint32_t (&A)[32]) {
+    uint32_t m = 0x0000FFFFu;
+    #pragma unroll
+    for (int j = 16; j != 0; j >>= 1) {
+        #pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((A[k] >> j) ^ A[k + j]) & m;
+            A[k] ^= t << j;
+            A[k + j] ^= t;
+        }
+        m ^= m << (j >> 1);
+    }
 }
 
 template <int J>
-__global__ void __launch_bounds__(544, 1)
-scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_genomes, uint32_t n_pad,
+__global__ void __launch_bounds__(384, 1)
+scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups, uint32_t n_pad,
             const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
-            const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t tile_w,
-            uint32_t n_tiles, int stages, uint32_t stage_bytes, uint32_t* __restrict__ counts,
+            const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t tile_groups,
+            uint32_t n_tiles, int stages, uint32_t row_bytes, uint32_t* __restrict__ counts,
             uint32_t* __restrict__ work_counter) {
+    // stage s: R rows of row_bytes (= 32 * tile_groups: half 0 then half 1)
     extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t stage_bytes = R * row_bytes;
     uint8_t* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
@@ -100,26 +179,13 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_genome
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const uint32_t half = row_bytes >> 1;        // bytes of one half in a stage row
 
     if (warp == (n_cons >> 5)) {
         // ---------------- producer warp ----------------
         int stage = 0;
         uint32_t phase = 0;
         const uint64_t n_items = (uint64_t)n_reads * n_tiles;
-        auto emit = [&](uint32_t splat, uint32_t flags, uint32_t q, uint32_t g0, const uint8_t* src,
-                        uint32_t bytes) {
-            if (lane == 0) {
-                mbar_wait(empty + stage, phase ^ 1);
-                meta[stage] = StageMeta{splat, flags, q, g0};
-                if (flags & F_ROW) {
-                    mbar_arrive_expect_tx(full + stage, bytes);
-                    bulk_g2s(ring + (size_t)stage * stage_bytes, src, bytes, full + stage);
-                } else {
-                    mbar_arrive(full + stage);
-                }
-            }
-            if (++stage == stages) { stage = 0; phase ^= 1; }
-        };
         for (;;) {
             unsigned long long item = 0;
             if (lane == 0) item = atomicAdd(work_counter, 1u);
@@ -127,100 +193,139 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_genome
             if (item >= n_items) break;
             const uint32_t q = (uint32_t)(item / n_tiles);
             const uint32_t t = (uint32_t)(item % n_tiles);
-            const uint32_t g0 = t * tile_w;
-            const uint32_t w = (n_genomes - g0 < tile_w) ? (n_genomes - g0) : tile_w;
-            const uint32_t bytes = (w + 15u) & ~15u;          // rows are padded to 128
+            const uint32_t grp0 = t * tile_groups;
+            const uint32_t gcount = (n_groups - grp0 < tile_groups) ? (n_groups - grp0) : tile_groups;
+            const uint32_t hbytes = gcount * 16u;             // bytes per half row of this tile
             const uint32_t L = list_len[q];
             const uint32_t* lst = list + list_off[q];
-            if (L == 0) {
-                emit(0, F_FIRST | F_LAST, q, g0, nullptr, 0);
-                continue;
-            }
-            for (uint32_t base = 0; base < L; base += 32) {
-                const uint32_t mine = (base + lane < L) ? __ldg(lst + base + lane) : 0u;
-                const uint32_t cnt = (L - base < 32u) ? (L - base) : 32u;
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    const uint32_t e = __shfl_sync(0xffffffffu, mine, (int)i);
-                    uint32_t flags = F_ROW;
-                    if (base + i == 0) flags |= F_FIRST;
-                    if (base + i == L - 1) flags |= F_LAST;
-                    emit((e & 0xFFu) * 0x01010101u, flags, q, g0,
-                         rows + (uint64_t)(e >> 8) * stride + g0, bytes);
+            const uint8_t* src0 = rows + (uint64_t)grp0 * 16u;
+            const uint8_t* src1 = src0 + (stride >> 1);
+            uint32_t done = 0;                                // rows of this item already issued
+            do {
+                // lanes 0..R-1 fetch the entries of this stage
+                const uint32_t nr = (L - done < (uint32_t)R) ? (L - done) : (uint32_t)R;
+                const uint32_t e = ((uint32_t)lane < nr) ? __ldg(lst + done + lane) : 0u;
+                const uint32_t in_chunk = done % CHUNK_ROWS;
+                uint32_t flags = 0;
+                if (in_chunk == 0) flags |= F_FIRST;
+                if (done + nr == L || in_chunk + nr == CHUNK_ROWS) flags |= F_LAST;
+                if (done >= CHUNK_ROWS) flags |= F_ACCUM;
+                if (lane == 0) mbar_wait(empty + stage, phase ^ 1);
+                __syncwarp();
+                StageMeta* m = meta + stage;
+                if ((uint32_t)lane < nr) {
+                    const uint32_t fp = e & 0xFFu;
+                    #pragma unroll
+                    for (int p = 0; p < 8; ++p) m->mask[lane][p] = ((fp >> p) & 1u) ? 0u : 0xFFFFFFFFu;
                 }
-            }
+                if (lane == 0) {
+                    m->flags = flags;
+                    m->nrows = nr;
+                    m->read = q;
+                    m->grp0 = grp0;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (nr) mbar_arrive_expect_tx(full + stage, nr * 2u * hbytes);
+                    else mbar_arrive(full + stage);
+                }
+                __syncwarp();
+                if ((uint32_t)lane < nr) {
+                    const uint64_t roff = (uint64_t)(e >> 8) * stride;
+                    uint8_t* dst = ring + (size_t)stage * stage_bytes + (size_t)lane * row_bytes;
+                    bulk_g2s(dst, src0 + roff, hbytes, full + stage);
+                    bulk_g2s(dst + half, src1 + roff, hbytes, full + stage);
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+                done += nr;
+            } while (done < L);
         }
-        emit(0, F_END, 0, 0, nullptr, 0);
+        if (lane == 0) {
+            mbar_wait(empty + stage, phase ^ 1);
+            meta[stage].flags = F_END;
+            meta[stage].nrows = 0;
+            mbar_arrive(full + stage);
+        }
     } else {
         // ---------------- consumers ----------------
         int stage = 0;
         uint32_t phase = 0;
-        uint32_t acc8[J][4];
-        uint32_t acc32[J][16];
-        uint32_t pending = 0;                       // rows folded into acc8 since the last spill
+        Counters cnt[J];
+        uint32_t nblk = 0;
         #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            #pragma unroll
-            for (int w = 0; w < 4; ++w) acc8[j][w] = 0;
-            #pragma unroll
-            for (int i = 0; i < 16; ++i) acc32[j][i] = 0;
-        }
-        auto spill = [&]() {
-            #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc32[j][4 * w + b] += (acc8[j][w] >> (8 * b)) & 0xFFu;
-                    acc8[j][w] = 0;
-                }
-            }
-            pending = 0;
-        };
+        for (int j = 0; j < J; ++j) cnt[j].reset();
         for (;;) {
             mbar_wait(full + stage, phase);
-            const StageMeta m = meta[stage];
-            if (m.flags & F_END) break;
-            if (m.flags & F_FIRST) {
+            const StageMeta* m = meta + stage;
+            const uint32_t flags = m->flags;
+            if (flags & F_END) break;
+            const uint32_t nr = m->nrows;
+            const uint32_t q = m->read, grp0 = m->grp0;
+            if (flags & F_FIRST) {
                 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    #pragma unroll
-                    for (int w = 0; w < 4; ++w) acc8[j][w] = 0;
-                    #pragma unroll
-                    for (int i = 0; i < 16; ++i) acc32[j][i] = 0;
-                }
-                pending = 0;
+                for (int j = 0; j < J; ++j) cnt[j].reset();
+                nblk = 0;
             }
-            if (m.flags & F_ROW) {
-                const uint4* row = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes);
+            if (nr) {
+                uint32_t e[J][R];
+                const uint8_t* base = ring + (size_t)stage * stage_bytes;
                 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const uint32_t col = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;   // 16-byte group
-                    if (col * 16u < stage_bytes) {
-                        const uint4 v = row[col];
-                        acc8[j][0] += zero_bytes(v.x ^ m.splat);
-                        acc8[j][1] += zero_bytes(v.y ^ m.splat);
-                        acc8[j][2] += zero_bytes(v.z ^ m.splat);
-                        acc8[j][3] += zero_bytes(v.w ^ m.splat);
+                for (int r = 0; r < R; ++r) {
+                    if ((uint32_t)r < nr) {
+                        const uint4 m0 = *reinterpret_cast<const uint4*>(&m->mask[r][0]);
+                        const uint4 m1 = *reinterpret_cast<const uint4*>(&m->mask[r][4]);
+                        #pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const uint32_t g = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;   // group in tile
+                            uint32_t x = 0;
+                            if (g < tile_groups) {
+                                const uint4 a = *reinterpret_cast<const uint4*>(base + (size_t)r * row_bytes + 16u * g);
+                                const uint4 b = *reinterpret_cast<const uint4*>(base + (size_t)r * row_bytes + half + 16u * g);
+                                x = a.x ^ m0.x;
+                                x = (a.y ^ m0.y) & x;
+                                x = (a.z ^ m0.z) & x;
+                                x = (a.w ^ m0.w) & x;
+                                x = (b.x ^ m1.x) & x;
+                                x = (b.y ^ m1.y) & x;
+                                x = (b.z ^ m1.z) & x;
+                                x = (b.w ^ m1.w) & x;
+                            }
+                            e[j][r] = x;
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < J; ++j) e[j][r] = 0;
                     }
                 }
-                ++pending;
+                #pragma unroll
+                for (int j = 0; j < J; ++j) cnt[j].add4(e[j][0], e[j][1], e[j][2], e[j][3], nblk);
+                ++nblk;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);       // stage may be refilled
             if (++stage == stages) { stage = 0; phase ^= 1; }
-            if (pending == 255u || (m.flags & F_LAST)) spill();
-            if (m.flags & F_LAST) {
-                const uint32_t w = (n_genomes - m.g0 < tile_w) ? (n_genomes - m.g0) : tile_w;
-                uint32_t* out = counts + (uint64_t)m.read * n_pad + m.g0;
+            if (flags & F_LAST) {
+                const uint32_t gcount = (n_groups - grp0 < tile_groups) ? (n_groups - grp0) : tile_groups;
                 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const uint32_t c0 = ((uint32_t)threadIdx.x + (uint32_t)n_cons * j) * 16u;
-                    if (c0 < w) {                    // n_pad is a multiple of 16: whole group fits
-                        uint4* o = reinterpret_cast<uint4*>(out + c0);
-                        #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            o[v] = make_uint4(acc32[j][4 * v], acc32[j][4 * v + 1], acc32[j][4 * v + 2],
-                                              acc32[j][4 * v + 3]);
+                    const uint32_t g = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;
+                    if (g < gcount) {
+                        uint32_t P[32];
+                        cnt[j].planes(nblk, P);
+                        transpose32(P);                       // P[i] = count of genome 32 (grp0+g) + i
+                        uint4* o = reinterpret_cast<uint4*>(counts + (uint64_t)q * n_pad + 32ull * (grp0 + g));
+                        if (flags & F_ACCUM) {
+                            #pragma unroll
+                            for (int v = 0; v < 8; ++v) {
+                                uint4 old = o[v];
+                                o[v] = make_uint4(old.x + P[4 * v], old.y + P[4 * v + 1], old.z + P[4 * v + 2],
+                                                  old.w + P[4 * v + 3]);
+                            }
+                        } else {
+                            #pragma unroll
+                            for (int v = 0; v < 8; ++v)
+                                o[v] = make_uint4(P[4 * v], P[4 * v + 1], P[4 * v + 2], P[4 * v + 3]);
+                        }
                     }
                 }
             }
@@ -232,34 +337,40 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_genome
 
 int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out) {
     if (n_genomes == 0) return -1;
-    const uint32_t MAXW = 16384;                   // widest tile: 512 threads x 2 groups x 16 B
-    const uint32_t n16 = (n_genomes + 15) / 16;    // 16-byte groups per row
-    uint32_t n_tiles = (n_genomes + MAXW - 1) / MAXW;
-    uint32_t g_per_tile = (n16 + n_tiles - 1) / n_tiles;   // groups per tile
-    // threads x J >= g_per_tile with the least idle lanes; prefer small J (more threads)
+    const uint32_t MAXG = 512;                     // widest tile: 512 groups = 16,384 genomes
+    const uint32_t G = (n_genomes + 31) / 32;      // 32-genome groups per row
+    const uint32_t n_tiles = (G + MAXG - 1) / MAXG;
+    const uint32_t tg = (G + n_tiles - 1) / n_tiles;
+    // threads x J >= tg with the least idle lanes; prefer small J (more warps in flight)
     int best_t = 0, best_j = 0;
     uint32_t best_waste = ~0u;
     for (int j = 1; j <= MAX_J; ++j) {
-        uint32_t t = (g_per_tile + j - 1) / j;
+        uint32_t t = (tg + j - 1) / j;
         t = (t + 31) / 32 * 32;
-        if (t < 32) t = 32;
-        if (t > 512) continue;
-        const uint32_t waste = t * j - g_per_tile;
+        if (t > 352) continue;          // 11 consumer warps + the producer warp = 384 threads
+        const uint32_t waste = t * j - tg;
         if (waste < best_waste) { best_waste = waste; best_t = (int)t; best_j = j; }
     }
     if (!best_t) return -2;
     out->threads = best_t;
     out->J = best_j;
-    out->tile_w = g_per_tile * 16;
+    out->tile_w = tg * 32;
     out->n_tiles = n_tiles;
-    uint32_t stage_bytes = (out->tile_w + 127) / 128 * 128;
-    const size_t budget = smem_optin - 1024;       // static smem + alignment slack
-    int stages = (int)(budget / (stage_bytes + 2 * sizeof(uint64_t) + sizeof(StageMeta)));
+    const size_t row_bytes = (size_t)tg * 32;
+    const size_t per_stage = R * row_bytes + 2 * sizeof(uint64_t) + sizeof(StageMeta);
+    // Narrow tiles leave an SM with two or three warps, which cannot hide their own
+    // dependency chains: co-schedule several CTAs (each with its own ring and producer)
+    // until about a dozen warps are resident, as long as every ring keeps >= 4 stages.
+    const int warps = best_t / 32 + 1;
+    int ctas = std::max(1, std::min(8, 12 / warps));
+    auto ring_budget = [&](int n) { return (smem_optin - 1024) / (size_t)n - 1024; };
+    while (ctas > 1 && ring_budget(ctas) / per_stage < 4) --ctas;
+    int stages = (int)(ring_budget(ctas) / per_stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return -3;
     out->stages = stages;
-    out->smem = (size_t)stages * (stage_bytes + 2 * sizeof(uint64_t) + sizeof(StageMeta));
-    out->grid = sm_count;
+    out->smem = (size_t)stages * per_stage + 128;
+    out->grid = sm_count * ctas;
     return 0;
 }
 
@@ -275,14 +386,15 @@ static int launch_scan_j(const ScanPlan& plan, const uint8_t* rows, uint64_t str
             return -1;
         configured = plan.smem;
     }
-    const uint32_t stage_bytes = (plan.tile_w + 127) / 128 * 128;
-    const uint32_t n_pad = (n_genomes + 15) / 16 * 16;
+    const uint32_t tg = plan.tile_w / 32;
+    const uint32_t n_groups = (n_genomes + 31) / 32;
+    const uint32_t n_pad = n_groups * 32;
     uint64_t items = (uint64_t)n_reads * plan.n_tiles;
     int grid = plan.grid;
     if ((uint64_t)grid > items) grid = (int)(items ? items : 1);
     scan_kernel<J><<<grid, plan.threads + 32, plan.smem, st>>>(
-        rows, stride, n_genomes, n_pad, list, list_off, list_len, n_reads, plan.tile_w, plan.n_tiles,
-        plan.stages, stage_bytes, counts, work_counter);
+        rows, stride, n_groups, n_pad, list, list_off, list_len, n_reads, tg, plan.n_tiles, plan.stages,
+        tg * 32, counts, work_counter);
     return 0;
 }
 

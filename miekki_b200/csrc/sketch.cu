@@ -209,23 +209,92 @@ bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint8_t* _
     }
 }
 
-// fp[s][b] -> rows[b][col0 + s] through a 32 x 32 shared-memory transpose, so that both the
-// reads (along b) and the writes (along the genome axis) are contiguous.
+// ---- bit-plane row layout (see scan.cu) ------------------------------------------------
+// row b = [half 0 | half 1] (stride/2 bytes each); group j = genomes 32j..32j+31 keeps planes
+// 0-3 as one uint4 at half0 + 16 j and planes 4-7 at half1 + 16 j; bit i of plane p = bit p of
+// the fingerprint of genome 32 j + i.  An untouched row is all ones (every fingerprint 255).
+__device__ __forceinline__ uint4* plane_ptr(uint8_t* rows, uint64_t stride, uint64_t b, uint32_t group,
+                                            int half) {
+    return reinterpret_cast<uint4*>(rows + b * stride + (half ? (stride >> 1) : 0) + 16ull * group);
+}
+
+// fp[s][b] (s = genome col0 + s) -> plane bits.  One thread per bucket: reads along b are
+// contiguous across the warp; the read-modify-write touches the <= 2 groups the chunk spans.
 __global__ void __launch_bounds__(256)
-scatter_rows_kernel(const uint8_t* __restrict__ fp, uint32_t n_seq, int h, uint8_t* __restrict__ rows,
-                    uint64_t stride, uint32_t col0) {
-    __shared__ uint8_t tile[32][33];
-    const uint32_t B = 1u << h;
-    const uint32_t b0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
-    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    for (uint32_t r = ty; r < 32; r += 8) {
-        const uint32_t s = s0 + r, b = b0 + tx;
-        tile[r][tx] = (s < n_seq && b < B) ? fp[((uint64_t)s << h) + b] : (uint8_t)EMPTY_FP;
+scatter_planes_kernel(const uint8_t* __restrict__ fp, uint32_t n_seq, int h, uint8_t* __restrict__ rows,
+                      uint64_t stride, uint32_t col0) {
+    const uint64_t B = 1ull << h;
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t g_first = col0 >> 5, g_last = (col0 + n_seq - 1) >> 5;
+    for (uint32_t grp = g_first; grp <= g_last; ++grp) {
+        const uint32_t lo = max(col0, grp << 5), hi = min(col0 + n_seq, (grp + 1) << 5);
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t mask = 0;
+        for (uint32_t g = lo; g < hi; ++g) {
+            const uint32_t f = fp[((uint64_t)(g - col0) << h) + b];
+            const uint32_t bit = g & 31u;
+            mask |= 1u << bit;
+            #pragma unroll
+            for (int p = 0; p < 8; ++p) w[p] |= ((f >> p) & 1u) << bit;
+        }
+        #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint4* q = plane_ptr(rows, stride, b, grp, half);
+            uint4 v = *q;
+            v.x = (v.x & ~mask) | w[4 * half + 0];
+            v.y = (v.y & ~mask) | w[4 * half + 1];
+            v.z = (v.z & ~mask) | w[4 * half + 2];
+            v.w = (v.w & ~mask) | w[4 * half + 3];
+            *q = v;
+        }
     }
-    __syncthreads();
-    for (uint32_t r = ty; r < 32; r += 8) {
-        const uint32_t b = b0 + r, s = s0 + tx;
-        if (s < n_seq && b < B) rows[(uint64_t)b * stride + col0 + s] = tile[tx][r];
+}
+
+// plane layout -> dense bytes out[(b - row0) * n + g] for rows [row0, row0 + nrows) (dump)
+__global__ void __launch_bounds__(256)
+planes_to_bytes_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint64_t row0, uint64_t nrows,
+                       uint32_t n, uint8_t* __restrict__ out) {
+    const uint32_t groups = (n + 31) / 32;
+    const uint64_t total = nrows * groups;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / groups;
+        const uint32_t grp = (uint32_t)(i % groups);
+        const uint4 a = *plane_ptr(const_cast<uint8_t*>(rows), stride, row0 + r, grp, 0);
+        const uint4 c = *plane_ptr(const_cast<uint8_t*>(rows), stride, row0 + r, grp, 1);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        const uint32_t cnt = min(32u, n - grp * 32);
+        uint8_t* o = out + r * n + (uint64_t)grp * 32;
+        for (uint32_t g = 0; g < cnt; ++g) {
+            uint32_t f = 0;
+            #pragma unroll
+            for (int p = 0; p < 8; ++p) f |= ((w[p] >> g) & 1u) << p;
+            o[g] = (uint8_t)f;
+        }
+    }
+}
+
+// dense bytes in[(b - row0) * in_stride + g] -> plane layout (load); columns >= n become 255
+__global__ void __launch_bounds__(256)
+bytes_to_planes_kernel(const uint8_t* __restrict__ in, uint64_t in_stride, uint64_t row0, uint64_t nrows,
+                       uint32_t n, uint8_t* __restrict__ rows, uint64_t stride) {
+    const uint32_t groups = (n + 31) / 32;
+    const uint64_t total = nrows * groups;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / groups;
+        const uint32_t grp = (uint32_t)(i % groups);
+        const uint32_t cnt = min(32u, n - grp * 32);
+        const uint8_t* src = in + r * in_stride + (uint64_t)grp * 32;
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t g = 0; g < 32; ++g) {
+            const uint32_t f = g < cnt ? src[g] : 255u;
+            #pragma unroll
+            for (int p = 0; p < 8; ++p) w[p] |= ((f >> p) & 1u) << g;
+        }
+        *plane_ptr(rows, stride, row0 + r, grp, 0) = make_uint4(w[0], w[1], w[2], w[3]);
+        *plane_ptr(rows, stride, row0 + r, grp, 1) = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
 
@@ -451,11 +520,25 @@ void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint3
     bloom_commit_kernel<<<grid, 256, 0, st>>>(anc, fp, p, bloom, owner);
 }
 
-void launch_scatter_rows(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
-                         uint32_t col0, cudaStream_t st) {
+void launch_scatter_planes(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
+                           uint32_t col0, cudaStream_t st) {
     if (!n_seq) return;
-    dim3 grid(((1u << h) + 31) / 32, (n_seq + 31) / 32);
-    scatter_rows_kernel<<<grid, 256, 0, st>>>(fp, n_seq, h, rows, stride, col0);
+    scatter_planes_kernel<<<(unsigned)(((1ull << h) + 255) / 256), 256, 0, st>>>(fp, n_seq, h, rows, stride, col0);
+}
+
+void launch_planes_to_bytes(const uint8_t* rows, uint64_t stride, uint64_t row0, uint64_t nrows, uint32_t n,
+                            uint8_t* out, cudaStream_t st) {
+    if (!nrows || !n) return;
+    const uint64_t total = nrows * ((n + 31) / 32);
+    planes_to_bytes_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, st>>>(rows, stride, row0, nrows, n, out);
+}
+
+void launch_bytes_to_planes(const uint8_t* in, uint64_t in_stride, uint64_t row0, uint64_t nrows, uint32_t n,
+                            uint8_t* rows, uint64_t stride, cudaStream_t st) {
+    if (!nrows || !n) return;
+    const uint64_t total = nrows * ((n + 31) / 32);
+    bytes_to_planes_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, st>>>(in, in_stride, row0, nrows, n, rows,
+                                                                          stride);
 }
 
 void launch_compact_list(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,

@@ -129,7 +129,7 @@ void launch_topk(const uint32_t* counts, uint32_t n_reads, uint32_t n_genomes, u
                  uint32_t min_score, double min_intersection, HitDev* heap, uint32_t* len,
                  int finalize, cudaStream_t st) {
     if (!n_reads) return;
-    const uint32_t n_pad = (n_genomes + 15) / 16 * 16;
+    const uint32_t n_pad = (n_genomes + 31) / 32 * 32;
     topk_kernel<<<(n_reads + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(
         counts, n_reads, n_genomes, n_pad, first_id, sketch_size, genome_size, nresults, min_score,
         min_intersection, heap, len, finalize);
