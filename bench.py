@@ -281,16 +281,13 @@ def main():
     total_genomes = a.genomes * (world if a.impl == "ours" else 1)
     if world > 1 and a.impl == "ours":
         # global Bloom filter: byte-wise "lowest rank wins" 
+        from miekki_b200 import sharded
         w = ix.bloom_window()
         mine = torch.empty(w, dtype=torch.uint8, device="cuda")
         ix.bloom_get_ptr(mine.data_ptr(), w)
-        allb = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allb, mine)
-        merged = allb[0]
-        for r in range(1, world):
-            merged = torch.where(merged != 0, merged, allb[r])
-        ix.bloom_set_ptr(merged.contiguous().data_ptr(), w)
-        del allb, merged, mine
+        merged = sharded.merge_bloom(mine).contiguous()
+        ix.bloom_set_ptr(merged.data_ptr(), w)
+        del merged, mine
 
     reads_np, offsets, rlens = make_reads(a, total_genomes)
     read_kbp = a.reads * a.read_len / 1e3
@@ -338,14 +335,8 @@ def main():
 
     def chained_topk():
         """N > 1: bounded heap chained through the ranks in ascending genome-id order."""
-        if rank > 0:
-            dist.recv(d_heap, src=rank - 1)
-            dist.recv(d_len, src=rank - 1)
-        ix.topk_ptr(d_heap.data_ptr(), d_len.data_ptr(), K, 10, min_int,
-                    chain_in=rank > 0, finalize=rank == world - 1)
-        if rank < world - 1:
-            dist.send(d_heap, dst=rank + 1)
-            dist.send(d_len, dst=rank + 1)
+        from miekki_b200 import sharded
+        sharded.chained_topk(ix, d_heap, d_len, K, 10, min_int)
 
     def step_resident():
         if world == 1:

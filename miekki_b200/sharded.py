@@ -1,0 +1,63 @@
+"""Genome-sharded runs: one process per GPU, `torch.distributed` for the plumbing.
+
+The index partitions by genome (matrix columns), so a query needs exactly two exchanges
+ and no index byte ever crosses NVLink:
+
+* after the build, the global Bloom filter: byte-wise "lowest rank with a non-zero byte wins"
+  (exact because each byte belongs to the smallest (genome id, bucket, probe) that maps to
+  it and shards are contiguous ascending id ranges);
+* after each rank has scanned its own columns, the bounded heap of Miekki.cpp:386-393 is
+  passed through the ranks in ascending id order (24 bytes x nresults per read), which
+  reproduces the sequential filter exactly, ties included; the last rank applies sort_heap.
+
+The functions are backend-agnostic: tensors live on the GPU with NCCL, or on the CPU with gloo
+(tests/test_sharded_cpu.py drives them with world_size 2 and an oracle-backed engine).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+HIT_BYTES = 24          # sizeof(mk_hit)
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous ascending ids [first, first + count) of `rank`: [r N / R, (r+1) N / R)."""
+    first = rank * n_total // world
+    return first, (rank + 1) * n_total // world - first
+
+
+def fold_bloom(tables: list[torch.Tensor]) -> torch.Tensor:
+    """tables[r] = Bloom bytes of rank r; the lowest rank's non-zero byte wins."""
+    merged = tables[0].clone()
+    for t in tables[1:]:
+        merged = torch.where(merged != 0, merged, t)
+    return merged
+
+
+def merge_bloom(local: torch.Tensor, group=None) -> torch.Tensor:
+    """All ranks end with the Bloom table a single in-order build would have produced."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    tables = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(tables, local, group=group)
+    return fold_bloom(tables)
+
+
+def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, min_score: int,
+                 min_intersection: float, group=None) -> None:
+    """heap: uint8 [n_reads, nresults * 24], lens: int32 [n_reads], on the engine's device.
+    `engine.topk_ptr(heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in,
+    finalize)` applies this rank's stored counts to the heap state in place.
+    After the call the LAST rank holds the final hit lists."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if rank > 0:
+        dist.recv(heap, src=rank - 1, group=group)
+        dist.recv(lens, src=rank - 1, group=group)
+    engine.topk_ptr(heap.data_ptr(), lens.data_ptr(), nresults, min_score, min_intersection,
+                    chain_in=rank > 0, finalize=rank == world - 1)
+    if rank < world - 1:
+        dist.send(heap, dst=rank + 1, group=group)
+        dist.send(lens, dst=rank + 1, group=group)

@@ -1,0 +1,89 @@
+"""The `miekki` command line (C++ host over the C ABI) against the reference binary's golden
+outputs: same flags, same hit lines, same exact-mode lines, and a gz dump the reference's own
+format parser reads back byte for byte (header byte 32 masked: quirk G7)."""
+import os
+import subprocess
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(H.ROOT, "miekki_b200", "cli", "miekki")
+
+
+def run_cli(args, cwd):
+    assert os.path.exists(CLI), "build the CLI first: make"
+    r = subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("s", [200, 0, 5000])
+def test_cli_build_query_dump(tmp_path, s):
+    d = os.path.join(H.GOLDEN, "caseA")
+    out, dump = tmp_path / "hits.txt", tmp_path / "idx.gz"
+    stdout = run_cli(["-l", "list.txt", "-a", "reads.fa", "-k", 31, "-h", 12, "-t", 4, "-s", s,
+                      "-o", out, "-d", dump], d)
+    assert "Reference indexed: 14" in stdout and stdout.count("elapsed time:") == 2
+    assert "Using 8 bits per minimizer, 4,096 minimizers so 32,768 bits per sequences" in stdout
+    assert out.read_text() == open(os.path.join(d, "hits_s%d.txt" % s)).read()
+    if s == 200:
+        got = orc.parse_dump(str(dump))
+        z = H.load_dump_npz(os.path.join(d, "dump.npz"))
+        assert (got.k, got.h, got.nbm, got.nbmant, got.n, got.b) == (31, 12, 8, 5, 14, 33)
+        assert got.bloom_bits == 1 << 33 and got.threshold == 200 and got.compressed == 1
+        assert np.array_equal(got.rows, z["rows"])
+        assert np.array_equal(got.genome_size, z["genome_size"])
+        assert np.array_equal(got.sketch_size, z["sketch_size"])
+        idx, val = H.bloom_nonzero(got.bloom)
+        assert np.array_equal(idx, z["bloom_idx"]) and np.array_equal(val, z["bloom_val"])
+        # -i: load our own dump, query again (flags -k/-h/-s ignored: quirk G6)
+        out2 = tmp_path / "hits2.txt"
+        stdout = run_cli(["-i", dump, "-a", os.path.join(d, "reads.fa"), "-o", out2, "-k", 21, "-s", 1], d)
+        assert "Load sucessful" in stdout
+        assert out2.read_text() == open(os.path.join(d, "hits_s200.txt")).read()
+
+
+@pytest.mark.parametrize("s,fname", [(200, "exact.txt"), (0, "exact_s0.txt")])
+def test_cli_exact_mode(tmp_path, s, fname):
+    d = os.path.join(H.GOLDEN, "caseA")
+    out = tmp_path / "exact.txt"
+    run_cli(["-l", "list.txt", "-a", "reads.fa", "-k", 31, "-h", 12, "-e", "-s", s, "-o", out], d)
+    got = [l for l in out.read_text().split("\n") if l]
+    want = [l for l in open(os.path.join(d, fname)).read().split("\n") if l]
+    assert Counter(got) == Counter(want)
+
+
+def test_cli_loads_reference_style_dump(tmp_path):
+    """A dump written the way the reference writes it (gzip, full 1 GiB Bloom table) loads."""
+    import gzip
+    d = os.path.join(H.GOLDEN, "caseA")
+    z = H.load_dump_npz(os.path.join(d, "dump.npz"))
+    bloom = np.zeros((1 << 33) // 8, np.uint8)
+    bloom[z["bloom_idx"]] = z["bloom_val"]
+    p = tmp_path / "ref.gz"
+    with gzip.open(p, "wb", compresslevel=1) as f:
+        f.write(np.array([31, 12, 8, 5, 14, 33], "<u4").tobytes())
+        f.write(np.array([1 << 33], "<u8").tobytes())
+        f.write(bytes([7, 0]))                       # garbage jaccard_estimation byte
+        f.write(np.array([200], "<u4").tobytes() + bytes([1]))
+        f.write(z["rows"].tobytes() + z["genome_size"].astype("<u8").tobytes())
+        f.write(bloom.tobytes())
+        f.write(z["sketch_size"].astype("<u4").tobytes())
+    out = tmp_path / "hits.txt"
+    run_cli(["-i", p, "-a", os.path.join(d, "reads.fa"), "-o", out], d)
+    assert out.read_text() == open(os.path.join(d, "hits_s200.txt")).read()
+
+
+def test_cli_messages(tmp_path):
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 0 and "This is a help message" in r.stdout
+    r = subprocess.run([CLI, "-a", "x.fa"], capture_output=True, text=True)
+    assert "What am I supposed to index ?" in r.stdout
+    r = subprocess.run([CLI, "-l", "nope.txt", "-f", "11", "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert "not implemented" in r.stdout            # quirk G12
