@@ -4,7 +4,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX := $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
+NVFLAGS := $(ARCH) -ccbin $(CXX) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
 SRC := miekki_b200/csrc
 OBJ := build/obj
 LIB := miekki_b200/libmiekki_b200.so
@@ -20,7 +20,7 @@ $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -ccbin $(CXX) -o $@ $(OBJS) -lpthread
 
 $(CLI): miekki_b200/cli/main.cpp miekki_b200/cli/fasta.hpp include/miekki_b200.h $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -Wextra -fopenmp -Iinclude -o $@ miekki_b200/cli/main.cpp \

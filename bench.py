@@ -401,10 +401,10 @@ def main():
         from miekki_b200 import synth
         m = a.build_e2e_genomes
         bx = miekki_b200.Miekki(k=a.k, h=a.hbits, b=33, threshold=a.threshold, device=local)
-        bx.reserve(m)
+        bx.reserve(2 * m)
         hosts = [synth.cb_bases(SEED, g, 0, a.genome_len).tobytes() for g in range(min(m, 8))]
         seqs = [hosts[i % len(hosts)] for i in range(m)]
-        bx.insert_sequences(seqs[:8])                      # warm-up
+        bx.insert_sequences(seqs)                          # warm-up: same call, sizes all scratch
         t0 = time.perf_counter()
         bx.insert_sequences(seqs)
         dt = time.perf_counter() - t0
@@ -446,7 +446,10 @@ def main():
                          "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(st["scan_row_bytes"] // max(1, st["scan_launches"])),
                          "launch_ms": st["scan_ms"] / max(1, st["scan_launches"]),
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         # ncu's DRAM bytes per algorithmic byte (one capture), scaled to this launch size
+                         "traffic": (int(traffic["dram_bytes_per_algorithmic_byte"] *
+                                         (st["scan_row_bytes"] // max(1, st["scan_launches"])))
+                                     if traffic else None),
                          "traffic_source": (traffic or {}).get("source")},
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/miekki_b200.h"
@@ -57,6 +58,7 @@ struct mk_ctx {
     int device = 0, sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t aux_stream = nullptr;     // top-k of one count tile overlaps the scan of the next
     std::mutex mu;
     std::string err;
 
@@ -71,7 +73,7 @@ struct mk_ctx {
     uint32_t* owner = nullptr;
     uint64_t window = 0;          // bytes, multiple of 16
 
-    DevBuf planeF, planeR, keys, fp, meta, list, list_len, counts, heap, heap_len, misc;
+    DevBuf planeF, planeR, keys, fp, meta, list, list_len, counts, counts2, heap, heap_len, misc;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint32_t* d_work = nullptr;
@@ -151,14 +153,15 @@ cudaEvent_t get_event(mk_ctx* c) {
 struct PhaseTimer {
     mk_ctx* c;
     PendingEvent pe;
-    PhaseTimer(mk_ctx* ctx, int phase) : c(ctx) {
+    cudaStream_t st;
+    PhaseTimer(mk_ctx* ctx, int phase, cudaStream_t stream = nullptr) : c(ctx), st(stream ? stream : ctx->stream) {
         pe.a = get_event(c);
         pe.b = get_event(c);
         pe.phase = phase;
-        cudaEventRecord(pe.a, c->stream);
+        cudaEventRecord(pe.a, st);
     }
     ~PhaseTimer() {
-        cudaEventRecord(pe.b, c->stream);
+        cudaEventRecord(pe.b, st);
         c->ev_pending.push_back(pe);
     }
 };
@@ -265,6 +268,25 @@ void batch_release(mk_batch* b) {
     delete b;
 }
 
+// memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 takes ~50)
+void parallel_memcpy(char* dst, const char* src, size_t n) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), n / (2u << 20));
+    if (nt <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (n / nt + 63) & ~(size_t)63;
+    for (unsigned t = 1; t < nt; ++t) {
+        const size_t o = (size_t)t * per;
+        if (o >= n) break;
+        th.emplace_back([=] { memcpy(dst + o, src + o, std::min(per, n - o)); });
+    }
+    memcpy(dst, src, std::min(per, n));
+    for (auto& x : th) x.join();
+}
+
 // gathers sequences [first, first+n) of (seqs, lens) into a new device batch
 int upload_range(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, mk_batch** out) {
     mk_batch* b = new mk_batch();
@@ -276,12 +298,33 @@ int upload_range(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint3
     if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     const bool big = n && (b->bases / n) >= (1u << 20);
     if (big) {
-        // few long sequences (genomes): copy each straight from the caller's memory
-        for (uint32_t i = 0; i < n; ++i) {
-            if (!lens[i]) continue;
-            e = cudaMemcpyAsync(b->chars + b->h_coff[i], seqs[i], lens[i], cudaMemcpyHostToDevice, c->stream);
-            if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
+        // few long sequences (genomes) in pageable memory: a ring of pinned pieces, filled by a
+        // few host threads while the previous pieces are in flight over PCIe
+        constexpr size_t PIECE = 16u << 20;
+        constexpr int SLOTS = 4;
+        r = reserve_pinned(c, PIECE * SLOTS);
+        if (r != MK_OK) { batch_release(b); return r; }
+        char* st = static_cast<char*>(c->pinned);
+        cudaEvent_t ev[SLOTS];
+        bool used[SLOTS] = {false, false, false, false};
+        for (int s = 0; s < SLOTS; ++s) ev[s] = get_event(c);
+        int slot = 0;
+        for (uint32_t i = 0; i < n && e == cudaSuccess; ++i) {
+            for (uint64_t off = 0; off < lens[i] && e == cudaSuccess; off += PIECE) {
+                const size_t m = (size_t)std::min<uint64_t>(PIECE, lens[i] - off);
+                if (used[slot]) e = cudaEventSynchronize(ev[slot]);
+                if (e != cudaSuccess) break;
+                parallel_memcpy(st + (size_t)slot * PIECE, seqs[i] + off, m);
+                e = cudaMemcpyAsync(b->chars + b->h_coff[i] + off, st + (size_t)slot * PIECE, m,
+                                    cudaMemcpyHostToDevice, c->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[slot], c->stream);
+                used[slot] = true;
+                slot = (slot + 1) % SLOTS;
+            }
         }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // staging is reused by the next call
+        for (int s = 0; s < SLOTS; ++s) c->ev_pool.push_back(ev[s]);
+        if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     } else if (n) {
         // many short sequences (reads): pack into pinned staging, one copy
         r = reserve_pinned(c, b->h_coff[n] + 64);
@@ -340,7 +383,7 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
     TRY(reserve(c, c->planeF, (w + 4) * 4));
     TRY(reserve(c, c->planeR, (w + 4) * 4));
     TRY(reserve(c, c->keys, (size_t)n * c->B * 8));
-    TRY(reserve(c, c->fp, (size_t)n * c->B));
+    TRY(reserve(c, c->fp, (size_t)n * c->B * 2));     // fp[n][B] | Bloom claim flags[n][B]
     const size_t meta_bytes = ((size_t)n + 1) * 8 + (size_t)n * 8 + (size_t)n * 8;
     TRY(reserve(c, c->meta, meta_bytes));
     uint64_t* d_woff = static_cast<uint64_t*>(c->meta.p);
@@ -523,12 +566,13 @@ uint32_t scan_batch_reads(const mk_ctx* c, uint32_t n_reads) {
     return (uint32_t)q;
 }
 
-// scans reads [q0, q0+nq) into c->counts
-int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPlan& plan) {
+// scans reads [q0, q0+nq) into `counts` (default: c->counts)
+int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPlan& plan,
+               uint32_t* counts = nullptr) {
     PhaseTimer t(c, PH_SCAN);
     CU(cudaMemsetAsync(c->d_work, 0, 4, c->stream));
     int r = launch_scan(plan, c->rows, c->stride, c->n, L.list, L.list_off + q0, L.list_len + q0, nq,
-                        static_cast<uint32_t*>(c->counts.p), c->d_work, c->stream);
+                        counts ? counts : static_cast<uint32_t*>(c->counts.p), c->d_work, c->stream);
     if (r != 0) return fail(c, MK_ERR_CUDA, "scan launch configuration failed");
     c->stats.kernel_launches += 1;
     c->stats.scan_launches += 1;
@@ -574,19 +618,45 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
         ScanPlan plan{};
         if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
             return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
-        const uint32_t qb = scan_batch_reads(c, n);
+        // Sub-batches of reads, two count tiles: the top-k of tile i runs on the aux stream
+        // while the (DRAM-bound, persistent) scan of tile i+1 runs on the main one.
+        const uint32_t qb = std::max<uint32_t>(1, scan_batch_reads(c, n) / 2);
         const uint64_t n_pad = (c->n + 31) / 32 * 32;
         TRY(reserve(c, c->counts, (size_t)qb * n_pad * 4));
-        for (uint32_t q0 = 0; q0 < n; q0 += qb) {
+        TRY(reserve(c, c->counts2, (size_t)qb * n_pad * 4));
+        uint32_t* tile[2] = {static_cast<uint32_t*>(c->counts.p), static_cast<uint32_t*>(c->counts2.p)};
+        cudaEvent_t scanned[2] = {get_event(c), get_event(c)}, done[2] = {get_event(c), get_event(c)};
+        bool busy[2] = {false, false};
+        int rc = MK_OK;
+        uint32_t i = 0;
+        for (uint32_t q0 = 0; q0 < n && rc == MK_OK; q0 += qb, ++i) {
             const uint32_t nq = std::min(qb, n - q0);
-            TRY(scan_reads(c, L, q0, nq, plan));
-            PhaseTimer t(c, PH_TOPK);
-            launch_topk(static_cast<uint32_t*>(c->counts.p), nq, c->n, c->first_id, c->d_sketch_size,
-                        c->d_genome_size, K, min_score, min_int, d_heap + (size_t)q0 * K, d_hlen + q0,
-                        finalize, c->stream);
+            const int s = (int)(i & 1);
+            if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);     // tile s is free again
+            rc = scan_reads(c, L, q0, nq, plan, tile[s]);
+            if (rc != MK_OK) break;
+            cudaEventRecord(scanned[s], c->stream);
+            cudaStreamWaitEvent(c->aux_stream, scanned[s], 0);
+            {
+                PhaseTimer t(c, PH_TOPK, c->aux_stream);
+                launch_topk(tile[s], nq, c->n, c->first_id, c->d_sketch_size, c->d_genome_size, K, min_score,
+                            min_int, d_heap + (size_t)q0 * K, d_hlen + q0, finalize, c->aux_stream);
+            }
+            cudaEventRecord(done[s], c->aux_stream);
+            busy[s] = true;
             c->stats.kernel_launches += 1;
-            CU(cudaGetLastError());
         }
+        for (int s = 0; s < 2; ++s)
+            if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);
+        cudaError_t le = cudaGetLastError();
+        if (cudaStreamSynchronize(c->aux_stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+            le != cudaSuccess)
+            rc = rc != MK_OK ? rc : fail(c, MK_ERR_CUDA, std::string("query pipeline: ") + cudaGetErrorString(le));
+        for (int s = 0; s < 2; ++s) {
+            c->ev_pool.push_back(scanned[s]);
+            c->ev_pool.push_back(done[s]);
+        }
+        if (rc != MK_OK) return rc;
     }
     if (heap_io) {
         CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDeviceToHost, c->stream));
@@ -710,6 +780,7 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
         cudaGetLastError();
     }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->bloom, ctx->window);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->owner, ctx->window * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work, 16);
@@ -730,8 +801,9 @@ void mk_destroy(mk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
-                      &c->heap, &c->heap_len, &c->misc})
+                      &c->counts2, &c->heap, &c->heap_len, &c->misc})
         if (b->p) cudaFree(b->p);
     for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->bloom,
                     (void*)c->owner, (void*)c->d_work})
@@ -740,6 +812,7 @@ void mk_destroy(mk_ctx* c) {
     for (auto& pe : c->ev_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     delete c;
 }
 

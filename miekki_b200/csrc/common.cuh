@@ -65,6 +65,27 @@ struct BloomProbe {
     }
 };
 
+// The probe offsets are < 1024 < 2^(b+3), so the five probes fall in at most two adjacent
+// table bytes.  For claiming / writing a byte only the FIRST probe that maps to it matters
+// (smallest probe index wins, Miekki.cpp:122-129 in probe order).  Returns the number of
+// distinct bytes (1 or 2); slot[j] / probe[j] describe that first probe.
+__device__ __forceinline__ int bloom_first_probes(const BloomProbe& pr, uint32_t b, uint64_t (&slot)[2],
+                                                  uint32_t (&probe)[2]) {
+    slot[0] = pr.slot(0, b);
+    probe[0] = 0;
+    int n = 1;
+    #pragma unroll
+    for (uint32_t i = 1; i < 5; ++i) {
+        const uint64_t s = pr.slot(i, b);
+        if (n == 1 && (s >> 3) != (slot[0] >> 3)) {
+            slot[1] = s;
+            probe[1] = i;
+            n = 2;
+        }
+    }
+    return n;
+}
+
 // Bloom_Filter bytes are only ever zero or one power of two (insert writes 1 << bit into
 // a zero byte, Miekki.cpp:127-128); membership is "all five bytes non-zero" (:141).
 __device__ __forceinline__ bool bloom_check(const uint8_t* __restrict__ table, uint64_t window,

@@ -165,12 +165,19 @@ resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __rest
             sum = 1ull << (31 - (fp >> 3));       // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
             if (owner != nullptr) {               // Bloom pass A (Miekki.cpp:295-299)
                 BloomProbe pr(anc);
-                #pragma unroll
-                for (uint32_t i = 0; i < 5; ++i) {
-                    const uint64_t byte = pr.slot(i, p.bloom_log2) >> 3;
-                    if (byte < p.bloom_window && bloom[byte] == 0)
-                        atomicMin(owner + byte, owner_key(s, b, i, p.h));
+                uint64_t slot[2];
+                uint32_t probe[2];
+                const int nd = bloom_first_probes(pr, p.bloom_log2, slot, probe);
+                uint8_t claimed = 0;
+                for (int j = 0; j < nd; ++j) {
+                    const uint64_t byte = slot[j] >> 3;
+                    if (byte < p.bloom_window && bloom[byte] == 0) {
+                        atomicMin(owner + byte, owner_key(s, b, probe[j], p.h));
+                        claimed = 1;
+                    }
                 }
+                // claim flags live behind the fp block: pass B only revisits claimants
+                fp_out[((uint64_t)gridDim.y << p.h) + idx] = claimed;
             }
         }
         keys_anc[idx] = anc;
@@ -197,14 +204,16 @@ bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint8_t* _
     if (b >= B) return;
     const uint64_t idx = ((uint64_t)s << p.h) + b;
     if (fp[idx] == EMPTY_FP) return;
+    if (fp[((uint64_t)gridDim.y << p.h) + idx] == 0) return;    // made no claim in pass A
     BloomProbe pr(anc[idx]);
-    #pragma unroll
-    for (uint32_t i = 0; i < 5; ++i) {
-        const uint64_t slot = pr.slot(i, p.bloom_log2);
-        const uint64_t byte = slot >> 3;
-        if (byte < p.bloom_window && owner[byte] == owner_key(s, b, i, p.h)) {
-            bloom[byte] = (uint8_t)(1u << (slot & 7));   // Miekki.cpp:128
-            owner[byte] = 0xFFFFFFFFu;                   // the winner also clears its claim
+    uint64_t slot[2];
+    uint32_t probe[2];
+    const int nd = bloom_first_probes(pr, p.bloom_log2, slot, probe);
+    for (int j = 0; j < nd; ++j) {
+        const uint64_t byte = slot[j] >> 3;
+        if (byte < p.bloom_window && owner[byte] == owner_key(s, b, probe[j], p.h)) {
+            bloom[byte] = (uint8_t)(1u << (slot[j] & 7));   // Miekki.cpp:128
+            owner[byte] = 0xFFFFFFFFu;                      // the winner also clears its claim
         }
     }
 }
