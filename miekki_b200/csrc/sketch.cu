@@ -338,7 +338,7 @@ compact_list_kernel(const unsigned long long* __restrict__ anc, const uint8_t* _
 //   slot = bucket << 40 | fp << 32 | position ; ~0 = empty.  Linear probing; a slot is claimed
 //   by its bucket with atomicCAS and then lowered with atomicMin, which orders (fp, position)
 //   because the bucket bits above them are equal.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 sketch_reads_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
                     const uint64_t* __restrict__ len, const uint32_t* __restrict__ read_ids,
                     uint32_t n_ids, uint32_t max_words, uint32_t slots, SketchParams p,
@@ -588,7 +588,9 @@ int launch_sketch_reads(const uint8_t* chars, const uint64_t* coff, const uint64
         configured = smem;
     }
     const unsigned grid = n_ids < 148u * 32u ? n_ids : 148u * 32u;
-    sketch_reads_kernel<<<grid, 128, smem, st>>>(chars, coff, len, read_ids, n_ids, words, slots, p,
+    // a long read owns most of an SM's shared memory: give it enough warps to hide latency
+    const unsigned threads = slots >= 8192 ? 512u : slots >= 4096 ? 256u : 128u;
+    sketch_reads_kernel<<<grid, threads, smem, st>>>(chars, coff, len, read_ids, n_ids, words, slots, p,
                                                  bloom, list_off, list, list_len);
     return 0;
 }

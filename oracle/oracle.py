@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         L.mko_sketch.restype = C.c_uint32
         L.mko_sketch.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                  C.c_uint32, C.c_void_p, C.c_void_p]
+        L.mko_bloom_check.restype = C.c_int
+        L.mko_bloom_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         L.mko_bloom_window.restype = C.c_uint64
         L.mko_bloom_window.argtypes = [C.c_uint32, C.c_uint32]
         L.mko_index_new.restype = C.c_void_p
