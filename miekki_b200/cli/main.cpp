@@ -49,6 +49,7 @@ void help() {   // main.cpp:102-121
     cout << "-i load a constructed index from disk" << endl;
     cout << "-l construct an index from a list of file" << endl;
     cout << "-a query a fasta file" << endl;
+    cout << "-A query  fasta from file of file" << endl;
     cout << "\nOutput " << endl;
     cout << "-o output file name (out.txt)" << endl;
     cout << "-d dump the index on disk" << endl;
@@ -344,6 +345,125 @@ void query_file_exact(Index& ix, const string& path) {
     *ix.out << flush;
 }
 
+// ---- -A: whole-file queries, Miekki.cpp:487-514 + :592-612 ------------------------------------
+// Each listed file is one query: all non-header lines concatenated; a line `path:hits` is
+// written only when there are hits.  Files are parsed in parallel and scored in waves; lines
+// come out in list order (the reference's order for -t 1).
+void query_file_of_file(Index& ix, const string& list) {
+    if (!exists_test(list)) {
+        cout << "Missed file of file: " << list << endl;
+        return;
+    }
+    vector<string> names;
+    {
+        mkcli::LineReader in(list);
+        string name;
+        while (!in.eof()) {
+            in.getline(name);
+            if (name.size() > 3) names.push_back(name);          // :606
+        }
+    }
+    const size_t wave = max<size_t>(16, 2 * (size_t)ix.threads);
+    for (size_t w0 = 0; w0 < names.size(); w0 += wave) {
+        const size_t m = min(wave, names.size() - w0);
+        vector<string> seqs(m);
+        vector<char> ok(m, 0);
+        #pragma omp parallel for num_threads(ix.threads) schedule(dynamic, 1)
+        for (size_t i = 0; i < m; ++i) {
+            const string& fn = names[w0 + i];
+            if (!exists_test(fn)) {
+                #pragma omp critical(msg)
+                cout << "File problem" << endl;                  // :488
+                continue;
+            }
+            seqs[i] = mkcli::read_genome_concat(fn);             // :491-497
+            ok[i] = seqs[i].size() >= ix.k;                      // :498
+        }
+        ReadBatch b;
+        vector<size_t> which;
+        for (size_t i = 0; i < m; ++i) {
+            if (ok[i]) {
+                b.heads.push_back(names[w0 + i]);
+                b.seqs.push_back(std::move(seqs[i]));
+                which.push_back(i);
+            }
+            cout << "-" << flush;                                // :608
+        }
+        if (b.size() == 0) continue;
+        vector<mk_hit> hits;
+        vector<uint32_t> nhits;
+        run_query(ix, b, 10, 10, 0.5 * ix.threshold, hits, nhits);   // :500
+        for (size_t i = 0; i < b.size(); ++i) {
+            if (nhits[i] == 0) continue;                         // :506
+            string s;
+            for (uint32_t j = 0; j < nhits[i]; ++j) {
+                const mk_hit& sim = hits[i * 10 + j];
+                s += to_string(sim.genome) + "\t" + to_string(sim.matches) + "\t" +
+                     to_string((unsigned)sim.intersection) + "\t" + to_string(sim.jaccard) + ";";
+            }
+            *ix.out << b.heads[i] << ":" << s << "\n";           // :509
+        }
+    }
+    *ix.out << flush;
+}
+
+// ---- -A -e: Miekki.cpp:616-645 + :763-788 -------------------------------------------------
+// The query is the file's lines after the first that are at least k long and start with one of
+// ACGTN (shorter lines are dropped, :771); candidates = filter_results(..., 5, 5, threshold).
+void query_file_of_file_exact(Index& ix, const string& list) {
+    if (!exists_test(list)) {
+        cout << "Missed file of file: " << list << endl;
+        return;
+    }
+    if (ix.file_names.empty()) {
+        cerr << "miekki: exact mode needs the genome list (-l) in the same run" << endl;
+        return;
+    }
+    vector<string> names;
+    {
+        mkcli::LineReader in(list);
+        string name;
+        while (!in.eof()) {
+            in.getline(name);
+            if (name.size() > 3) names.push_back(name);
+        }
+    }
+    map<uint32_t, vector<Candidate>> per_genome;
+    ReadBatch b;
+    for (const string& fn : names) {
+        cout << "-" << flush;
+        if (!exists_test(fn)) {
+            cout << "File problem" << endl;
+            continue;
+        }
+        mkcli::LineReader in(fn);
+        string ref, head, line;
+        in.getline(head);                                        // :768
+        while (!in.eof()) {
+            in.getline(line);
+            if (line.size() < ix.k) continue;                    // :771
+            const char c = line[0];
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') continue;
+            ref += line;
+        }
+        if (ref.size() <= ix.k) continue;       // the reference sketches nothing here: no hits
+        b.heads.push_back(head);
+        b.seqs.push_back(std::move(ref));
+    }
+    if (b.size()) {
+        vector<mk_hit> hits;
+        vector<uint32_t> nhits;
+        run_query(ix, b, 5, 5, (double)ix.threshold, hits, nhits);   // :778
+        for (size_t i = 0; i < b.size(); ++i)
+            for (uint32_t j = 0; j < nhits[i]; ++j) {
+                const mk_hit& sim = hits[i * 5 + j];
+                per_genome[sim.genome].push_back({b.seqs[i], b.heads[i], sim.jaccard, sim.intersection});
+            }
+    }
+    for (auto& kv : per_genome) ground_truth(ix, ix.file_names[kv.first], kv.second);
+    *ix.out << flush;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -426,7 +546,13 @@ int main(int argc, char** argv) {
             query_file(ix, query_fa);
         }
     } else if (!query_list.empty()) {
-        cout << "-A (whole-file queries) is not part of this build; see DESIGN.md, out of scope" << endl;
+        if (exact_mode) {
+            cout << "running in exact mode, actual intersection will be computed on hits found by the index" << endl;
+            query_file_of_file_exact(ix, query_list);
+        } else {
+            cout << "running in approx mode, intersection is estimated by the index" << endl;
+            query_file_of_file(ix, query_list);
+        }
     } else {
         cout << "No query file, No queries" << endl;
     }

@@ -143,6 +143,45 @@ def case_a():
         shutil.copy(os.path.join(tmp, "exact0.txt"), os.path.join(d, "exact_s0.txt"))
 
 
+def case_a_whole_files():
+    """-A: whole-file queries (Miekki.cpp:487-514, :592-612) and -A -e (:616-645, :763-788)."""
+    d = os.path.join(HERE, "caseA")
+    qd = os.path.join(d, "qfiles")
+    os.makedirs(qd, exist_ok=True)
+    genomes = [H_genome(os.path.join(d, "gA%d.fa.gz" % g)) for g in range(14)]
+    rng = np.random.default_rng(79)
+    specs = [(0, 1000, 31000), (1, 20000, 52000), (3, 500, 9000), (7, 0, 100000), (5, 900, 7000)]
+    names = []
+    for i, (g, a, b) in enumerate(specs):
+        seq = synth.substitute(np.frombuffer(genomes[g][a:b], np.uint8), 0.01, rng).tobytes()
+        name = "qfiles/q%d.fa" % i
+        with open(os.path.join(d, name), "wb") as f:
+            f.write(b">whole%d from gA%d\n" % (i, g))
+            for o in range(0, len(seq), 60):
+                f.write(seq[o:o + 60] + b"\n")
+        names.append(name)
+    with open(os.path.join(d, "qfiles/short.fa"), "wb") as f:      # shorter than k: no output line
+        f.write(b">short\nACGTACGTAC\n")
+    names.append("qfiles/short.fa")
+    with open(os.path.join(d, "qfiles/unrelated.fa"), "wb") as f:  # no hits: -A prints nothing
+        f.write(b">unrelated\n" + synth.genome(998, 4000) + b"\n")
+    names.append("qfiles/unrelated.fa")
+    with open(os.path.join(d, "alist.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    with tempfile.TemporaryDirectory() as tmp:
+        run_ref(d, ["-l", "list.txt", "-A", "alist.txt", "-k", 31, "-h", 12, "-t", 1,
+                    "-o", os.path.join(tmp, "a.txt")])
+        shutil.copy(os.path.join(tmp, "a.txt"), os.path.join(d, "hits_A.txt"))
+        run_ref(d, ["-l", "list.txt", "-A", "alist.txt", "-k", 31, "-h", 12, "-t", 1, "-e",
+                    "-o", os.path.join(tmp, "ae.txt")])
+        shutil.copy(os.path.join(tmp, "ae.txt"), os.path.join(d, "exact_A.txt"))
+
+
+def H_genome(path):
+    with gzip.open(path, "rb") as f:
+        return b"".join(l for l in f.read().split(b"\n") if l[:1] != b">")
+
+
 def case_b():
     a = os.path.join(HERE, "caseA")
     d = os.path.join(HERE, "caseB")
@@ -199,6 +238,7 @@ if __name__ == "__main__":
     if not REF.available:
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     case_a()
+    case_a_whole_files()
     case_b()
     case_c()
     print("golden vectors written under", HERE)

@@ -59,6 +59,19 @@ def test_cli_exact_mode(tmp_path, s, fname):
     assert Counter(got) == Counter(want)
 
 
+def test_cli_whole_file_queries(tmp_path):
+    """-A and -A -e: whole files as queries, long-sequence sketch path."""
+    d = os.path.join(H.GOLDEN, "caseA")
+    out = tmp_path / "a.txt"
+    run_cli(["-l", "list.txt", "-A", "alist.txt", "-k", 31, "-h", 12, "-t", 3, "-o", out], d)
+    assert out.read_text() == open(os.path.join(d, "hits_A.txt")).read()
+    oute = tmp_path / "ae.txt"
+    run_cli(["-l", "list.txt", "-A", "alist.txt", "-k", 31, "-h", 12, "-e", "-o", oute], d)
+    got = [l for l in oute.read_text().split("\n") if l]
+    want = [l for l in open(os.path.join(d, "exact_A.txt")).read().split("\n") if l]
+    assert Counter(got) == Counter(want) and len(want) > 10
+
+
 def test_cli_loads_reference_style_dump(tmp_path):
     """A dump written the way the reference writes it (gzip, full 1 GiB Bloom table) loads."""
     import gzip
