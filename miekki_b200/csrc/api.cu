@@ -67,6 +67,7 @@ struct mk_ctx {
     uint32_t n = 0, cap = 0, first_id = 0;
     uint32_t* d_sketch_size = nullptr;
     uint64_t* d_genome_size = nullptr;
+    float* d_ratio = nullptr;     // float(genome_size / sketch_size), screen of the top-k kernel
     std::vector<uint32_t> h_sketch_size;
     std::vector<uint64_t> h_genome_size;
     uint8_t* bloom = nullptr;
@@ -213,15 +214,33 @@ int ensure_capacity(mk_ctx* c, uint32_t need) {
         CU(cudaMemcpyAsync(nss, c->d_sketch_size, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(ngs, c->d_genome_size, (size_t)c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
+    float* nratio = nullptr;
+    CU(cudaMalloc(&nratio, (size_t)ncap * 4));
+    CU(cudaMemsetAsync(nratio, 0, (size_t)ncap * 4, c->stream));
+    if (c->n) CU(cudaMemcpyAsync(nratio, c->d_ratio, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->rows) CU(cudaFree(c->rows));
     if (c->d_sketch_size) CU(cudaFree(c->d_sketch_size));
     if (c->d_genome_size) CU(cudaFree(c->d_genome_size));
+    if (c->d_ratio) CU(cudaFree(c->d_ratio));
     c->rows = nrows;
     c->d_sketch_size = nss;
     c->d_genome_size = ngs;
+    c->d_ratio = nratio;
     c->cap = ncap;
     c->stride = ncap;
+    return MK_OK;
+}
+
+// ratio[g] = float(genome_size / sketch_size) for ids [first, first + n): the top-k screen
+int upload_ratio(mk_ctx* c, uint32_t first, uint32_t n) {
+    if (!n) return MK_OK;
+    std::vector<float> r(n);
+    for (uint32_t i = 0; i < n; ++i)
+        r[i] = (float)((double)c->h_genome_size[first + i] / (double)c->h_sketch_size[first + i]);
+    CU(cudaMemcpyAsync(c->d_ratio + first, r.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (size_t)n * 4;
     return MK_OK;
 }
 
@@ -455,6 +474,7 @@ int index_add_view(mk_ctx* c, const mk_batch* b) {
         CU(cudaStreamSynchronize(c->stream));
         c->h_sketch_size.insert(c->h_sketch_size.end(), act.begin(), act.end());
         c->h_genome_size.insert(c->h_genome_size.end(), gs.begin(), gs.end());
+        TRY(upload_ratio(c, c->n, n));
         c->n += n;
         c->stats.bases_sketched += v.bases;
         c->stats.d2h_bytes += (size_t)n * 12;
@@ -639,7 +659,7 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
             cudaStreamWaitEvent(c->aux_stream, scanned[s], 0);
             {
                 PhaseTimer t(c, PH_TOPK, c->aux_stream);
-                launch_topk(tile[s], nq, c->n, c->first_id, c->d_sketch_size, c->d_genome_size, K, min_score,
+                launch_topk(tile[s], nq, c->n, c->first_id, c->d_sketch_size, c->d_genome_size, c->d_ratio, K, min_score,
                             min_int, d_heap + (size_t)q0 * K, d_hlen + q0, finalize, c->aux_stream);
             }
             cudaEventRecord(done[s], c->aux_stream);
@@ -711,7 +731,7 @@ int topk_stored(mk_ctx* c, uint32_t K, uint32_t min_score, double min_int, mk_hi
     if (c->n > 0) {
         PhaseTimer t(c, PH_TOPK);
         launch_topk(static_cast<uint32_t*>(c->counts.p), n, c->n, c->first_id, c->d_sketch_size,
-                    c->d_genome_size, K, min_score, min_int, d_heap, d_hlen, finalize, c->stream);
+                    c->d_genome_size, c->d_ratio, K, min_score, min_int, d_heap, d_hlen, finalize, c->stream);
         c->stats.kernel_launches += 1;
         CU(cudaGetLastError());
     } else if (finalize) {
@@ -805,7 +825,7 @@ void mk_destroy(mk_ctx* c) {
     for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
                       &c->counts2, &c->heap, &c->heap_len, &c->misc})
         if (b->p) cudaFree(b->p);
-    for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->bloom,
+    for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->d_ratio, (void*)c->bloom,
                     (void*)c->owner, (void*)c->d_work})
         if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1043,6 +1063,7 @@ int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_st
     CU(cudaStreamSynchronize(c->stream));
     c->h_sketch_size.assign(sketch_size, sketch_size + n);
     c->h_genome_size.assign(genome_size, genome_size + n);
+    TRY(upload_ratio(c, 0, n));
     c->n = n;
     return MK_OK;
 }

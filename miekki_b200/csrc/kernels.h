@@ -78,9 +78,10 @@ int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint
 struct HitDev { uint32_t genome, matches; double jaccard, intersection; };
 // heap: n_reads x nresults HitDev, len: n_reads.  chained across shards (first_id offsets).
 void launch_topk(const uint32_t* counts, uint32_t n_reads, uint32_t n_genomes, uint32_t first_id,
-                 const uint32_t* sketch_size, const uint64_t* genome_size, uint32_t nresults,
-                 uint32_t min_score, double min_intersection, HitDev* heap, uint32_t* len,
-                 int finalize, cudaStream_t st);
+                 const uint32_t* sketch_size, const uint64_t* genome_size, const float* ratio,
+                 uint32_t nresults, uint32_t min_score, double min_intersection, HitDev* heap,
+                 uint32_t* len, int finalize, cudaStream_t st);
+// ratio[g] = float(genome_size[g] / sketch_size[g]): the top-k kernel's cheap screen
 
 // ---- exact.cu -------------------------------------------------------------------
 // open-addressing exact sets of canonical k-mers (utils.cpp:276 str2num); tables pre-set to ~0

@@ -60,9 +60,9 @@ __device__ __forceinline__ void pop(HitDev* a, int n) {
 __global__ void __launch_bounds__(WARPS * 32)
 topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_genomes, uint32_t n_pad,
             uint32_t first_id, const uint32_t* __restrict__ sketch_size,
-            const uint64_t* __restrict__ genome_size, uint32_t K, uint32_t min_score,
-            double min_intersection, HitDev* __restrict__ heap_io, uint32_t* __restrict__ len_io,
-            int finalize) {
+            const uint64_t* __restrict__ genome_size, const float* __restrict__ ratio, uint32_t K,
+            uint32_t min_score, double min_intersection, HitDev* __restrict__ heap_io,
+            uint32_t* __restrict__ len_io, int finalize) {
     __shared__ HitDev heaps[WARPS][MAX_RESULTS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t q = blockIdx.x * WARPS + warp;
@@ -82,9 +82,17 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
         if (g < n_genomes) {
             sc = cq[g];
             if (sc >= min_score) {                                     // :381
-                jac = (double)sc / (double)sketch_size[g];             // :382
-                x = jac * (double)genome_size[g];                      // :383
-                cand = !(x < min_intersection);                        // :384
+                // Cheap exact-safe screen: ratio[g] = float(genome_size / sketch_size), so
+                // sc * ratio is within 3 * 2^-24 of the f64 value below.  A candidate whose
+                // upper bound is still under the heap minimum would be skipped at :387 and
+                // leaves no trace, so the f64 divide is spent only on possible entrants
+                // (NaN / inf ratios fail the test and take the exact path).
+                const double ub = (double)((float)sc * ratio[g]) * 1.000001;
+                if (!(len >= K && ub < hmin)) {
+                    jac = (double)sc / (double)sketch_size[g];         // :382
+                    x = jac * (double)genome_size[g];                  // :383
+                    cand = !(x < min_intersection);                    // :384
+                }
             }
         }
         // :386-387 with the heap as it stood at the start of this step
@@ -125,13 +133,13 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
 }  // namespace
 
 void launch_topk(const uint32_t* counts, uint32_t n_reads, uint32_t n_genomes, uint32_t first_id,
-                 const uint32_t* sketch_size, const uint64_t* genome_size, uint32_t nresults,
-                 uint32_t min_score, double min_intersection, HitDev* heap, uint32_t* len,
-                 int finalize, cudaStream_t st) {
+                 const uint32_t* sketch_size, const uint64_t* genome_size, const float* ratio,
+                 uint32_t nresults, uint32_t min_score, double min_intersection, HitDev* heap,
+                 uint32_t* len, int finalize, cudaStream_t st) {
     if (!n_reads) return;
     const uint32_t n_pad = (n_genomes + 31) / 32 * 32;
     topk_kernel<<<(n_reads + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(
-        counts, n_reads, n_genomes, n_pad, first_id, sketch_size, genome_size, nresults, min_score,
+        counts, n_reads, n_genomes, n_pad, first_id, sketch_size, genome_size, ratio, nresults, min_score,
         min_intersection, heap, len, finalize);
 }
 
