@@ -1,12 +1,17 @@
 // miekki -- command line of the B200-native sketch-and-query path.
 //
-// Drop-in for the reference's main.cpp:125-238 on the flags -l -a -o -d -i -h -k -s -f -b
+// Drop-in for the reference's main.cpp:125-238 on the flags -l -a -A -o -d -i -h -k -s -f -b
 // -e -t: same getopt string, same defaults (h=17, t=8, k=31, b=33, f=3, s=200, out.txt), same
 // hit-line format (Miekki.cpp:438-445), exact-line format (Miekki.cpp:853) and gz index dump
 // (Miekki.cpp:649-719).  The host keeps file parsing (plain/gz FASTA) and text formatting;
 // sketching, scoring, filtering and the exact intersection run on the GPU through the C ABI
 // in include/miekki_b200.h.  Genome ids are list order (the reference's `-t 1` order) for any
 // -t; -t only sets the number of host parser threads.
+//
+// --gpus N shards the genomes (matrix columns) over N GPUs of the box in contiguous ascending
+// id ranges: every GPU builds and scans its own columns, the Bloom table is
+// folded "lowest shard wins" after the build and the bounded heap is chained through the
+// shards in id order, so every output byte is the same as with one GPU.
 #include <getopt.h>
 #include <omp.h>
 #include <sys/stat.h>
@@ -20,6 +25,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fasta.hpp"
@@ -63,7 +69,9 @@ void help() {   // main.cpp:102-121
     cout << "-b 2^b bits used for the bloom filter  " << endl;
     cout << "-e exact mode, real intersection will be computed on hits" << endl;
     cout << "\nB200 " << endl;
-    cout << "--device N  CUDA device ordinal (0)" << endl;
+    cout << "--device N  first CUDA device ordinal (0)" << endl;
+    cout << "--gpus N    shard the genomes over N GPUs (1)" << endl;
+    cout << "--devices a,b,..  explicit device ordinal per shard" << endl;
 }
 
 [[noreturn]] void die(mk_ctx* ctx, const char* what) {
@@ -72,36 +80,76 @@ void help() {   // main.cpp:102-121
 }
 
 struct Index {
-    mk_ctx* ctx = nullptr;
+    vector<mk_ctx*> shard;               // one context per GPU; ids ascend with the shard number
+    vector<uint32_t> first;              // first genome id of each shard
     uint32_t k = 31, h = 17, nbm = 8, nbmant = 5, b = 33, threshold = 200;
     bool compressed_flag = false;        // header byte 38
     vector<string> file_names;           // Miekki.h:58; not part of the dump (quirk G4)
     ofstream* out = nullptr;
-    int threads = 8;
+    int threads = 8, device0 = 0, gpus = 1;
+    vector<int> devices;                 // --devices a,b,...: explicit ordinals (repeats allowed)
+
+    uint32_t size() const {
+        uint32_t n = 0, t = 0;
+        for (mk_ctx* c : shard) { mk_index_size(c, &t); n += t; }
+        return n;
+    }
+    void create_shards() {
+        shard.assign((size_t)gpus, nullptr);
+        for (int r = 0; r < gpus; ++r)
+            if (mk_create(k, h, nbm, nbmant, b, threshold, devices.empty() ? device0 + r : devices[(size_t)r],
+                          &shard[(size_t)r]) != MK_OK) {
+                cerr << "miekki: " << mk_last_error(nullptr) << endl;
+                exit(1);
+            }
+    }
+    // ids of the shards + the global Bloom table (byte-wise: the lowest shard's non-zero byte wins)
+    void seal_shards() {
+        first.assign(shard.size(), 0);
+        uint32_t acc = 0, t = 0;
+        for (size_t r = 0; r < shard.size(); ++r) {
+            first[r] = acc;
+            mk_set_shard(shard[r], acc);
+            mk_index_size(shard[r], &t);
+            acc += t;
+        }
+        if (shard.size() < 2) return;
+        const uint64_t w = mk_bloom_window(shard[0]);
+        vector<uint8_t> merged(w), other(w);
+        if (mk_bloom_get(shard[0], merged.data(), w) != MK_OK) die(shard[0], "mk_bloom_get");
+        for (size_t r = 1; r < shard.size(); ++r) {
+            if (mk_bloom_get(shard[r], other.data(), w) != MK_OK) die(shard[r], "mk_bloom_get");
+            #pragma omp parallel for num_threads(threads) schedule(static)
+            for (uint64_t i = 0; i < w; ++i)
+                if (merged[i] == 0) merged[i] = other[i];
+        }
+        for (mk_ctx* c : shard)
+            if (mk_bloom_set(c, merged.data(), w) != MK_OK) die(c, "mk_bloom_set");
+    }
 };
 
-// ---- build: Miekki::index_file_of_file, Miekki.cpp:540-588 ----------------------------------
-void index_file_of_file(Index& ix, const string& list) {
-    if (!exists_test(list)) {
-        cout << "Missed file of file: " << list << endl;
-        return;
-    }
+vector<string> read_list(const string& list) {
     vector<string> names;
-    {
-        mkcli::LineReader in(list);
-        string name;
-        while (!in.eof()) {
-            in.getline(name);
-            if (name.size() > 3) names.push_back(name);          // :555
-        }
+    mkcli::LineReader in(list);
+    string name;
+    while (!in.eof()) {
+        in.getline(name);
+        if (name.size() > 3) names.push_back(name);              // Miekki.cpp:555, :606
     }
+    return names;
+}
+
+// ---- build: Miekki::index_file_of_file, Miekki.cpp:540-588 ----------------------------------
+// files [lo, hi) of the list go to one shard, in list order
+void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo, size_t hi, int threads,
+                 vector<string>& kept) {
     // parse `wave` files in parallel, then insert in list order so that ids are deterministic
-    const size_t wave = max<size_t>(32, 4 * (size_t)ix.threads);
-    for (size_t w0 = 0; w0 < names.size(); w0 += wave) {
-        const size_t m = min(wave, names.size() - w0);
+    const size_t wave = max<size_t>(32, 4 * (size_t)threads);
+    for (size_t w0 = lo; w0 < hi; w0 += wave) {
+        const size_t m = min(wave, hi - w0);
         vector<string> seqs(m);
         vector<char> ok(m, 0);
-        #pragma omp parallel for num_threads(ix.threads) schedule(dynamic, 1)
+        #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
         for (size_t i = 0; i < m; ++i) {
             const string& fn = names[w0 + i];
             if (!exists_test(fn)) {
@@ -118,30 +166,65 @@ void index_file_of_file(Index& ix, const string& list) {
             if (!ok[i]) continue;
             ptr.push_back(seqs[i].data());
             len.push_back(seqs[i].size());
-            ix.file_names.push_back(names[w0 + i]);              // :303
+            kept.push_back(names[w0 + i]);                       // :303
+            #pragma omp critical(msg)
             cout << "-" << flush;                                // :575
         }
-        if (!ptr.empty() && mk_index_add(ix.ctx, ptr.data(), len.data(), (uint32_t)ptr.size()) != MK_OK)
-            die(ix.ctx, "mk_index_add");
+        if (!ptr.empty() && mk_index_add(ctx, ptr.data(), len.data(), (uint32_t)ptr.size()) != MK_OK)
+            die(ctx, "mk_index_add");
     }
-    uint32_t n = 0;
-    mk_index_size(ix.ctx, &n);
+}
+
+void index_file_of_file(Index& ix, const string& list) {
+    if (!exists_test(list)) {
+        cout << "Missed file of file: " << list << endl;
+        return;
+    }
+    const vector<string> names = read_list(list);
+    const size_t R = ix.shard.size();
+    vector<vector<string>> kept(R);
+    if (R == 1) {
+        build_shard(ix, ix.shard[0], names, 0, names.size(), ix.threads, kept[0]);
+    } else {
+        // contiguous slices of the list per GPU, built concurrently; nested OpenMP teams parse
+        omp_set_max_active_levels(2);
+        const int per = max(1, ix.threads / (int)R);
+        #pragma omp parallel for num_threads((int)R) schedule(static, 1)
+        for (size_t r = 0; r < R; ++r)
+            build_shard(ix, ix.shard[r], names, r * names.size() / R, (r + 1) * names.size() / R, per, kept[r]);
+    }
+    for (auto& v : kept) ix.file_names.insert(ix.file_names.end(), v.begin(), v.end());
+    ix.seal_shards();
     cout << endl;
-    cout << "Reference indexed: " << n << endl;                  // :583
+    cout << "Reference indexed: " << ix.size() << endl;          // :583
     cout << "BF size:" << int_to_string(1ull << ix.b) << endl;   // :585
 }
 
 // ---- dump / load: Miekki.cpp:649-719, SURVEY.md Appendix C -----------------------------------
 void dump_disk(Index& ix, const string& path) {
-    uint32_t n = 0;
-    mk_index_size(ix.ctx, &n);
+    const uint32_t n = ix.size();
     const uint64_t B = 1ull << ix.h;
     const uint64_t bloom_bits = 1ull << ix.b;
     vector<uint8_t> rows(B * (uint64_t)n), bloom(bloom_bits / 8);
     vector<uint64_t> gs(n);
     vector<uint32_t> ss(n);
-    if (mk_index_export(ix.ctx, rows.data(), gs.data(), bloom.data(), bloom.size(), ss.data()) != MK_OK)
-        die(ix.ctx, "mk_index_export");
+    if (ix.shard.size() == 1) {
+        if (mk_index_export(ix.shard[0], rows.data(), gs.data(), bloom.data(), bloom.size(), ss.data()) != MK_OK)
+            die(ix.shard[0], "mk_index_export");
+    } else {
+        // shard r owns columns [first[r], first[r] + n_r) of every row
+        for (size_t r = 0; r < ix.shard.size(); ++r) {
+            uint32_t nr = 0;
+            mk_index_size(ix.shard[r], &nr);
+            vector<uint8_t> part(B * (uint64_t)nr);
+            if (mk_index_export(ix.shard[r], part.data(), gs.data() + ix.first[r], r == 0 ? bloom.data() : nullptr,
+                                r == 0 ? bloom.size() : 0, ss.data() + ix.first[r]) != MK_OK)
+                die(ix.shard[r], "mk_index_export");
+            #pragma omp parallel for num_threads(ix.threads) schedule(static)
+            for (uint64_t b = 0; b < B; ++b)
+                memcpy(rows.data() + b * n + ix.first[r], part.data() + b * nr, nr);
+        }
+    }
     mkcli::GzWriter w(path);
     const uint8_t jaccard_estimation = 0;       // uninitialised in the reference (quirk G7)
     const uint8_t containment_estimation = 0;
@@ -164,7 +247,7 @@ void dump_disk(Index& ix, const string& path) {
     w.close();
 }
 
-bool load_disk(Index& ix, const string& path, int device) {
+bool load_disk(Index& ix, const string& path) {
     if (!exists_test(path)) {
         cout << "File problem" << endl;                          // :683-686
         return false;
@@ -185,10 +268,8 @@ bool load_disk(Index& ix, const string& path, int device) {
     memcpy(&ix.b, head + 20, 4);
     memcpy(&bloom_bits, head + 24, 8);
     memcpy(&ix.threshold, head + 34, 4);
-    if (mk_create(ix.k, ix.h, ix.nbm, ix.nbmant, ix.b, ix.threshold, device, &ix.ctx) != MK_OK) {
-        cerr << "miekki: " << mk_last_error(nullptr) << endl;
-        exit(1);
-    }
+    if ((uint32_t)ix.gpus > max(1u, n)) ix.gpus = (int)max(1u, n);
+    ix.create_shards();
     const uint64_t B = 1ull << ix.h;
     vector<uint8_t> rows(B * (uint64_t)n), bloom(bloom_bits / 8);
     vector<uint64_t> gs(n);
@@ -201,8 +282,14 @@ bool load_disk(Index& ix, const string& path, int device) {
         cerr << "miekki: truncated index dump" << endl;
         return false;
     }
-    if (mk_index_import(ix.ctx, n, rows.data(), n, gs.data(), bloom.data(), bloom.size(), ss.data()) != MK_OK)
-        die(ix.ctx, "mk_index_import");
+    const size_t R = ix.shard.size();
+    for (size_t r = 0; r < R; ++r) {
+        const uint32_t lo = (uint32_t)(r * (uint64_t)n / R), hi = (uint32_t)((r + 1) * (uint64_t)n / R);
+        if (mk_index_import(ix.shard[r], hi - lo, rows.data() + lo, n, gs.data() + lo, bloom.data(), bloom.size(),
+                            ss.data() + lo) != MK_OK)
+            die(ix.shard[r], "mk_index_import");
+    }
+    ix.seal_shards();      // every shard already holds the whole Bloom table: the fold is a no-op
     ix.compressed_flag = false;                                   // :705
     return true;
 }
@@ -243,9 +330,35 @@ void run_query(Index& ix, ReadBatch& b, uint32_t nresults, uint32_t min_score, d
     }
     hits.assign(n * nresults, mk_hit{});
     nhits.assign(n, 0);
-    if (mk_query(ix.ctx, ptr.data(), len.data(), (uint32_t)n, nresults, min_score, min_int, hits.data(),
-                 nhits.data()) != MK_OK)
-        die(ix.ctx, "mk_query");
+    const size_t R = ix.shard.size();
+    if (R == 1) {
+        if (mk_query(ix.shard[0], ptr.data(), len.data(), (uint32_t)n, nresults, min_score, min_int, hits.data(),
+                     nhits.data()) != MK_OK)
+            die(ix.shard[0], "mk_query");
+        return;
+    }
+    // every shard sketches the reads and scans its own columns concurrently ...
+    vector<mk_batch*> up(R, nullptr);
+    #pragma omp parallel for num_threads((int)R) schedule(static, 1)
+    for (size_t r = 0; r < R; ++r) {
+        if (mk_batch_upload(ix.shard[r], ptr.data(), len.data(), (uint32_t)n, &up[r]) != MK_OK)
+            die(ix.shard[r], "mk_batch_upload");
+        if (mk_scan(ix.shard[r], up[r]) != MK_OK) die(ix.shard[r], "mk_scan");
+    }
+    // ... then the bounded heap walks the shards in ascending id order (Miekki.cpp:379-394)
+    for (size_t r = 0; r < R; ++r) {
+        if (mk_topk(ix.shard[r], nresults, min_score, min_int, hits.data(), nhits.data(), r > 0, r + 1 == R) != MK_OK)
+            die(ix.shard[r], "mk_topk");
+        mk_batch_free(ix.shard[r], up[r]);
+    }
+}
+
+string hit_text(const mk_hit* h, uint32_t n) {                   // Miekki.cpp:442
+    string s;
+    for (uint32_t j = 0; j < n; ++j)
+        s += to_string(h[j].genome) + "\t" + to_string(h[j].matches) + "\t" +
+             to_string((unsigned)h[j].intersection) + "\t" + to_string(h[j].jaccard) + ";";
+    return s;
 }
 
 void query_file(Index& ix, const string& path) {
@@ -263,16 +376,8 @@ void query_file(Index& ix, const string& path) {
         run_query(ix, b, 10, 10, 0.5 * ix.threshold, hits, nhits);   // :437
         vector<string> lines(b.size());
         #pragma omp parallel for num_threads(ix.threads) schedule(static)
-        for (size_t i = 0; i < b.size(); ++i) {
-            string& s = lines[i];
-            s = b.heads[i] + ":";                                // :440
-            for (uint32_t j = 0; j < nhits[i]; ++j) {
-                const mk_hit& sim = hits[i * 10 + j];            // :442
-                s += to_string(sim.genome) + "\t" + to_string(sim.matches) + "\t" +
-                     to_string((unsigned)sim.intersection) + "\t" + to_string(sim.jaccard) + ";";
-            }
-            s += "\n";
-        }
+        for (size_t i = 0; i < b.size(); ++i)
+            lines[i] = b.heads[i] + ":" + hit_text(&hits[i * 10], nhits[i]) + "\n";   // :440-444
         for (const string& s : lines) *ix.out << s;
     }
     *ix.out << flush;
@@ -284,11 +389,14 @@ struct Candidate {
     double jaccard, intersection;
 };
 
-void ground_truth(Index& ix, const string& file, vector<Candidate>& v) {
-    if (v.empty()) return;
+// Miekki.cpp:792-859 for one genome file; returns the text block of its lines
+string ground_truth(Index& ix, mk_ctx* ctx, const string& file, vector<Candidate>& v) {
+    ostringstream os;
+    if (v.empty()) return "";
     if (!exists_test(file)) {
+        #pragma omp critical(msg)
         cout << "File problem: " << file << endl;                // :796-799
-        return;
+        return "";
     }
     vector<string> recs = mkcli::read_genome_records(file, ix.k);
     vector<const char*> rp(recs.size()), qp(v.size());
@@ -297,17 +405,32 @@ void ground_truth(Index& ix, const string& file, vector<Candidate>& v) {
     for (size_t i = 0; i < v.size(); ++i) { qp[i] = v[i].seq.data(); ql[i] = v[i].seq.size(); }
     vector<uint64_t> inter(v.size()), uni(v.size());
     uint64_t nB = 0;
-    if (mk_exact(ix.ctx, rp.data(), rl.data(), (uint32_t)recs.size(), qp.data(), ql.data(), (uint32_t)v.size(),
+    if (mk_exact(ctx, rp.data(), rl.data(), (uint32_t)recs.size(), qp.data(), ql.data(), (uint32_t)v.size(),
                  inter.data(), uni.data(), &nB) != MK_OK)
-        die(ix.ctx, "mk_exact");
+        die(ctx, "mk_exact");
     for (size_t i = 0; i < v.size(); ++i) {
         const double nb_inter = (double)inter[i], nb_union = (double)uni[i];
         if (nb_inter > 0) {                                      // :843
             const double real_jax = nb_inter / nb_union;         // :845-846
-            *ix.out << real_jax << "\t" << v[i].jaccard << "\t" << nb_inter << "\t" << v[i].intersection
-                    << "\t" << v[i].head << "\t" << file << "\n";   // :853
+            os << real_jax << "\t" << v[i].jaccard << "\t" << nb_inter << "\t" << v[i].intersection << "\t"
+               << v[i].head << "\t" << file << "\n";             // :853
         }
     }
+    return os.str();
+}
+
+// genomes are independent: one host thread per GPU works through them
+void ground_truth_all(Index& ix, map<uint32_t, vector<Candidate>>& per_genome) {
+    vector<pair<uint32_t, vector<Candidate>*>> work;
+    for (auto& kv : per_genome) work.push_back({kv.first, &kv.second});
+    vector<string> text(work.size());
+    const int R = (int)ix.shard.size();
+    #pragma omp parallel for num_threads(R) schedule(dynamic, 1)
+    for (size_t i = 0; i < work.size(); ++i)
+        text[i] = ground_truth(ix, ix.shard[(size_t)omp_get_thread_num() % ix.shard.size()],
+                               ix.file_names[work[i].first], *work[i].second);
+    for (const string& s : text) *ix.out << s;
+    per_genome.clear();
 }
 
 void query_file_exact(Index& ix, const string& path) {
@@ -326,11 +449,6 @@ void query_file_exact(Index& ix, const string& path) {
     vector<uint32_t> nhits;
     map<uint32_t, vector<Candidate>> per_genome;
     size_t held = 0;
-    auto flush_all = [&]() {
-        for (auto& kv : per_genome) ground_truth(ix, ix.file_names[kv.first], kv.second);
-        per_genome.clear();
-        held = 0;
-    };
     while (next_reads(in, ix.k, 1 << 14, b, true)) {
         run_query(ix, b, 5, 10, (double)ix.threshold, hits, nhits);   // :741
         for (size_t i = 0; i < b.size(); ++i)
@@ -339,9 +457,12 @@ void query_file_exact(Index& ix, const string& path) {
                 per_genome[sim.genome].push_back({b.seqs[i], b.heads[i], sim.jaccard, sim.intersection});
                 ++held;
             }
-        if (held > (1u << 20)) flush_all();      // the reference flushes per genome at 100 (:745)
+        if (held > (1u << 20)) {                 // the reference flushes per genome at 100 (:745)
+            ground_truth_all(ix, per_genome);
+            held = 0;
+        }
     }
-    flush_all();
+    ground_truth_all(ix, per_genome);
     *ix.out << flush;
 }
 
@@ -354,15 +475,7 @@ void query_file_of_file(Index& ix, const string& list) {
         cout << "Missed file of file: " << list << endl;
         return;
     }
-    vector<string> names;
-    {
-        mkcli::LineReader in(list);
-        string name;
-        while (!in.eof()) {
-            in.getline(name);
-            if (name.size() > 3) names.push_back(name);          // :606
-        }
-    }
+    const vector<string> names = read_list(list);
     const size_t wave = max<size_t>(16, 2 * (size_t)ix.threads);
     for (size_t w0 = 0; w0 < names.size(); w0 += wave) {
         const size_t m = min(wave, names.size() - w0);
@@ -380,12 +493,10 @@ void query_file_of_file(Index& ix, const string& list) {
             ok[i] = seqs[i].size() >= ix.k;                      // :498
         }
         ReadBatch b;
-        vector<size_t> which;
         for (size_t i = 0; i < m; ++i) {
             if (ok[i]) {
                 b.heads.push_back(names[w0 + i]);
                 b.seqs.push_back(std::move(seqs[i]));
-                which.push_back(i);
             }
             cout << "-" << flush;                                // :608
         }
@@ -393,16 +504,9 @@ void query_file_of_file(Index& ix, const string& list) {
         vector<mk_hit> hits;
         vector<uint32_t> nhits;
         run_query(ix, b, 10, 10, 0.5 * ix.threshold, hits, nhits);   // :500
-        for (size_t i = 0; i < b.size(); ++i) {
-            if (nhits[i] == 0) continue;                         // :506
-            string s;
-            for (uint32_t j = 0; j < nhits[i]; ++j) {
-                const mk_hit& sim = hits[i * 10 + j];
-                s += to_string(sim.genome) + "\t" + to_string(sim.matches) + "\t" +
-                     to_string((unsigned)sim.intersection) + "\t" + to_string(sim.jaccard) + ";";
-            }
-            *ix.out << b.heads[i] << ":" << s << "\n";           // :509
-        }
+        for (size_t i = 0; i < b.size(); ++i)
+            if (nhits[i])                                        // :506
+                *ix.out << b.heads[i] << ":" << hit_text(&hits[i * 10], nhits[i]) << "\n";   // :509
     }
     *ix.out << flush;
 }
@@ -419,15 +523,7 @@ void query_file_of_file_exact(Index& ix, const string& list) {
         cerr << "miekki: exact mode needs the genome list (-l) in the same run" << endl;
         return;
     }
-    vector<string> names;
-    {
-        mkcli::LineReader in(list);
-        string name;
-        while (!in.eof()) {
-            in.getline(name);
-            if (name.size() > 3) names.push_back(name);
-        }
-    }
+    const vector<string> names = read_list(list);
     map<uint32_t, vector<Candidate>> per_genome;
     ReadBatch b;
     for (const string& fn : names) {
@@ -460,7 +556,7 @@ void query_file_of_file_exact(Index& ix, const string& list) {
                 per_genome[sim.genome].push_back({b.seqs[i], b.heads[i], sim.jaccard, sim.intersection});
             }
     }
-    for (auto& kv : per_genome) ground_truth(ix, ix.file_names[kv.first], kv.second);
+    ground_truth_all(ix, per_genome);
     *ix.out << flush;
 }
 
@@ -475,8 +571,12 @@ int main(int argc, char** argv) {
     uint64_t H = 17, core_number = 8, kmer_size = 31, bloom_size = 33, fingerprint_size = 3;
     double threshold = 200;
     bool exact_mode = false;
-    int device = 0;
-    static const option longopts[] = {{"device", required_argument, nullptr, 1000}, {nullptr, 0, nullptr, 0}};
+    int device = 0, gpus = 1;
+    vector<int> devices;
+    static const option longopts[] = {{"device", required_argument, nullptr, 1000},
+                                      {"gpus", required_argument, nullptr, 1001},
+                                      {"devices", required_argument, nullptr, 1002},
+                                      {nullptr, 0, nullptr, 0}};
     int c;
     while ((c = getopt_long(argc, argv, "i:l:a:h:t:f:k:s:b:o:ed:A:", longopts, nullptr)) != -1) {
         switch (c) {
@@ -494,6 +594,13 @@ int main(int argc, char** argv) {
             case 'e': exact_mode = true; break;
             case 'd': index_dump = optarg; break;
             case 1000: device = stoi(optarg); break;
+            case 1001: gpus = max(1, stoi(optarg)); break;
+            case 1002: {
+                stringstream ss(optarg);
+                string tok;
+                while (getline(ss, tok, ',')) devices.push_back(stoi(tok));
+                break;
+            }
         }
     }
     const uint32_t bit_per_min = (uint32_t)(5 + fingerprint_size);
@@ -502,8 +609,11 @@ int main(int argc, char** argv) {
     auto start = chrono::system_clock::now();
     Index ix;
     ix.threads = (int)max<uint64_t>(1, core_number);
+    ix.device0 = device;
+    ix.gpus = devices.empty() ? gpus : (int)devices.size();
+    ix.devices = devices;
     if (!index_file.empty()) {
-        if (!load_disk(ix, index_file, device)) return 1;
+        if (!load_disk(ix, index_file)) return 1;
         ix.out = new ofstream(output_file.c_str());
         cout << "I output results in " << output_file << endl;
         cout << "Load sucessful" << endl;                        // main.cpp:193 (sic)
@@ -517,10 +627,7 @@ int main(int argc, char** argv) {
             cout << "not implemented" << endl;                   // Miekki.cpp:236-237 (quirk G12)
             exit(0);
         }
-        if (mk_create(ix.k, ix.h, ix.nbm, 5, ix.b, ix.threshold, device, &ix.ctx) != MK_OK) {
-            cerr << "miekki: " << mk_last_error(nullptr) << endl;
-            return 1;
-        }
+        ix.create_shards();
         ix.out = new ofstream(output_file.c_str());
         cout << "I output results in " << output_file << endl;   // Miekki.h:75
         index_file_of_file(ix, list_file);
@@ -561,6 +668,6 @@ int main(int argc, char** argv) {
     cout << "elapsed time: " << elapsed.count() << "s\n";
     cout << "The end" << endl;
     if (ix.out) ix.out->close();
-    mk_destroy(ix.ctx);
+    for (mk_ctx* s : ix.shard) mk_destroy(s);
     return 0;
 }

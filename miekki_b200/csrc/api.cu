@@ -728,14 +728,12 @@ int topk_stored(mk_ctx* c, uint32_t K, uint32_t min_score, double min_int, mk_hi
     } else {
         CU(cudaMemsetAsync(d_hlen, 0, (size_t)n * 4, c->stream));
     }
-    if (c->n > 0) {
+    if (c->n > 0 || finalize) {      // an empty shard still passes the heap on / sorts it
         PhaseTimer t(c, PH_TOPK);
         launch_topk(static_cast<uint32_t*>(c->counts.p), n, c->n, c->first_id, c->d_sketch_size,
                     c->d_genome_size, c->d_ratio, K, min_score, min_int, d_heap, d_hlen, finalize, c->stream);
         c->stats.kernel_launches += 1;
         CU(cudaGetLastError());
-    } else if (finalize) {
-        return fail(c, MK_ERR_STATE, "mk_topk: the finalizing shard must hold at least one genome");
     }
     CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, c->stream));
     CU(cudaMemcpyAsync(len_io, d_hlen, (size_t)n * 4, cudaMemcpyDefault, c->stream));
