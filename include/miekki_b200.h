@@ -160,6 +160,17 @@ int mk_query_chain(mk_ctx *ctx, const mk_batch *reads, uint32_t nresults, uint32
 int mk_scan(mk_ctx *ctx, const mk_batch *reads);
 int mk_topk(mk_ctx *ctx, uint32_t nresults, uint32_t min_score, double min_intersection,
             mk_hit *heap_io, uint32_t *len_io, int chain_in, int finalize);
+/* Pipelined form of the pair above.  mk_scan_async only enqueues the sketch + scan on the ctx
+ * stream and returns at once; counts land in one of two tiles, *slot says which.
+ * mk_topk_slot waits (on the device) for that scan, runs the heap step on a second stream and
+ * returns when heap_io/len_io are written, without waiting for later scans -- so batch i+1
+ * scans while batch i's heap travels through the shards.  At most two batches in flight: call
+ * mk_topk_slot for a slot before its tile is scanned into again.  `reads` must stay alive
+ * until the scan has run (e.g. until the matching mk_topk_slot returned). */
+int mk_scan_async(mk_ctx *ctx, const mk_batch *reads, int *slot);
+int mk_topk_slot(mk_ctx *ctx, int slot, uint32_t nresults, uint32_t min_score,
+                 double min_intersection, mk_hit *heap_io, uint32_t *len_io, int chain_in,
+                 int finalize);
 
 /* Test hook: raw shared-fingerprint counts, the matrix Miekki::query_sequences returns
  * (Miekki.cpp:352): counts[i * N + g].  surviving (may be NULL) receives A(q), the number of

@@ -72,6 +72,8 @@ SIGNATURES = {
     "mk_bloom_set": (_i, [_vp, _vp, _u64]),
     "mk_scan": (_i, [_vp, _vp]),
     "mk_topk": (_i, [_vp, _u32, _u32, _d, _vp, _vp, _i, _i]),
+    "mk_scan_async": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "mk_topk_slot": (_i, [_vp, _i, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_query": (_i, [_vp, _vp, _vp, _u32, _u32, _u32, _d, _vp, _vp]),
     "mk_query_batch": (_i, [_vp, _vp, _u32, _u32, _d, _vp, _vp]),
     "mk_query_chain": (_i, [_vp, _vp, _u32, _u32, _d, _vp, _vp, _i]),
@@ -312,6 +314,20 @@ class Miekki:
         self._ck(lib().mk_topk(self._ctx, nresults, min_score, float(min_intersection),
                                C.c_void_p(heap_ptr), C.c_void_p(len_ptr), 1 if chain_in else 0,
                                1 if finalize else 0))
+
+    def scan_async(self, batch: Batch) -> int:
+        """Enqueue sketch + scan and return at once; -> slot (0/1) for topk_ptr(slot=...)."""
+        slot = C.c_int(0)
+        self._ck(lib().mk_scan_async(self._ctx, batch._h, C.byref(slot)))
+        return slot.value
+
+    def topk_slot_ptr(self, slot: int, heap_ptr: int, len_ptr: int, nresults=10, min_score=10,
+                      min_intersection=None, chain_in=False, finalize=True):
+        if min_intersection is None:
+            min_intersection = 0.5 * self.threshold
+        self._ck(lib().mk_topk_slot(self._ctx, slot, nresults, min_score, float(min_intersection),
+                                    C.c_void_p(heap_ptr), C.c_void_p(len_ptr), 1 if chain_in else 0,
+                                    1 if finalize else 0))
 
     def topk(self, heap: np.ndarray, lens: np.ndarray, **kw):
         assert heap.dtype == HIT_DTYPE and heap.flags.c_contiguous and lens.dtype == np.uint32

@@ -74,11 +74,18 @@ struct mk_ctx {
     uint32_t* owner = nullptr;
     uint64_t window = 0;          // bytes, multiple of 16
 
-    DevBuf planeF, planeR, keys, fp, meta, list, list_len, counts, counts2, heap, heap_len, misc;
+    DevBuf planeF, planeR, keys, fp, meta, list, list_len, counts, counts2, heap, heap_len, heap2, heap_len2, misc;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint32_t* d_work = nullptr;
-    uint32_t scanned_reads = 0;   // rows of `counts` left by mk_scan
+    // mk_scan_async / mk_topk_slot: two count tiles (counts, counts2) and heap scratches
+    int next_slot = 0, last_slot = 0;
+    uint32_t slot_reads[2] = {0, 0};
+    cudaEvent_t slot_ev[2] = {nullptr, nullptr};
+    void* meta_pin[2] = {nullptr, nullptr};
+    size_t meta_pin_cap[2] = {0, 0};
+    int meta_flip = 0;
+    unsigned long long* d_stat = nullptr;   // device work counters: rows, row bytes
 
     std::vector<cudaEvent_t> ev_pool;
     std::vector<PendingEvent> ev_pending;
@@ -491,9 +498,28 @@ struct Lists {
 };
 constexpr uint64_t SPARSE_MAX_KMERS = 12288;   // 16384-slot table at load <= 0.75
 
+// small pinned staging areas for per-call metadata (two, alternating): uploads from them never
+// make the host wait for work already queued on the stream, which mk_scan_async relies on
+int pinned_meta(mk_ctx* c, size_t bytes, void** out) {
+    const int w = (c->meta_flip ^= 1);
+    if (bytes > c->meta_pin_cap[w]) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->meta_pin[w]) CU(cudaFreeHost(c->meta_pin[w]));
+        c->meta_pin[w] = nullptr;
+        c->meta_pin_cap[w] = 0;
+        CU(cudaMallocHost(&c->meta_pin[w], bytes + bytes / 4 + 4096));
+        c->meta_pin_cap[w] = bytes + bytes / 4 + 4096;
+    }
+    *out = c->meta_pin[w];
+    return MK_OK;
+}
+
 int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
     const uint32_t n = b->n;
-    std::vector<uint64_t> off((size_t)n + 1);
+    void* pin = nullptr;
+    TRY(pinned_meta(c, ((size_t)n + 1) * 8 + (size_t)n * 4 + 64, &pin));
+    uint64_t* off = static_cast<uint64_t*>(pin);
+    uint32_t* ids = reinterpret_cast<uint32_t*>(off + n + 1);
     std::vector<uint32_t> sparse_ids, dense_ids;
     uint64_t total = 0, sparse_max = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -522,13 +548,14 @@ int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
     uint64_t* d_off = reinterpret_cast<uint64_t*>(base + ll_bytes);
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(base + ll_bytes + lo_bytes);
     CU(cudaMemsetAsync(d_len, 0, ll_bytes, c->stream));
-    CU(cudaMemcpyAsync(d_off, off.data(), lo_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_off, off, lo_bytes, cudaMemcpyHostToDevice, c->stream));
     c->stats.h2d_bytes += lo_bytes;
-    std::vector<uint32_t> ids(sparse_ids);
-    ids.insert(ids.end(), dense_ids.begin(), dense_ids.end());
-    if (!ids.empty()) {
-        CU(cudaMemcpyAsync(d_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        c->stats.h2d_bytes += ids.size() * 4;
+    const size_t n_ids = sparse_ids.size() + dense_ids.size();
+    std::copy(sparse_ids.begin(), sparse_ids.end(), ids);
+    std::copy(dense_ids.begin(), dense_ids.end(), ids + sparse_ids.size());
+    if (n_ids) {
+        CU(cudaMemcpyAsync(d_ids, ids, n_ids * 4, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += n_ids * 4;
     }
     auto* list = static_cast<uint32_t*>(c->list.p);
     PhaseTimer t(c, PH_READ_SKETCH);
@@ -602,15 +629,14 @@ int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPl
 
 // accumulates A(q) statistics from the device list lengths
 int account_lists(mk_ctx* c, const Lists& L, uint32_t n, uint32_t* surviving) {
-    std::vector<uint32_t> ll(n);
-    if (n) CU(cudaMemcpyAsync(ll.data(), L.list_len, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    uint64_t rows = 0;
-    for (uint32_t i = 0; i < n; ++i) rows += ll[i];
-    c->stats.scan_rows += rows;
-    c->stats.scan_row_bytes += rows * c->n;
-    c->stats.d2h_bytes += (size_t)n * 4;
-    if (surviving) memcpy(surviving, ll.data(), (size_t)n * 4);
+    // device-side counters (fetched by mk_stats_get): no host round trip on the async path
+    launch_account_rows(L.list_len, n, c->n, c->d_stat, c->stream);
+    c->stats.kernel_launches += 1;
+    if (surviving) {
+        if (n) CU(cudaMemcpyAsync(surviving, L.list_len, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += (size_t)n * 4;
+    }
     return MK_OK;
 }
 
@@ -690,54 +716,77 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     return sync(c);
 }
 
-// sketch + scan of a whole batch with the counts kept in HBM (for the chained top-k)
-int scan_all(mk_ctx* c, const mk_batch* b) {
+// sketch + scan of a whole batch with the counts kept in HBM (for the chained top-k).
+// Asynchronous: everything is enqueued on the ctx stream, the counts go to one of two tiles
+// ("slots") so that the top-k of one batch can run (aux stream) while the next batch scans.
+int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
     const uint32_t n = b->n;
-    c->scanned_reads = 0;
+    const int slot = (c->next_slot ^= 1);
+    c->slot_reads[slot] = 0;
+    if (slot_out) *slot_out = slot;
+    c->last_slot = slot;
     if (n == 0) return MK_OK;
     const uint64_t n_pad = (c->n + 31) / 32 * 32;
     if ((uint64_t)n * std::max<uint64_t>(n_pad, 16) * 4 > (16ull << 30))
         return fail(c, MK_ERR_ARG, "mk_scan: count matrix would exceed 16 GiB, split the reads");
+    if (!c->slot_ev[0]) {
+        CU(cudaEventCreateWithFlags(&c->slot_ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->slot_ev[1], cudaEventDisableTiming));
+    }
     Lists L{};
     TRY(build_lists(c, b, &L));
+    DevBuf& tile = slot ? c->counts2 : c->counts;
     if (c->n > 0) {
         ScanPlan plan{};
         if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
             return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
-        TRY(reserve(c, c->counts, (size_t)n * n_pad * 4));
-        TRY(scan_reads(c, L, 0, n, plan));
+        TRY(reserve(c, tile, (size_t)n * n_pad * 4));
+        TRY(scan_reads(c, L, 0, n, plan, static_cast<uint32_t*>(tile.p)));
     }
     TRY(account_lists(c, L, n, nullptr));
-    c->scanned_reads = n;
-    return sync(c);
+    CU(cudaEventRecord(c->slot_ev[slot], c->stream));
+    c->slot_reads[slot] = n;
+    return MK_OK;
 }
 
-int topk_stored(mk_ctx* c, uint32_t K, uint32_t min_score, double min_int, mk_hit* heap_io,
-                uint32_t* len_io, bool chain_in, int finalize) {
+// bounded-heap step on the counts of `slot`, on the aux stream; waits for that stream only
+int topk_slot(mk_ctx* c, int slot, uint32_t K, uint32_t min_score, double min_int, mk_hit* heap_io,
+              uint32_t* len_io, bool chain_in, int finalize) {
     if (K < 1 || K > 64) return fail(c, MK_ERR_ARG, "nresults must be in [1, 64]");
-    const uint32_t n = c->scanned_reads;
+    if (slot < 0 || slot > 1) return fail(c, MK_ERR_ARG, "mk_topk: bad slot");
+    const uint32_t n = c->slot_reads[slot];
     if (n == 0) return MK_OK;
     if (!heap_io || !len_io) return fail(c, MK_ERR_ARG, "mk_topk needs heap_io and len_io");
-    TRY(reserve(c, c->heap, (size_t)n * K * sizeof(HitDev)));
-    TRY(reserve(c, c->heap_len, (size_t)n * 4));
-    auto* d_heap = static_cast<HitDev*>(c->heap.p);
-    auto* d_hlen = static_cast<uint32_t*>(c->heap_len.p);
+    cudaStream_t st = c->aux_stream;
+    // the heap scratch is per slot as well: two batches may be in flight
+    DevBuf& hb = slot ? c->heap2 : c->heap;
+    DevBuf& lb = slot ? c->heap_len2 : c->heap_len;
+    if ((size_t)n * K * sizeof(HitDev) > hb.cap || (size_t)n * 4 > lb.cap) {
+        CU(cudaStreamSynchronize(st));
+        TRY(reserve(c, hb, (size_t)n * K * sizeof(HitDev)));
+        TRY(reserve(c, lb, (size_t)n * 4));
+    }
+    auto* d_heap = static_cast<HitDev*>(hb.p);
+    auto* d_hlen = static_cast<uint32_t*>(lb.p);
+    CU(cudaStreamWaitEvent(st, c->slot_ev[slot], 0));
     if (chain_in) {
-        CU(cudaMemcpyAsync(d_heap, heap_io, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, c->stream));
-        CU(cudaMemcpyAsync(d_hlen, len_io, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+        CU(cudaMemcpyAsync(d_heap, heap_io, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(d_hlen, len_io, (size_t)n * 4, cudaMemcpyDefault, st));
     } else {
-        CU(cudaMemsetAsync(d_hlen, 0, (size_t)n * 4, c->stream));
+        CU(cudaMemsetAsync(d_hlen, 0, (size_t)n * 4, st));
     }
     if (c->n > 0 || finalize) {      // an empty shard still passes the heap on / sorts it
-        PhaseTimer t(c, PH_TOPK);
-        launch_topk(static_cast<uint32_t*>(c->counts.p), n, c->n, c->first_id, c->d_sketch_size,
-                    c->d_genome_size, c->d_ratio, K, min_score, min_int, d_heap, d_hlen, finalize, c->stream);
+        PhaseTimer t(c, PH_TOPK, st);
+        launch_topk(static_cast<uint32_t*>((slot ? c->counts2 : c->counts).p), n, c->n, c->first_id,
+                    c->d_sketch_size, c->d_genome_size, c->d_ratio, K, min_score, min_int, d_heap, d_hlen,
+                    finalize, st);
         c->stats.kernel_launches += 1;
         CU(cudaGetLastError());
     }
-    CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(len_io, d_hlen, (size_t)n * 4, cudaMemcpyDefault, c->stream));
-    return sync(c);
+    CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(len_io, d_hlen, (size_t)n * 4, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    return MK_OK;
 }
 
 struct Guard {
@@ -802,6 +851,8 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     if (e == cudaSuccess) e = cudaMalloc(&ctx->bloom, ctx->window);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->owner, ctx->window * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stat, 16);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_stat, 0, 16);
     if (e != cudaSuccess) {
         std::string msg = std::string("mk_create: ") + cudaGetErrorString(e);
         mk_destroy(ctx);
@@ -821,12 +872,16 @@ void mk_destroy(mk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
-                      &c->counts2, &c->heap, &c->heap_len, &c->misc})
+                      &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc})
         if (b->p) cudaFree(b->p);
     for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->d_ratio, (void*)c->bloom,
-                    (void*)c->owner, (void*)c->d_work})
+                    (void*)c->owner, (void*)c->d_work, (void*)c->d_stat})
         if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (void* p : c->meta_pin)
+        if (p) cudaFreeHost(p);
+    for (cudaEvent_t e : c->slot_ev)
+        if (e) cudaEventDestroy(e);
     for (auto& pe : c->ev_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1129,14 +1184,28 @@ int mk_query_chain(mk_ctx* c, const mk_batch* reads, uint32_t nresults, uint32_t
 int mk_scan(mk_ctx* c, const mk_batch* reads) {
     if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_scan: NULL argument");
     Guard g(c);
-    return scan_all(c, reads);
+    TRY(scan_all_async(c, reads, nullptr));
+    return sync(c);
+}
+
+int mk_scan_async(mk_ctx* c, const mk_batch* reads, int* slot) {
+    if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_scan_async: NULL argument");
+    Guard g(c);
+    return scan_all_async(c, reads, slot);
 }
 
 int mk_topk(mk_ctx* c, uint32_t nresults, uint32_t min_score, double min_intersection, mk_hit* heap_io,
             uint32_t* len_io, int chain_in, int finalize) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
-    return topk_stored(c, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
+    return topk_slot(c, c->last_slot, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
+}
+
+int mk_topk_slot(mk_ctx* c, int slot, uint32_t nresults, uint32_t min_score, double min_intersection,
+                 mk_hit* heap_io, uint32_t* len_io, int chain_in, int finalize) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    return topk_slot(c, slot, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
 }
 
 int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, uint32_t* counts,
@@ -1277,10 +1346,22 @@ int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, ui
 
 // ---- measurement ---------------------------------------------------------------------
 
+// folds the device-side work counters into the host statistics
+static int fold_device_stats(mk_ctx* c) {
+    CU(cudaStreamSynchronize(c->aux_stream));
+    TRY(sync(c));
+    unsigned long long st[2] = {0, 0};
+    CU(cudaMemcpy(st, c->d_stat, sizeof(st), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->d_stat, 0, sizeof(st)));
+    c->stats.scan_rows += st[0];
+    c->stats.scan_row_bytes += st[1];
+    return MK_OK;
+}
+
 int mk_stats_get(mk_ctx* c, mk_stats* out) {
     if (!c || !out) return MK_ERR_ARG;
     Guard g(c);
-    TRY(sync(c));
+    TRY(fold_device_stats(c));
     *out = c->stats;
     return MK_OK;
 }
@@ -1288,7 +1369,7 @@ int mk_stats_get(mk_ctx* c, mk_stats* out) {
 int mk_stats_reset(mk_ctx* c) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
-    TRY(sync(c));
+    TRY(fold_device_stats(c));
     c->stats = mk_stats{};
     return MK_OK;
 }

@@ -52,6 +52,9 @@ int launch_sketch_reads(const uint8_t* chars, const uint64_t* coff, const uint64
                         const uint32_t* read_ids, uint32_t n_ids, uint64_t max_len, SketchParams p,
                         const uint8_t* bloom, const uint64_t* list_off, uint32_t* list,
                         uint32_t* list_len, cudaStream_t st);
+// stat[0] += sum list_len, stat[1] += sum list_len * n_genomes (device-side work counters)
+void launch_account_rows(const uint32_t* list_len, uint32_t n, uint32_t n_genomes, unsigned long long* stat,
+                         cudaStream_t st);
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);
 void launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st);
 void launch_synth(uint8_t* chars, const uint64_t* coff, uint64_t seed, uint32_t first_g,

@@ -23,6 +23,7 @@
 // counters; at the end of an item the planes are bit-transposed into 32 counts per group and
 // written with 16-byte stores.  Algorithmic bytes = sum_q A(q) * N (one byte per compare).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -363,7 +364,13 @@ int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out
     // until about a dozen warps are resident, as long as every ring keeps >= 4 stages.
     const int warps = best_t / 32 + 1;
     int ctas = std::max(1, std::min(8, 12 / warps));
-    auto ring_budget = [&](int n) { return (smem_optin - 1024) / (size_t)n - 1024; };
+    // Leave part of every SM's shared memory to kernels that must run beside the persistent
+    // scan: the top-k of the previous tile and, in sharded runs, NCCL's send/recv kernels.
+    static const size_t reserve = [] {
+        const char* e = getenv("MIEKKI_SCAN_SMEM_RESERVE_KB");
+        return (size_t)(e ? atoi(e) : 40) * 1024;
+    }();
+    auto ring_budget = [&](int n) { return (smem_optin - reserve - 1024) / (size_t)n - 1024; };
     while (ctas > 1 && ring_budget(ctas) / per_stage < 4) --ctas;
     int stages = (int)(ring_budget(ctas) / per_stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;

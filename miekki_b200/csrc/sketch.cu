@@ -487,7 +487,29 @@ __global__ void bloom_merge_kernel(uint8_t* __restrict__ dst, const uint8_t* __r
     }
 }
 
+// work counters kept on the device so that asynchronous scans need no host round trip:
+// stat[0] += sum_q A(q), stat[1] += sum_q A(q) * N  (the scan's algorithmic bytes)
+__global__ void __launch_bounds__(256)
+account_rows_kernel(const uint32_t* __restrict__ list_len, uint32_t n, uint32_t n_genomes,
+                    unsigned long long* __restrict__ stat) {
+    unsigned long long s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += list_len[i];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) {
+        atomicAdd(stat, s);
+        atomicAdd(stat + 1, s * n_genomes);
+    }
+}
+
 // ---- launchers ---------------------------------------------------------------------
+
+void launch_account_rows(const uint32_t* list_len, uint32_t n, uint32_t n_genomes, unsigned long long* stat,
+                         cudaStream_t st) {
+    if (!n) return;
+    const unsigned grid = (n + 255) / 256 < 296u ? (n + 255) / 256 : 296u;
+    account_rows_kernel<<<grid, 256, 0, st>>>(list_len, n, n_genomes, stat);
+}
 
 static inline unsigned blocks_for(uint64_t items, unsigned per_block, unsigned cap) {
     uint64_t b = (items + per_block - 1) / per_block;

@@ -46,18 +46,66 @@ def merge_bloom(local: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, min_score: int,
-                 min_intersection: float, group=None) -> None:
+                 min_intersection: float, group=None, slot: int | None = None) -> None:
     """heap: uint8 [n_reads, nresults * 24], lens: int32 [n_reads], on the engine's device.
     `engine.topk_ptr(heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in,
-    finalize)` applies this rank's stored counts to the heap state in place.
-    After the call the LAST rank holds the final hit lists."""
+    finalize)` applies this rank's stored counts to the heap state in place
+    (`engine.topk_slot_ptr(slot, ...)` when `slot` is given: the pipelined form, where the
+    caller has already enqueued the next batch's scan with `scan_async`).
+    After the call the LAST rank holds the final hit lists.
+
+    On GPUs the receive is followed by a wait on the current stream only, so when this runs
+    under `torch.cuda.stream(side_stream)` the main stream keeps scanning."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if rank > 0:
         dist.recv(heap, src=rank - 1, group=group)
         dist.recv(lens, src=rank - 1, group=group)
-    engine.topk_ptr(heap.data_ptr(), lens.data_ptr(), nresults, min_score, min_intersection,
-                    chain_in=rank > 0, finalize=rank == world - 1)
+        if heap.is_cuda:
+            torch.cuda.current_stream().synchronize()      # the engine reads the buffers next
+    kw = dict(chain_in=rank > 0, finalize=rank == world - 1)
+    if slot is None:
+        engine.topk_ptr(heap.data_ptr(), lens.data_ptr(), nresults, min_score, min_intersection, **kw)
+    else:
+        engine.topk_slot_ptr(slot, heap.data_ptr(), lens.data_ptr(), nresults, min_score,
+                             min_intersection, **kw)
     if rank < world - 1:
         dist.send(heap, dst=rank + 1, group=group)
         dist.send(lens, dst=rank + 1, group=group)
+
+
+def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nresults: int,
+                    min_score: int, min_intersection: float, on_result=None, after_chain=None,
+                    group=None) -> None:
+    """Software pipeline over read batches: the scan of batch i+1 is enqueued before batch i's
+    heap is chained through the ranks, so the cheap, latency-bound chain hides behind the scan.
+    `batches` yields engine batches; `on_result(i)` is called on the last rank when batch i's hit
+    lists are final in (heap, lens); `after_chain(i)` on every rank once its own step for batch i
+    is done (its scan has run by then, so the batch may be freed)."""
+    side = torch.cuda.Stream() if heap.is_cuda else None
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def finish(i, slot):
+        def body():
+            chained_topk(engine, heap, lens, nresults, min_score, min_intersection, group, slot)
+            if on_result is not None and rank == world - 1:
+                on_result(i)
+            if after_chain is not None:
+                after_chain(i)
+        if side is not None:
+            with torch.cuda.stream(side):
+                body()
+        else:
+            body()
+
+    pending = None
+    for i, b in enumerate(batches):
+        slot = engine.scan_async(b)
+        if pending is not None:
+            finish(*pending)
+        pending = (i, slot)
+    if pending is not None:
+        finish(*pending)
+    if side is not None:
+        side.synchronize()

@@ -174,6 +174,33 @@ def test_case_a_sharded_chain_equals_unsharded(mk, case_a):
         x.close()
 
 
+def test_case_a_pipelined_scan_and_topk_slots(mk, case_a):
+    """mk_scan_async / mk_topk_slot: two read batches in flight (scan of the second enqueued
+    before the first one's heap step) give the same lists as the plain query."""
+    d, ix, _ = case_a
+    reads = [s for _, s in H.reads_like_reference(os.path.join(d, "reads.fa"), 31)]
+    parts = [reads[:20], reads[20:], reads[5:33]]
+    batches = [ix.upload(p) for p in parts]
+    want = [ix.query(p, 10, 10, 100.0) for p in parts]
+    heaps = [np.zeros((len(p), 10), mk.HIT_DTYPE) for p in parts]
+    lens = [np.zeros(len(p), np.uint32) for p in parts]
+    slots = [ix.scan_async(batches[0]), ix.scan_async(batches[1])]
+    assert sorted(slots) == [0, 1]
+    ix.topk_slot_ptr(slots[0], heaps[0].ctypes.data, lens[0].ctypes.data, 10, 10, 100.0)
+    slots.append(ix.scan_async(batches[2]))          # reuses the tile of batch 0
+    assert slots[2] == slots[0]
+    ix.topk_slot_ptr(slots[1], heaps[1].ctypes.data, lens[1].ctypes.data, 10, 10, 100.0)
+    ix.topk_slot_ptr(slots[2], heaps[2].ctypes.data, lens[2].ctypes.data, 10, 10, 100.0)
+    ix.sync()
+    for p, w, hp, ln in zip(parts, want, heaps, lens):
+        for i in range(len(p)):
+            assert hp[i, :ln[i]].tobytes() == w[i].tobytes()
+    for b in batches:
+        b.free()
+    st = ix.stats()
+    assert st["scan_rows"] > 0 and st["scan_row_bytes"] == st["scan_rows"] * ix.n
+
+
 # ---- exact mode ---------------------------------------------------------------------------
 
 @pytest.mark.parametrize("s,fname", [(200, "exact.txt"), (0, "exact_s0.txt")])
