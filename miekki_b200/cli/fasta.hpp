@@ -4,6 +4,7 @@
 #pragma once
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -187,6 +188,85 @@ private:
     FILE* f_ = nullptr;
     z_stream zs_;
     std::vector<unsigned char> buf_;
+};
+
+// Parallel gzip-1 writer for the index dump: the payload is cut into 32 MiB chunks, each
+// deflated by its own thread into an independent gzip member, written in order.  Concatenated
+// members are a valid gzip file, and the reference's reader restarts its inflator at every
+// member end (zstr.hpp:193-197), so the dump stays loadable by the reference's -i.
+class ParallelGzWriter {
+public:
+    ParallelGzWriter(const std::string& path, int threads) : threads_(threads < 1 ? 1 : threads) {
+        f_ = fopen(path.c_str(), "wb");
+        if (!f_) throw std::runtime_error("cannot open " + path);
+    }
+    ~ParallelGzWriter() { close(); }
+    // small pieces (header fields) are gathered and leave with the next large block
+    void write(const void* p, size_t n) {
+        const unsigned char* src = (const unsigned char*)p;
+        if (n < CHUNK / 4) {
+            pending_.insert(pending_.end(), src, src + n);
+            if (pending_.size() >= CHUNK) flush_pending();
+            return;
+        }
+        flush_pending();
+        compress_and_write(src, n);
+    }
+    void close() {
+        if (!f_) return;
+        flush_pending();
+        if (!wrote_any_) {                      // an empty payload is still a valid gzip file
+            std::vector<unsigned char> out;
+            deflate_member(nullptr, 0, out);
+            fwrite(out.data(), 1, out.size(), f_);
+        }
+        fclose(f_);
+        f_ = nullptr;
+    }
+
+private:
+    static constexpr size_t CHUNK = 32u << 20;
+    static void deflate_member(const unsigned char* src, size_t n, std::vector<unsigned char>& out) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, 1, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+            throw std::runtime_error("deflateInit2 failed");
+        out.resize(deflateBound(&zs, (uLong)n) + 64);
+        zs.next_in = const_cast<unsigned char*>(src);
+        zs.avail_in = (uInt)n;
+        zs.next_out = out.data();
+        zs.avail_out = (uInt)out.size();
+        const int r = deflate(&zs, Z_FINISH);
+        const size_t produced = out.size() - zs.avail_out;
+        deflateEnd(&zs);
+        if (r != Z_STREAM_END) throw std::runtime_error("deflate failed");
+        out.resize(produced);
+    }
+    void flush_pending() {
+        if (pending_.empty()) return;
+        std::vector<unsigned char> tmp;
+        tmp.swap(pending_);
+        compress_and_write(tmp.data(), tmp.size());
+    }
+    void compress_and_write(const unsigned char* src, size_t n) {
+        const size_t nchunks = (n + CHUNK - 1) / CHUNK;
+        // waves of `threads_` chunks keep memory bounded
+        for (size_t c0 = 0; c0 < nchunks; c0 += (size_t)threads_) {
+            const size_t m = std::min<size_t>((size_t)threads_, nchunks - c0);
+            std::vector<std::vector<unsigned char>> outs(m);
+            #pragma omp parallel for num_threads(threads_) schedule(dynamic, 1)
+            for (size_t i = 0; i < m; ++i) {
+                const size_t off = (c0 + i) * CHUNK;
+                deflate_member(src + off, std::min(CHUNK, n - off), outs[i]);
+            }
+            for (size_t i = 0; i < m; ++i) fwrite(outs[i].data(), 1, outs[i].size(), f_);
+        }
+        wrote_any_ = wrote_any_ || n > 0;
+    }
+    FILE* f_ = nullptr;
+    int threads_;
+    bool wrote_any_ = false;
+    std::vector<unsigned char> pending_;
 };
 
 // Miekki.cpp:559-567 (index_file_of_file): every line that does not start with '>' is

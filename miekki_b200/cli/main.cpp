@@ -225,7 +225,7 @@ void dump_disk(Index& ix, const string& path) {
                 memcpy(rows.data() + b * n + ix.first[r], part.data() + b * nr, nr);
         }
     }
-    mkcli::GzWriter w(path);
+    mkcli::ParallelGzWriter w(path, ix.threads);   // gzip level 1 like zstr::ofstream, multi-member
     const uint8_t jaccard_estimation = 0;       // uninitialised in the reference (quirk G7)
     const uint8_t containment_estimation = 0;
     const uint8_t compressed = ix.compressed_flag ? 1 : 0;

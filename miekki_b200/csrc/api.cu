@@ -662,7 +662,7 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     TRY(build_lists(c, b, &L));
     if (c->n > 0) {
         ScanPlan plan{};
-        if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
+        if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
             return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
         // Sub-batches of reads, two count tiles: the top-k of tile i runs on the aux stream
         // while the (DRAM-bound, persistent) scan of tile i+1 runs on the main one.
@@ -738,7 +738,7 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
     DevBuf& tile = slot ? c->counts2 : c->counts;
     if (c->n > 0) {
         ScanPlan plan{};
-        if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
+        if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
             return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
         TRY(reserve(c, tile, (size_t)n * n_pad * 4));
         TRY(scan_reads(c, L, 0, n, plan, static_cast<uint32_t*>(tile.p)));
@@ -1220,7 +1220,7 @@ int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, ui
         TRY(build_lists(c, b, &L));
         if (c->n) {
             ScanPlan plan{};
-            if (scan_plan(c->n, c->sm_count, c->smem_optin, &plan) != 0)
+            if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
                 return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
             const uint32_t qb = scan_batch_reads(c, n);
             const uint64_t n_pad = (c->n + 31) / 32 * 32;

@@ -68,10 +68,13 @@ struct ScanPlan {
     uint32_t tile_w;    // genomes per tile (multiple of 32, <= 32 * threads * J)
     uint32_t n_tiles;   // genome tiles per row
     int stages;         // smem ring depth
+    int blocks;         // 4-row carry-save blocks per stage (1 for wide tiles, up to 8)
+    int whole_rows;     // 1: a stage row is a whole index row (one bulk copy), else two half copies
+    uint32_t row_bytes; // pitch of a row inside a stage
     size_t smem;
     int grid;
 };
-int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out);
+int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, ScanPlan* out);
 // counts[q * n_genomes + g] = #{entries e of read q : rows[bucket(e)][g] == fp(e)}
 int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes,
                 const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len,

@@ -33,18 +33,19 @@ namespace mk {
 namespace {
 
 constexpr uint32_t F_FIRST = 1, F_LAST = 2, F_END = 8, F_ACCUM = 16;
-constexpr int R = 4;                 // rows per stage
+constexpr int R = 4;                 // rows per carry-save block
+constexpr int MAX_BLOCKS = 8;        // blocks per stage: narrow tiles put up to 32 rows behind one barrier
 constexpr int MAX_J = 4;
 constexpr int MAX_STAGES = 48;
 constexpr int TOP = 16;              // counter planes: counts up to 65535 per chunk
-constexpr uint32_t CHUNK_ROWS = 65532;   // rows per chunk, multiple of R, < 2^16
+constexpr uint32_t CHUNK_ROWS = 65504;   // rows per chunk: multiple of 32 (largest stage), < 2^16
 
 struct __align__(16) StageMeta {
     uint32_t flags;
-    uint32_t nrows;     // rows in this stage (1..R), 0 for an empty item
+    uint32_t nrows;     // rows in this stage (1..R*blocks), 0 for an empty item
     uint32_t read;
     uint32_t grp0;      // first 32-genome group of the tile
-    uint32_t mask[R][8];   // mask[r][p] = (fp_r bit p) ? 0 : ~0
+    uint32_t mask[R * MAX_BLOCKS][8];   // mask[r][p] = (fp_r bit p) ? 0 : ~0
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -160,11 +161,12 @@ __global__ void __launch_bounds__(384, 1)
 scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups, uint32_t n_pad,
             const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
             const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t tile_groups,
-            uint32_t n_tiles, int stages, uint32_t row_bytes, uint32_t* __restrict__ counts,
-            uint32_t* __restrict__ work_counter) {
-    // stage s: R rows of row_bytes (= 32 * tile_groups: half 0 then half 1)
+            uint32_t n_tiles, int stages, uint32_t row_bytes, uint32_t half, int whole_rows, int blocks,
+            uint32_t* __restrict__ counts, uint32_t* __restrict__ work_counter) {
+    // stage s: R * blocks rows of row_bytes (= 32 * tile_groups: half 0 then half 1)
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t stage_bytes = R * row_bytes;
+    const uint32_t stage_rows = (uint32_t)(R * blocks);
+    const uint32_t stage_bytes = stage_rows * row_bytes;
     uint8_t* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
@@ -180,7 +182,9 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t half = row_bytes >> 1;        // bytes of one half in a stage row
+    // half = offset of planes 4-7 inside a stage row.  whole_rows: the tile is the whole row
+    // (one genome tile, little padding), fetched with ONE bulk copy of `stride` bytes instead
+    // of one per half.
 
     if (warp == (n_cons >> 5)) {
         // ---------------- producer warp ----------------
@@ -203,8 +207,8 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
             const uint8_t* src1 = src0 + (stride >> 1);
             uint32_t done = 0;                                // rows of this item already issued
             do {
-                // lanes 0..R-1 fetch the entries of this stage
-                const uint32_t nr = (L - done < (uint32_t)R) ? (L - done) : (uint32_t)R;
+                // lanes 0..stage_rows-1 fetch the entries of this stage (at most 32)
+                const uint32_t nr = (L - done < stage_rows) ? (L - done) : stage_rows;
                 const uint32_t e = ((uint32_t)lane < nr) ? __ldg(lst + done + lane) : 0u;
                 const uint32_t in_chunk = done % CHUNK_ROWS;
                 uint32_t flags = 0;
@@ -227,15 +231,19 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if (nr) mbar_arrive_expect_tx(full + stage, nr * 2u * hbytes);
+                    if (nr) mbar_arrive_expect_tx(full + stage, whole_rows ? nr * (uint32_t)stride : nr * 2u * hbytes);
                     else mbar_arrive(full + stage);
                 }
                 __syncwarp();
                 if ((uint32_t)lane < nr) {
                     const uint64_t roff = (uint64_t)(e >> 8) * stride;
                     uint8_t* dst = ring + (size_t)stage * stage_bytes + (size_t)lane * row_bytes;
-                    bulk_g2s(dst, src0 + roff, hbytes, full + stage);
-                    bulk_g2s(dst + half, src1 + roff, hbytes, full + stage);
+                    if (whole_rows) {
+                        bulk_g2s(dst, rows + roff, (uint32_t)stride, full + stage);
+                    } else {
+                        bulk_g2s(dst, src0 + roff, hbytes, full + stage);
+                        bulk_g2s(dst + half, src1 + roff, hbytes, full + stage);
+                    }
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
                 done += nr;
@@ -268,39 +276,43 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
                 nblk = 0;
             }
             if (nr) {
-                uint32_t e[J][R];
                 const uint8_t* base = ring + (size_t)stage * stage_bytes;
-                #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((uint32_t)r < nr) {
-                        const uint4 m0 = *reinterpret_cast<const uint4*>(&m->mask[r][0]);
-                        const uint4 m1 = *reinterpret_cast<const uint4*>(&m->mask[r][4]);
-                        #pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            const uint32_t g = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;   // group in tile
-                            uint32_t x = 0;
-                            if (g < tile_groups) {
-                                const uint4 a = *reinterpret_cast<const uint4*>(base + (size_t)r * row_bytes + 16u * g);
-                                const uint4 b = *reinterpret_cast<const uint4*>(base + (size_t)r * row_bytes + half + 16u * g);
-                                x = a.x ^ m0.x;
-                                x = (a.y ^ m0.y) & x;
-                                x = (a.z ^ m0.z) & x;
-                                x = (a.w ^ m0.w) & x;
-                                x = (b.x ^ m1.x) & x;
-                                x = (b.y ^ m1.y) & x;
-                                x = (b.z ^ m1.z) & x;
-                                x = (b.w ^ m1.w) & x;
+                for (uint32_t r0 = 0; r0 < nr; r0 += R) {       // one carry-save block of R rows
+                    uint32_t e[J][R];
+                    #pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t row = r0 + r;
+                        if (row < nr) {
+                            const uint4 m0 = *reinterpret_cast<const uint4*>(&m->mask[row][0]);
+                            const uint4 m1 = *reinterpret_cast<const uint4*>(&m->mask[row][4]);
+                            #pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                const uint32_t g = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;   // group in tile
+                                uint32_t x = 0;
+                                if (g < tile_groups) {
+                                    const uint8_t* rp = base + (size_t)row * row_bytes + 16u * g;
+                                    const uint4 a = *reinterpret_cast<const uint4*>(rp);
+                                    const uint4 b = *reinterpret_cast<const uint4*>(rp + half);
+                                    x = a.x ^ m0.x;
+                                    x = (a.y ^ m0.y) & x;
+                                    x = (a.z ^ m0.z) & x;
+                                    x = (a.w ^ m0.w) & x;
+                                    x = (b.x ^ m1.x) & x;
+                                    x = (b.y ^ m1.y) & x;
+                                    x = (b.z ^ m1.z) & x;
+                                    x = (b.w ^ m1.w) & x;
+                                }
+                                e[j][r] = x;
                             }
-                            e[j][r] = x;
+                        } else {
+                            #pragma unroll
+                            for (int j = 0; j < J; ++j) e[j][r] = 0;
                         }
-                    } else {
-                        #pragma unroll
-                        for (int j = 0; j < J; ++j) e[j][r] = 0;
                     }
+                    #pragma unroll
+                    for (int j = 0; j < J; ++j) cnt[j].add4(e[j][0], e[j][1], e[j][2], e[j][3], nblk);
+                    ++nblk;
                 }
-                #pragma unroll
-                for (int j = 0; j < J; ++j) cnt[j].add4(e[j][0], e[j][1], e[j][2], e[j][3], nblk);
-                ++nblk;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);       // stage may be refilled
@@ -336,7 +348,7 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
 
 }  // namespace
 
-int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out) {
+int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, ScanPlan* out) {
     if (n_genomes == 0) return -1;
     const uint32_t MAXG = 512;                     // widest tile: 512 groups = 16,384 genomes
     const uint32_t G = (n_genomes + 31) / 32;      // 32-genome groups per row
@@ -357,8 +369,24 @@ int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out
     out->J = best_j;
     out->tile_w = tg * 32;
     out->n_tiles = n_tiles;
-    const size_t row_bytes = (size_t)tg * 32;
-    const size_t per_stage = R * row_bytes + 2 * sizeof(uint64_t) + sizeof(StageMeta);
+    // one genome tile and <= 2 % padding: stage whole rows (one copy per row instead of two)
+    static const bool allow_whole = [] {
+        const char* e = getenv("MIEKKI_SCAN_WHOLE_ROWS");
+        return !e || atoi(e) != 0;
+    }();
+    // (measured: +1.3 % at N = 10,000 with 1 % padding; -6 % at N = 300 where padding is 20 %)
+    out->whole_rows = (allow_whole && n_tiles == 1 && (stride - (uint64_t)tg * 32) * 50 <= (uint64_t)tg * 32) ? 1 : 0;
+    const size_t row_bytes = out->whole_rows ? (size_t)stride : (size_t)tg * 32;
+    out->row_bytes = (uint32_t)row_bytes;
+    // narrow tiles: several carry-save blocks per stage so that a stage is ~16 KB
+    static const size_t stage_target = [] {
+        const char* e = getenv("MIEKKI_SCAN_STAGE_TARGET_B");
+        return (size_t)(e ? atoi(e) : 4096);   // measured: 16 KB stages cost resident CTAs at N = 2,000
+    }();
+    int blocks = (int)(stage_target / (R * row_bytes));
+    blocks = std::max(1, std::min(MAX_BLOCKS, blocks));
+    out->blocks = blocks;
+    const size_t per_stage = (size_t)blocks * R * row_bytes + 2 * sizeof(uint64_t) + sizeof(StageMeta);
     // Narrow tiles leave an SM with two or three warps, which cannot hide their own
     // dependency chains: co-schedule several CTAs (each with its own ring and producer)
     // until about a dozen warps are resident, as long as every ring keeps >= 4 stages.
@@ -368,7 +396,7 @@ int scan_plan(uint32_t n_genomes, int sm_count, size_t smem_optin, ScanPlan* out
     // scan: the top-k of the previous tile and, in sharded runs, NCCL's send/recv kernels.
     static const size_t reserve = [] {
         const char* e = getenv("MIEKKI_SCAN_SMEM_RESERVE_KB");
-        return (size_t)(e ? atoi(e) : 40) * 1024;
+        return (size_t)(e ? atoi(e) : 0) * 1024;   // measured: 0 vs 40 KB -> 2 % faster step at N = 10,000
     }();
     auto ring_budget = [&](int n) { return (smem_optin - reserve - 1024) / (size_t)n - 1024; };
     while (ctas > 1 && ring_budget(ctas) / per_stage < 4) --ctas;
@@ -401,7 +429,8 @@ static int launch_scan_j(const ScanPlan& plan, const uint8_t* rows, uint64_t str
     if ((uint64_t)grid > items) grid = (int)(items ? items : 1);
     scan_kernel<J><<<grid, plan.threads + 32, plan.smem, st>>>(
         rows, stride, n_groups, n_pad, list, list_off, list_len, n_reads, tg, plan.n_tiles, plan.stages,
-        tg * 32, counts, work_counter);
+        plan.row_bytes, plan.whole_rows ? (uint32_t)(stride / 2) : plan.row_bytes / 2, plan.whole_rows, plan.blocks,
+        counts, work_counter);
     return 0;
 }
 
