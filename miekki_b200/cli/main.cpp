@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <map>
 #include <sstream>
@@ -143,12 +144,18 @@ vector<string> read_list(const string& list) {
 // files [lo, hi) of the list go to one shard, in list order
 void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo, size_t hi, int threads,
                  vector<string>& kept) {
-    // parse `wave` files in parallel, then insert in list order so that ids are deterministic
+    // Files are parsed in waves by a team of host threads and inserted in list order, so ids are
+    // deterministic; wave i+1 is parsed (inflate, line joins) while wave i is on the GPU.
     const size_t wave = max<size_t>(32, 4 * (size_t)threads);
-    for (size_t w0 = lo; w0 < hi; w0 += wave) {
+    struct Wave {
+        vector<string> seqs;
+        vector<char> ok;
+    };
+    auto parse = [&](size_t w0) {
+        Wave w;
         const size_t m = min(wave, hi - w0);
-        vector<string> seqs(m);
-        vector<char> ok(m, 0);
+        w.seqs.resize(m);
+        w.ok.assign(m, 0);
         #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
         for (size_t i = 0; i < m; ++i) {
             const string& fn = names[w0 + i];
@@ -157,9 +164,19 @@ void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo,
                 cout << "Missed file: " << fn << endl;           // :557
                 continue;
             }
-            seqs[i] = mkcli::read_genome_concat(fn);
-            ok[i] = seqs[i].size() >= ix.k;                      // :569
+            w.seqs[i] = mkcli::read_genome_concat(fn);
+            w.ok[i] = w.seqs[i].size() >= ix.k;                  // :569
         }
+        return w;
+    };
+    future<Wave> next;
+    if (lo < hi) next = async(launch::async, parse, lo);
+    for (size_t w0 = lo; w0 < hi; w0 += wave) {
+        Wave cur = next.get();
+        if (w0 + wave < hi) next = async(launch::async, parse, w0 + wave);
+        const size_t m = cur.seqs.size();
+        vector<string>& seqs = cur.seqs;
+        vector<char>& ok = cur.ok;
         vector<const char*> ptr;
         vector<uint64_t> len;
         for (size_t i = 0; i < m; ++i) {
