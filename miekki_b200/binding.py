@@ -18,7 +18,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmiekki_b200.so")
+# MIEKKI_B200_LIB points at another build of the same ABI (A/B measurements)
+LIB_PATH = os.environ.get("MIEKKI_B200_LIB") or os.path.join(HERE, "libmiekki_b200.so")
 
 HIT_DTYPE = np.dtype([("genome", "<u4"), ("matches", "<u4"),
                       ("jaccard", "<f8"), ("intersection", "<f8")])

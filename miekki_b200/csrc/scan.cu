@@ -84,6 +84,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 // carry-save adder: (carry, sum) of three bit-planes
 __device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
     const uint32_t u = a ^ b;
@@ -107,21 +113,35 @@ struct Counters {
         csa(ta, ones, ones, e0, e1);
         csa(tb, ones, ones, e2, e3);
         csa(carry, twos, twos, ta, tb);          // carry has weight 4
-        // binary counter with one pending slot per level: amortised ~2 CSAs per block
-        bool go = true;
-        #pragma unroll
-        for (int l = 2; l < TOP; ++l) {
-            if (go) {
-                if ((nblk >> (l - 2)) & 1u) {    // slot occupied: combine, carry on
-                    uint32_t nc;
-                    csa(nc, c[l], c[l], pend[l], carry);
-                    carry = nc;
-                } else {                          // slot free: park the carry here
-                    pend[l] = carry;
-                    go = false;
-                }
-            }
+        // Binary counter with one pending slot per level: the t lowest levels whose slot is
+        // occupied (t = trailing ones of nblk, the same for every thread) combine and pass a
+        // carry up, the next level parks it.  Amortised one CSA per block; a jump table on t
+        // keeps every case straight-line with static register indices.
+#define MK_LVL(l) { uint32_t nc_; csa(nc_, c[l], c[l], pend[l], carry); carry = nc_; }
+        switch (__ffs((int)~nblk) - 1) {
+            case 0: pend[2] = carry; break;
+            case 1: MK_LVL(2) pend[3] = carry; break;
+            case 2: MK_LVL(2) MK_LVL(3) pend[4] = carry; break;
+            case 3: MK_LVL(2) MK_LVL(3) MK_LVL(4) pend[5] = carry; break;
+            case 4: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) pend[6] = carry; break;
+            case 5: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) pend[7] = carry; break;
+            case 6: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) pend[8] = carry; break;
+            case 7: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) pend[9] = carry; break;
+            case 8: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) MK_LVL(9)
+                    pend[10] = carry; break;
+            case 9: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) MK_LVL(9) MK_LVL(10)
+                    pend[11] = carry; break;
+            case 10: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) MK_LVL(9) MK_LVL(10)
+                     MK_LVL(11) pend[12] = carry; break;
+            case 11: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) MK_LVL(9) MK_LVL(10)
+                     MK_LVL(11) MK_LVL(12) pend[13] = carry; break;
+            case 12: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) MK_LVL(9) MK_LVL(10)
+                     MK_LVL(11) MK_LVL(12) MK_LVL(13) pend[14] = carry; break;
+            case 13: MK_LVL(2) MK_LVL(3) MK_LVL(4) MK_LVL(5) MK_LVL(6) MK_LVL(7) MK_LVL(8) MK_LVL(9) MK_LVL(10)
+                     MK_LVL(11) MK_LVL(12) MK_LVL(13) MK_LVL(14) pend[15] = carry; break;
+            default: break;      // 14 trailing ones would need nblk >= 16383: past CHUNK_ROWS / R
         }
+#undef MK_LVL
     }
     // resolve pending slots and return the TOP planes (plane l has weight 2^l)
     __device__ __forceinline__ void planes(uint32_t nblk, uint32_t (&P)[32]) {
@@ -276,37 +296,39 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
                 nblk = 0;
             }
             if (nr) {
-                const uint8_t* base = ring + (size_t)stage * stage_bytes;
+                // shared-memory addresses of this thread's groups in row 0 of the stage; lanes of
+                // idle groups (g >= tile_groups) read group 0 and their results are never written
+                const uint32_t stage_addr = smem_u32(ring) + (uint32_t)stage * stage_bytes;
+                const uint32_t mask_addr = smem_u32(&m->mask[0][0]);
+                uint32_t gaddr[J];
+                #pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t g = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;
+                    gaddr[j] = stage_addr + 16u * (g < tile_groups ? g : 0u);
+                }
                 for (uint32_t r0 = 0; r0 < nr; r0 += R) {       // one carry-save block of R rows
                     uint32_t e[J][R];
+                    const uint32_t left = nr - r0;                // >= 1; full blocks take the first branch
                     #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const uint32_t row = r0 + r;
-                        if (row < nr) {
-                            const uint4 m0 = *reinterpret_cast<const uint4*>(&m->mask[row][0]);
-                            const uint4 m1 = *reinterpret_cast<const uint4*>(&m->mask[row][4]);
-                            #pragma unroll
-                            for (int j = 0; j < J; ++j) {
-                                const uint32_t g = (uint32_t)threadIdx.x + (uint32_t)n_cons * j;   // group in tile
-                                uint32_t x = 0;
-                                if (g < tile_groups) {
-                                    const uint8_t* rp = base + (size_t)row * row_bytes + 16u * g;
-                                    const uint4 a = *reinterpret_cast<const uint4*>(rp);
-                                    const uint4 b = *reinterpret_cast<const uint4*>(rp + half);
-                                    x = a.x ^ m0.x;
-                                    x = (a.y ^ m0.y) & x;
-                                    x = (a.z ^ m0.z) & x;
-                                    x = (a.w ^ m0.w) & x;
-                                    x = (b.x ^ m1.x) & x;
-                                    x = (b.y ^ m1.y) & x;
-                                    x = (b.z ^ m1.z) & x;
-                                    x = (b.w ^ m1.w) & x;
-                                }
-                                e[j][r] = x;
-                            }
-                        } else {
-                            #pragma unroll
-                            for (int j = 0; j < J; ++j) e[j][r] = 0;
+                        // branch-free: a row slot past the end of the stage re-reads the block's
+                        // first row and its equality mask is zeroed below, so it contributes nothing
+                        const uint32_t row = r0 + ((uint32_t)r < left ? (uint32_t)r : 0u);
+                        const uint4 m0 = lds128(mask_addr + row * 32u);
+                        const uint4 m1 = lds128(mask_addr + row * 32u + 16u);
+                        #pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const uint4 a = lds128(gaddr[j] + row * row_bytes);
+                            const uint4 b = lds128(gaddr[j] + row * row_bytes + half);
+                            uint32_t x = a.x ^ m0.x;
+                            x = (a.y ^ m0.y) & x;
+                            x = (a.z ^ m0.z) & x;
+                            x = (a.w ^ m0.w) & x;
+                            x = (b.x ^ m1.x) & x;
+                            x = (b.y ^ m1.y) & x;
+                            x = (b.z ^ m1.z) & x;
+                            x = (b.w ^ m1.w) & x;
+                            e[j][r] = (uint32_t)r < left ? x : 0u;
                         }
                     }
                     #pragma unroll
