@@ -325,6 +325,38 @@ def test_random_index_and_long_reads_vs_oracle(mk):
     ix.close()
 
 
+def test_whole_genome_query_crosses_counter_chunks(mk):
+    """A query with more than 65,504 surviving buckets (a 1.2 Mbp sequence at -h 17) makes the scan
+    spill its 16-plane carry-save counters and accumulate across chunks (F_ACCUM path)."""
+    rng = np.random.default_rng(21)
+    k, h = 31, 17
+    base = np.frombuffer(rand_seq(rng, 1_200_000), np.uint8)
+    genomes = []
+    for i in range(5):
+        g = base.copy()
+        m = rng.random(len(g)) < 0.002 * i
+        g[m] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        genomes.append(g.tobytes())
+    genomes.append(rand_seq(rng, 300_000))
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.insert_sequences(genomes)
+    o = orc.Oracle(k=k, h=h, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    q = [genomes[2], genomes[0][:700_000], genomes[5]]
+    counts, surv = ix.query_counts(q)
+    assert surv[0] > 65_504
+    for i, s in enumerate(q):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa
+        assert np.array_equal(counts[i], oc), i
+    hits = ix.query(q, 10, 10, 0.0)
+    for i, s in enumerate(q):
+        oh = o.query(s, 10, 10, 0.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+    ix.close()
+
+
 def test_wide_index_tiles_and_padding(mk):
     """Index wider than one scan tile is not testable cheaply with real sketches; import a
     random matrix instead (N = 20,001: two genome tiles, ragged last 16-byte group) and
