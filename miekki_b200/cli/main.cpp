@@ -262,6 +262,12 @@ void dump_disk(Index& ix, const string& path) {
     w.write(bloom.data(), bloom.size());
     w.write(ss.data(), ss.size() * 4);
     w.close();
+    // file_names is not part of the dump (quirk G4: the reference's `-i ... -e` crashes).  A
+    // side-car `<dump>.names` keeps them, one path per id; the dump itself stays byte-compatible.
+    if (!ix.file_names.empty()) {
+        ofstream names((path + ".names").c_str());
+        for (const string& s : ix.file_names) names << s << "\n";
+    }
 }
 
 bool load_disk(Index& ix, const string& path) {
@@ -308,6 +314,10 @@ bool load_disk(Index& ix, const string& path) {
     }
     ix.seal_shards();      // every shard already holds the whole Bloom table: the fold is a no-op
     ix.compressed_flag = false;                                   // :705
+    if (exists_test(path + ".names")) {      // side-car written by our -d: makes `-i ... -e` work
+        vector<string> names = read_list(path + ".names");
+        if (names.size() == n) ix.file_names = names;
+    }
     return true;
 }
 

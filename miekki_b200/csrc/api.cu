@@ -85,6 +85,7 @@ struct mk_ctx {
     void* meta_pin[2] = {nullptr, nullptr};
     size_t meta_pin_cap[2] = {0, 0};
     int meta_flip = 0;
+    cudaEvent_t meta_ev[2] = {nullptr, nullptr};
     unsigned long long* d_stat = nullptr;   // device work counters: rows, row bytes
 
     std::vector<cudaEvent_t> ev_pool;
@@ -502,6 +503,9 @@ constexpr uint64_t SPARSE_MAX_KMERS = 12288;   // 16384-slot table at load <= 0.
 // make the host wait for work already queued on the stream, which mk_scan_async relies on
 int pinned_meta(mk_ctx* c, size_t bytes, void** out) {
     const int w = (c->meta_flip ^= 1);
+    // the copy that last read this area must have run before the host overwrites it
+    if (c->meta_ev[w]) CU(cudaEventSynchronize(c->meta_ev[w]));
+    else CU(cudaEventCreateWithFlags(&c->meta_ev[w], cudaEventDisableTiming));
     if (bytes > c->meta_pin_cap[w]) {
         CU(cudaStreamSynchronize(c->stream));
         if (c->meta_pin[w]) CU(cudaFreeHost(c->meta_pin[w]));
@@ -514,8 +518,12 @@ int pinned_meta(mk_ctx* c, size_t bytes, void** out) {
     return MK_OK;
 }
 
-int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
-    const uint32_t n = b->n;
+// lists of reads [first, first + n) of a batch; all indices inside are relative to `first`
+int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists* out) {
+    const uint64_t* b_len = b->h_len.data() + first;
+    const uint64_t* b_coff = b->h_coff.data() + first;
+    const uint64_t* bd_coff = b->d_coff + first;
+    const uint64_t* bd_len = b->d_len + first;
     void* pin = nullptr;
     TRY(pinned_meta(c, ((size_t)n + 1) * 8 + (size_t)n * 4 + 64, &pin));
     uint64_t* off = static_cast<uint64_t*>(pin);
@@ -524,7 +532,7 @@ int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
     uint64_t total = 0, sparse_max = 0;
     for (uint32_t i = 0; i < n; ++i) {
         off[i] = total;
-        const uint64_t len = b->h_len[i];
+        const uint64_t len = b_len[i];
         const uint64_t nk = len > c->k ? len - c->k : 0;
         // a list can hold at most one entry per k-mer and per bucket
         total += std::min<uint64_t>(nk, c->B);
@@ -557,10 +565,11 @@ int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
         CU(cudaMemcpyAsync(d_ids, ids, n_ids * 4, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += n_ids * 4;
     }
+    CU(cudaEventRecord(c->meta_ev[c->meta_flip], c->stream));   // pinned area free again after this
     auto* list = static_cast<uint32_t*>(c->list.p);
     PhaseTimer t(c, PH_READ_SKETCH);
     if (!sparse_ids.empty()) {
-        int r = launch_sketch_reads(b->chars, b->d_coff, b->d_len, d_ids, (uint32_t)sparse_ids.size(),
+        int r = launch_sketch_reads(b->chars, bd_coff, bd_len, d_ids, (uint32_t)sparse_ids.size(),
                                     sparse_max, c->sp(), c->bloom, d_off, list, d_len, c->stream);
         if (r != 0) return fail(c, MK_ERR_CUDA, "sketch_reads launch configuration failed");
         c->stats.kernel_launches += 1;
@@ -576,8 +585,8 @@ int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
             uint64_t max_len = 0, bases = 0;
             for (uint32_t i = 0; i < m; ++i) {
                 const uint32_t rid = dense_ids[first + i];
-                coff[i] = b->h_coff[rid];
-                len[i] = b->h_len[rid];
+                coff[i] = b_coff[rid];
+                len[i] = b_len[rid];
                 max_len = std::max(max_len, len[i]);
                 bases += len[i];
             }
@@ -600,7 +609,7 @@ int build_lists(mk_ctx* c, const mk_batch* b, Lists* out) {
     out->list = list;
     out->list_off = d_off;
     out->list_len = d_len;
-    c->stats.bases_queried += b->bases;
+    for (uint32_t i = 0; i < n; ++i) c->stats.bases_queried += b_len[i];
     return MK_OK;
 }
 
@@ -658,52 +667,75 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     } else {
         CU(cudaMemsetAsync(d_hlen, 0, (size_t)n * 4, c->stream));
     }
-    Lists L{};
-    TRY(build_lists(c, b, &L));
-    if (c->n > 0) {
-        ScanPlan plan{};
-        if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
-            return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
-        // Sub-batches of reads, two count tiles: the top-k of tile i runs on the aux stream
-        // while the (DRAM-bound, persistent) scan of tile i+1 runs on the main one.
-        const uint32_t qb = std::max<uint32_t>(1, scan_batch_reads(c, n) / 2);
-        const uint64_t n_pad = (c->n + 31) / 32 * 32;
-        TRY(reserve(c, c->counts, (size_t)qb * n_pad * 4));
-        TRY(reserve(c, c->counts2, (size_t)qb * n_pad * 4));
-        uint32_t* tile[2] = {static_cast<uint32_t*>(c->counts.p), static_cast<uint32_t*>(c->counts2.p)};
-        cudaEvent_t scanned[2] = {get_event(c), get_event(c)}, done[2] = {get_event(c), get_event(c)};
-        bool busy[2] = {false, false};
-        int rc = MK_OK;
-        uint32_t i = 0;
-        for (uint32_t q0 = 0; q0 < n && rc == MK_OK; q0 += qb, ++i) {
-            const uint32_t nq = std::min(qb, n - q0);
-            const int s = (int)(i & 1);
-            if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);     // tile s is free again
-            rc = scan_reads(c, L, q0, nq, plan, tile[s]);
-            if (rc != MK_OK) break;
-            cudaEventRecord(scanned[s], c->stream);
-            cudaStreamWaitEvent(c->aux_stream, scanned[s], 0);
-            {
-                PhaseTimer t(c, PH_TOPK, c->aux_stream);
-                launch_topk(tile[s], nq, c->n, c->first_id, c->d_sketch_size, c->d_genome_size, c->d_ratio, K, min_score,
-                            min_int, d_heap + (size_t)q0 * K, d_hlen + q0, finalize, c->aux_stream);
-            }
-            cudaEventRecord(done[s], c->aux_stream);
-            busy[s] = true;
-            c->stats.kernel_launches += 1;
+    // Slices of reads bound the list memory (one u32 per k-mer at most): 1M reads of 10 kbp
+    // would otherwise ask for 40 GB of lists.  Each slice is sketched once, then scanned in
+    // sub-batches into two count tiles: the top-k of tile i runs on the aux stream while the
+    // (DRAM-bound, persistent) scan of tile i+1 runs on the main one.
+    uint64_t LIST_BUDGET = 768ull << 20;                       // entries (3 GiB)
+    if (const char* e = getenv("MIEKKI_LIST_BUDGET_ENTRIES")) LIST_BUDGET = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    ScanPlan plan{};
+    if (c->n > 0 && scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
+        return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
+    const uint64_t n_pad = (c->n + 31) / 32 * 32;
+    cudaEvent_t scanned[2] = {get_event(c), get_event(c)}, done[2] = {get_event(c), get_event(c)};
+    bool busy[2] = {false, false};
+    int rc = MK_OK;
+    uint32_t tile_no = 0;
+    for (uint32_t first = 0; first < n && rc == MK_OK;) {
+        uint32_t cnt = 0;
+        uint64_t entries = 0;
+        while (first + cnt < n) {
+            const uint64_t len = b->h_len[first + cnt];
+            const uint64_t e = std::min<uint64_t>(len > c->k ? len - c->k : 0, c->B);
+            if (cnt && entries + e > LIST_BUDGET) break;
+            entries += e;
+            ++cnt;
         }
-        for (int s = 0; s < 2; ++s)
-            if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);
+        // the lists of the previous slice are still read by its last scans: same stream, ordered
+        Lists L{};
+        rc = build_lists(c, b, first, cnt, &L);
+        if (rc != MK_OK) break;
+        if (c->n > 0) {
+            const uint32_t qb = std::max<uint32_t>(1, scan_batch_reads(c, cnt) / 2);
+            rc = reserve(c, c->counts, (size_t)qb * n_pad * 4);
+            if (rc == MK_OK) rc = reserve(c, c->counts2, (size_t)qb * n_pad * 4);
+            if (rc != MK_OK) break;
+            uint32_t* tile[2] = {static_cast<uint32_t*>(c->counts.p), static_cast<uint32_t*>(c->counts2.p)};
+            for (uint32_t q0 = 0; q0 < cnt && rc == MK_OK; q0 += qb, ++tile_no) {
+                const uint32_t nq = std::min(qb, cnt - q0);
+                const int s = (int)(tile_no & 1);
+                if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);     // tile s is free again
+                rc = scan_reads(c, L, q0, nq, plan, tile[s]);
+                if (rc != MK_OK) break;
+                cudaEventRecord(scanned[s], c->stream);
+                cudaStreamWaitEvent(c->aux_stream, scanned[s], 0);
+                {
+                    PhaseTimer t(c, PH_TOPK, c->aux_stream);
+                    launch_topk(tile[s], nq, c->n, c->first_id, c->d_sketch_size, c->d_genome_size, c->d_ratio, K,
+                                min_score, min_int, d_heap + (size_t)(first + q0) * K, d_hlen + first + q0, finalize,
+                                c->aux_stream);
+                }
+                cudaEventRecord(done[s], c->aux_stream);
+                busy[s] = true;
+                c->stats.kernel_launches += 1;
+            }
+        }
+        if (rc == MK_OK) rc = account_lists(c, L, cnt, nullptr);
+        first += cnt;
+    }
+    for (int s = 0; s < 2; ++s)
+        if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);
+    {
         cudaError_t le = cudaGetLastError();
         if (cudaStreamSynchronize(c->aux_stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
             le != cudaSuccess)
             rc = rc != MK_OK ? rc : fail(c, MK_ERR_CUDA, std::string("query pipeline: ") + cudaGetErrorString(le));
-        for (int s = 0; s < 2; ++s) {
-            c->ev_pool.push_back(scanned[s]);
-            c->ev_pool.push_back(done[s]);
-        }
-        if (rc != MK_OK) return rc;
     }
+    for (int s = 0; s < 2; ++s) {
+        c->ev_pool.push_back(scanned[s]);
+        c->ev_pool.push_back(done[s]);
+    }
+    if (rc != MK_OK) return rc;
     if (heap_io) {
         CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDeviceToHost, c->stream));
         c->stats.d2h_bytes += (size_t)n * K * sizeof(HitDev);
@@ -712,7 +744,6 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
         CU(cudaMemcpyAsync(len_io, d_hlen, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
         c->stats.d2h_bytes += (size_t)n * 4;
     }
-    TRY(account_lists(c, L, n, nullptr));
     return sync(c);
 }
 
@@ -734,7 +765,7 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
         CU(cudaEventCreateWithFlags(&c->slot_ev[1], cudaEventDisableTiming));
     }
     Lists L{};
-    TRY(build_lists(c, b, &L));
+    TRY(build_lists(c, b, 0, n, &L));
     DevBuf& tile = slot ? c->counts2 : c->counts;
     if (c->n > 0) {
         ScanPlan plan{};
@@ -881,6 +912,8 @@ void mk_destroy(mk_ctx* c) {
     for (void* p : c->meta_pin)
         if (p) cudaFreeHost(p);
     for (cudaEvent_t e : c->slot_ev)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->meta_ev)
         if (e) cudaEventDestroy(e);
     for (auto& pe : c->ev_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1217,7 +1250,7 @@ int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, ui
     TRY(upload_range(c, seqs, lens, n, &b));
     auto body = [&]() -> int {
         Lists L{};
-        TRY(build_lists(c, b, &L));
+        TRY(build_lists(c, b, 0, n, &L));
         if (c->n) {
             ScanPlan plan{};
             if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)

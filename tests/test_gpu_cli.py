@@ -57,6 +57,13 @@ def test_cli_exact_mode(tmp_path, s, fname):
     got = [l for l in out.read_text().split("\n") if l]
     want = [l for l in open(os.path.join(d, fname)).read().split("\n") if l]
     assert Counter(got) == Counter(want)
+    # `-i dump -e`: the reference crashes (file names are not in the dump, quirk G4); our -d
+    # leaves a side-car <dump>.names, so exact mode also works from a loaded index
+    dump, out2 = tmp_path / "idx.gz", tmp_path / "exact2.txt"
+    run_cli(["-l", "list.txt", "-k", 31, "-h", 12, "-s", s, "-d", dump, "-o", tmp_path / "unused.txt"], d)
+    assert os.path.exists(str(dump) + ".names")
+    run_cli(["-i", dump, "-a", "reads.fa", "-e", "-o", out2], d)
+    assert Counter(l for l in out2.read_text().split("\n") if l) == Counter(want)
 
 
 def test_cli_whole_file_queries(tmp_path):

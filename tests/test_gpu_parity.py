@@ -174,6 +174,18 @@ def test_case_a_sharded_chain_equals_unsharded(mk, case_a):
         x.close()
 
 
+def test_case_a_read_slices_bound_list_memory(mk, case_a, monkeypatch):
+    """mk_query cuts a batch into slices of reads so that list memory stays bounded; with a tiny
+    budget (several slices, slices of one read) the lines must not change."""
+    d, ix, _ = case_a
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    want = open(os.path.join(d, "hits_s200.txt")).read()
+    for budget in (1, 3000, 20000):
+        monkeypatch.setenv("MIEKKI_LIST_BUDGET_ENTRIES", str(budget))
+        assert gpu_hit_lines(ix, reads, 200, chunk=64) == want
+    monkeypatch.delenv("MIEKKI_LIST_BUDGET_ENTRIES")
+
+
 def test_case_a_pipelined_scan_and_topk_slots(mk, case_a):
     """mk_scan_async / mk_topk_slot: two read batches in flight (scan of the second enqueued
     before the first one's heap step) give the same lists as the plain query."""
