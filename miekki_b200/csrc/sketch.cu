@@ -10,6 +10,8 @@
 //   * a fingerprint of 255 never registers (Miekki.cpp:172 with res[] preset to 255);
 //   * Bloom bytes: the byte value belongs to the smallest (genome, bucket, probe) that maps
 //     to it (order-independent restatement of Miekki.cpp:295-299).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -101,7 +103,7 @@ encode_planes_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restri
 __global__ void __launch_bounds__(256)
 sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restrict__ planeR,
                     const uint64_t* __restrict__ len, const uint64_t* __restrict__ woff, int k, int h,
-                    unsigned long long* __restrict__ keys) {
+                    unsigned long long* __restrict__ keys, int prefilter) {
     const uint32_t s = blockIdx.y;
     const uint64_t n = len[s];
     if (n <= (uint64_t)k) return;
@@ -122,8 +124,13 @@ sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restr
             if (pos < nk) {
                 const uint64_t x = kmer_hash(f0, f1, f2, r0, r1, r2, j, k, kmask);
                 const uint32_t fp = mantis(x & pmask, h);
-                if (fp != EMPTY_FP)
-                    atomicMin(kz + (x >> (64 - h)), ((unsigned long long)fp << POS_BITS) | pos);
+                if (fp != EMPTY_FP) {
+                    unsigned long long* slot = kz + (x >> (64 - h));
+                    const unsigned long long key = ((unsigned long long)fp << POS_BITS) | pos;
+                    // Keys only ever decrease, so a (possibly stale) read that is already <= key
+                    // proves the atomic would change nothing: most k-mers of a bucket lose.
+                    if (!prefilter || key < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, key);
+                }
             }
         }
     }
@@ -532,7 +539,11 @@ void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const u
     if (!n_seq || max_len <= (uint64_t)k) return;
     const uint64_t nwk = (max_len - k + 15) / 16;
     dim3 grid(blocks_for(nwk, 256, 148 * 16), n_seq);
-    sketch_dense_kernel<<<grid, 256, 0, st>>>(planeF, planeR, len, woff, k, h, keys);
+    static const int prefilter = [] {
+        const char* e = getenv("MIEKKI_SKETCH_PREFILTER");
+        return e ? atoi(e) : 0;   // measured: no gain at -h 17, -13 % at -h 20 (a RED costs about a read)
+    }();
+    sketch_dense_kernel<<<grid, 256, 0, st>>>(planeF, planeR, len, woff, k, h, keys, prefilter);
 }
 
 void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const uint32_t* planeR,
