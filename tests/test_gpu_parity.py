@@ -407,6 +407,40 @@ def test_synthetic_generator_matches_host(mk):
     ix.close()
 
 
+def test_empty_and_degenerate_inputs(mk):
+    """Empty index, empty batches, reads with no valid k-mer, low-complexity sequences."""
+    k, h = 31, 10
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    rng = np.random.default_rng(8)
+    r1 = rand_seq(rng, 500)
+    # empty index: every read gets an empty list (and an output line in the CLI)
+    assert [len(x) for x in ix.query([r1, b"ACGT", b""], 10, 0, 0.0)] == [0, 0, 0]
+    c, surv = ix.query_counts([r1])
+    assert c.shape == (1, 0) and surv[0] == 0          # nothing is in the Bloom filter yet
+    assert ix.query([]) == []
+    ix.insert_sequences([])                              # no-op
+    assert ix.n == 0
+    genomes = [rand_seq(rng, 20_000), b"A" * 5_000, b"N" * 3_000, (b"ACGT" * 2_000), b"acgt" * 1_000 + r1]
+    ix.insert_sequences(genomes)
+    o = orc.Oracle(k=k, h=h, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    e = ix.export()
+    assert np.array_equal(e["rows"], o.rows)
+    assert np.array_equal(e["sketch_size"], o.sketch_size) and np.array_equal(e["genome_size"], o.genome_size)
+    reads = [b"A" * 200, b"N" * 200, b"ACGT" * 50, genomes[0][100:400], b"acgt" * 50, r1, b"", b"ACGTN" * 30,
+             genomes[0][:31], genomes[0][:32]]
+    counts, surv = ix.query_counts(reads)
+    hits = ix.query(reads, 10, 1, 0.0)
+    for i, s in enumerate(reads):
+        oc, oa = (o.counts(s) if len(s) >= 1 else (np.zeros(len(genomes), np.uint32), 0))
+        assert surv[i] == oa, i
+        assert np.array_equal(counts[i], oc), i
+        oh = o.filter(oc, 10, 1, 0.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+    ix.close()
+
+
 def test_errors(mk):
     with pytest.raises(mk.MiekkiError):
         mk.Miekki(k=32)
