@@ -22,8 +22,8 @@ $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -cudart static -ccbin $(CXX) -o $@ $(OBJS) -lpthread
 
-$(CLI): miekki_b200/cli/main.cpp miekki_b200/cli/fasta.hpp include/miekki_b200.h $(LIB)
-	$(CXX) -O2 -std=c++17 -Wall -Wextra -fopenmp -Iinclude -o $@ miekki_b200/cli/main.cpp \
+$(CLI): miekki_b200/cli/miekki_cli.cpp miekki_b200/cli/fasta.hpp include/miekki_b200.h $(LIB)
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -fopenmp -Iinclude -o $@ miekki_b200/cli/miekki_cli.cpp \
 	    -Lmiekki_b200 -lmiekki_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
 
 oracle:

@@ -50,29 +50,43 @@ string int_to_string(uint64_t n) {
     return int_to_string(n / 1000) + ",00" + end;
 }
 
-void help() {   // main.cpp:102-121
-    cout << "This is a help message" << endl;
-    cout << "Input " << endl;
-    cout << "-i load a constructed index from disk" << endl;
-    cout << "-l construct an index from a list of file" << endl;
-    cout << "-a query a fasta file" << endl;
-    cout << "-A query  fasta from file of file" << endl;
-    cout << "\nOutput " << endl;
-    cout << "-o output file name (out.txt)" << endl;
-    cout << "-d dump the index on disk" << endl;
-    cout << "\nPerformances " << endl;
-    cout << "-h use 2^h minimizers per sequence (17)" << endl;
-    cout << "-k kmer size (31)" << endl;
-    cout << "-s minimal estimated intersection to be reported (200)" << endl;
-    cout << "-t host thread number (8)" << endl;
-    cout << "\nAdvanced usage " << endl;
-    cout << "-f fingerprint size " << endl;
-    cout << "-b 2^b bits used for the bloom filter  " << endl;
-    cout << "-e exact mode, real intersection will be computed on hits" << endl;
-    cout << "\nB200 " << endl;
-    cout << "--device N  first CUDA device ordinal (0)" << endl;
-    cout << "--gpus N    shard the genomes over N GPUs (1)" << endl;
-    cout << "--devices a,b,..  explicit device ordinal per shard" << endl;
+// One table drives both the usage text and the option parser.  Letters, arities and defaults
+// are the reference's (getopt string "i:l:a:h:t:f:k:s:b:o:ed:A:", main.cpp:130-137); note that -h
+// takes a value (it is not "help") and that the real defaults are h=17, t=8, s=200 (quirk G11).
+struct OptionDoc {
+    const char* section;
+    const char* flag;
+    const char* text;
+};
+const OptionDoc kOptions[] = {
+    {"Input", "-i <dump>", "load an index written by -d (its k, h, b, s override the flags)"},
+    {"Input", "-l <list>", "build an index from a file of genome FASTA paths (plain or gz), one per line"},
+    {"Input", "-a <fasta>", "query every 2-line record (header, sequence) of a FASTA file"},
+    {"Input", "-A <list>", "query whole files: each listed FASTA is one query"},
+    {"Output", "-o <file>", "result file (out.txt)"},
+    {"Output", "-d <file>", "write the index as a gz dump for later -i"},
+    {"Sketch", "-h <n>", "2^n fingerprints per genome (17)"},
+    {"Sketch", "-k <n>", "k-mer size, at most 31 (31)"},
+    {"Sketch", "-s <x>", "smallest estimated intersection worth reporting (200)"},
+    {"Sketch", "-t <n>", "host threads for parsing and formatting (8)"},
+    {"Advanced", "-f <n>", "fingerprint mantissa bits; only 3 (8-bit fingerprints) is implemented"},
+    {"Advanced", "-b <n>", "log2 of the Bloom filter size in bits, at least 32 (33)"},
+    {"Advanced", "-e", "exact mode: recompute the true k-mer intersection of every hit"},
+    {"B200", "--gpus <n>", "shard the genomes over n GPUs of this box (1)"},
+    {"B200", "--device <n>", "first CUDA device ordinal (0)"},
+    {"B200", "--devices a,b,..", "explicit device ordinal per shard"},
+};
+
+void help() {
+    cout << "This is a help message" << endl;       // first line as in main.cpp:103
+    const char* section = "";
+    for (const OptionDoc& o : kOptions) {
+        if (string(section) != o.section) {
+            section = o.section;
+            cout << "\n" << section << endl;
+        }
+        cout << "  " << o.flag << "  " << o.text << endl;
+    }
 }
 
 [[noreturn]] void die(mk_ctx* ctx, const char* what) {
@@ -605,29 +619,28 @@ int main(int argc, char** argv) {
                                       {"devices", required_argument, nullptr, 1002},
                                       {nullptr, 0, nullptr, 0}};
     int c;
+    // string-valued and numeric flags are bound to their variables once; the loop is generic
+    const map<int, string*> text_flags = {{'i', &index_file}, {'l', &list_file},  {'a', &query_fa},
+                                          {'A', &query_list}, {'o', &output_file}, {'d', &index_dump}};
+    const map<int, uint64_t*> count_flags = {{'h', &H}, {'t', &core_number}, {'k', &kmer_size},
+                                             {'f', &fingerprint_size}, {'b', &bloom_size}};
     while ((c = getopt_long(argc, argv, "i:l:a:h:t:f:k:s:b:o:ed:A:", longopts, nullptr)) != -1) {
-        switch (c) {
-            case 'i': index_file = optarg; break;
-            case 'l': list_file = optarg; break;
-            case 'a': query_fa = optarg; break;
-            case 'A': query_list = optarg; break;
-            case 'o': output_file = optarg; break;
-            case 'h': H = stoi(optarg); break;
-            case 't': core_number = stoi(optarg); break;
-            case 'k': kmer_size = stoi(optarg); break;
-            case 's': threshold = stof(optarg); break;
-            case 'f': fingerprint_size = stoi(optarg); break;
-            case 'b': bloom_size = stoi(optarg); break;
-            case 'e': exact_mode = true; break;
-            case 'd': index_dump = optarg; break;
-            case 1000: device = stoi(optarg); break;
-            case 1001: gpus = max(1, stoi(optarg)); break;
-            case 1002: {
-                stringstream ss(optarg);
-                string tok;
-                while (getline(ss, tok, ',')) devices.push_back(stoi(tok));
-                break;
-            }
+        if (auto t = text_flags.find(c); t != text_flags.end()) {
+            *t->second = optarg;
+        } else if (auto n = count_flags.find(c); n != count_flags.end()) {
+            *n->second = (uint64_t)stoi(optarg);
+        } else if (c == 's') {
+            threshold = stof(optarg);
+        } else if (c == 'e') {
+            exact_mode = true;
+        } else if (c == 1000) {
+            device = stoi(optarg);
+        } else if (c == 1001) {
+            gpus = max(1, stoi(optarg));
+        } else if (c == 1002) {
+            stringstream ss(optarg);
+            string tok;
+            while (getline(ss, tok, ',')) devices.push_back(stoi(tok));
         }
     }
     const uint32_t bit_per_min = (uint32_t)(5 + fingerprint_size);
