@@ -407,6 +407,56 @@ def test_synthetic_generator_matches_host(mk):
     ix.close()
 
 
+def test_sketch_arbitrary_bytes_fuzz(mk):
+    """Any byte is legal input (NUL, high-bit, lowercase, IUPAC): the reference maps what it does
+    not know to code 0 on both strands (utils.cpp:31-49,107-125).  200 random strings."""
+    rng = np.random.default_rng(99)
+    ix = mk.Miekki(k=21, h=9)
+    alphabets = [np.arange(256, dtype=np.uint8), np.frombuffer(b"ACGTacgtNnRYKM-*\x00\xff", np.uint8),
+                 np.frombuffer(b"ACGTN", np.uint8)]
+    for it in range(200):
+        al = alphabets[it % 3]
+        n = int(rng.integers(0, 900))
+        s = al[rng.integers(0, len(al), n)].tobytes()
+        fp, anc, act = ix.sketch(s)
+        ofp, oanc, oact = orc.sketch(s, 21, 9)
+        assert act == oact and np.array_equal(fp, ofp) and np.array_equal(anc, oanc), (it, n)
+    ix.close()
+
+
+@pytest.mark.parametrize("k,h,b,nres", [(2, 1, 32, 1), (3, 5, 33, 3), (11, 13, 36, 64), (16, 9, 40, 10),
+                                        (17, 18, 33, 10), (31, 22, 34, 5), (25, 7, 32, 12)])
+def test_parameter_corners_vs_oracle(mk, k, h, b, nres):
+    """Corners of the parameter space (k 2..31, h 1..22, b 32..40, nresults 1..64): index, counts
+    and hit lists against the oracle on small seeded inputs."""
+    rng = np.random.default_rng(k * 1000 + h)
+    base = rand_seq(rng, 6000, special=True)
+    genomes = [base, rand_seq(rng, 3000), base[:2000] + rand_seq(rng, 2500), rand_seq(rng, 40 + k),
+               base[1000:5000]]
+    ix = mk.Miekki(k=k, h=h, b=b, threshold=2)
+    ix.insert_sequences(genomes)
+    o = orc.Oracle(k=k, h=h, b=b, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    e = ix.export()
+    assert np.array_equal(e["rows"], o.rows)
+    assert np.array_equal(e["sketch_size"], o.sketch_size)
+    assert np.array_equal(e["genome_size"], o.genome_size)
+    m = min(len(e["bloom"]), len(o.bloom))
+    assert np.array_equal(e["bloom"][:m], o.bloom[:m])
+    reads = [base[100:700], base[3000:3300], genomes[1][5:900], rand_seq(rng, 300), genomes[3], base[:k + 1]]
+    counts, surv = ix.query_counts(reads)
+    hits = ix.query(reads, nres, 1, 1.0)
+    for i, s in enumerate(reads):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa, i
+        assert np.array_equal(counts[i], oc), i
+        oh = o.filter(oc, nres, 1, 1.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+        np.testing.assert_allclose(hits[i]["intersection"], oh["intersection"], rtol=REL_TOL, atol=0)
+    ix.close()
+
+
 def test_empty_and_degenerate_inputs(mk):
     """Empty index, empty batches, reads with no valid k-mer, low-complexity sequences."""
     k, h = 31, 10
