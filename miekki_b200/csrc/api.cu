@@ -407,8 +407,7 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
         w += (v.h_len[i] + 15) / 16 + 2;
     }
     woff[n] = w;
-    TRY(reserve(c, c->planeF, (w + 4) * 4));
-    TRY(reserve(c, c->planeR, (w + 4) * 4));
+    TRY(reserve(c, c->planeF, (w + 4) * 8));      // F and R words interleaved: {F, R} per 16 bases
     TRY(reserve(c, c->keys, (size_t)n * c->B * 8));
     TRY(reserve(c, c->fp, (size_t)n * c->B * 2));     // fp[n][B] | Bloom claim flags[n][B]
     const size_t meta_bytes = ((size_t)n + 1) * 8 + (size_t)n * 8 + (size_t)n * 8;
@@ -421,10 +420,10 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
     auto* keys = static_cast<unsigned long long*>(c->keys.p);
     launch_fill_u64(keys, (uint64_t)n * c->B, ~0ull, c->stream);
     launch_encode_planes(v.chars, v.d_coff, v.d_len, d_woff, n, v.max_len, (int)c->k,
-                         static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeR.p), c->stream);
-    launch_sketch_dense(static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeR.p), v.d_len,
+                         static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, c->stream);
+    launch_sketch_dense(static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, v.d_len,
                         d_woff, n, v.max_len, (int)c->k, (int)c->h, keys, c->stream);
-    launch_resolve(keys, static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeR.p), d_woff, n,
+    launch_resolve(keys, static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, d_woff, n,
                    c->sp(), static_cast<uint8_t*>(c->fp.p), d_active, d_ssum, c->bloom,
                    bloom_insert ? c->owner : nullptr, c->stream);
     c->stats.kernel_launches += 4;

@@ -15,6 +15,7 @@ struct SketchParams {
 // Dense path (genomes, long reads): sequences -> 2-bit planes -> per-bucket min key.
 //   chars     : concatenated ASCII, sequence s at chars + coff[s] (16-byte aligned)
 //   woff[s]   : first plane word of sequence s (each sequence owns ceil(len/16)+2 words)
+//   planes    : interleaved, planeR == planeF + 1 and word w of a plane sits at index 2 w
 //   keys      : n_seq x 2^h u64, pre-set to ~0; afterwards fp << 56 | first position
 void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
                           const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k,

@@ -94,8 +94,11 @@ encode_planes_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restri
             const bool pv = (16 * w < (uint64_t)(k - 1)) ? prefix_valid(seq, n, k, lut) : true;
             encode_word(seq, n, w, k, pv, lut, F, R);
         }
-        planeF[woff[s] + w] = F;
-        planeR[woff[s] + w] = R;
+        // the two planes are interleaved word by word (planeR == planeF + 1): the three words a
+        // k-mer needs from each plane are then 24 contiguous bytes, i.e. one or two sectors
+        // instead of two to four for the random look-ups of resolve_kernel
+        *reinterpret_cast<uint2*>(planeF + 2 * (woff[s] + w)) = make_uint2(F, R);
+        (void)planeR;
     }
 }
 
@@ -111,13 +114,14 @@ sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restr
     const uint64_t nwk = (nk + 15) / 16;
     const uint64_t kmask = (1ull << (2 * k)) - 1;
     const uint64_t pmask = (1ull << (64 - h)) - 1;
-    const uint32_t* F = planeF + woff[s];
-    const uint32_t* R = planeR + woff[s];
+    const uint2* P = reinterpret_cast<const uint2*>(planeF) + woff[s];   // .x = F word, .y = R word
+    (void)planeR;
     unsigned long long* kz = keys + ((uint64_t)s << h);
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwk;
          w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t f0 = F[w], f1 = F[w + 1], f2 = F[w + 2];
-        const uint32_t r0 = R[w], r1 = R[w + 1], r2 = R[w + 2];
+        const uint2 p0 = P[w], p1 = P[w + 1], p2 = P[w + 2];
+        const uint32_t f0 = p0.x, f1 = p1.x, f2 = p2.x;
+        const uint32_t r0 = p0.y, r1 = p1.y, r2 = p2.y;
         #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const uint64_t pos = 16 * w + j;
@@ -137,12 +141,11 @@ sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restr
 }
 
 // hash of the k-mer starting at `pos`, from the planes in global memory
-__device__ __forceinline__ uint64_t hash_at(const uint32_t* __restrict__ F,
-                                            const uint32_t* __restrict__ R, uint64_t pos, int k) {
+__device__ __forceinline__ uint64_t hash_at(const uint2* __restrict__ P, uint64_t pos, int k) {
     const uint64_t w = pos >> 4;
     const int j = (int)(pos & 15);
-    return kmer_hash(F[w], F[w + 1], F[w + 2], R[w], R[w + 1], R[w + 2], j, k,
-                     (1ull << (2 * k)) - 1);
+    const uint2 a = P[w], b = P[w + 1], c = P[w + 2];
+    return kmer_hash(a.x, b.x, c.x, a.y, b.y, c.y, j, k, (1ull << (2 * k)) - 1);
 }
 
 // key = (seq_in_batch, bucket, probe) packed so that u32 order == lexicographic order
@@ -167,7 +170,7 @@ resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __rest
         const uint32_t fp = (uint32_t)(key >> POS_BITS);
         unsigned long long anc = EMPTY_ANC;
         if (fp != EMPTY_FP) {
-            anc = hash_at(planeF + woff[s], planeR + woff[s], key & POS_MASK, p.k);
+            anc = hash_at(reinterpret_cast<const uint2*>(planeF) + woff[s], key & POS_MASK, p.k);
             act = 1;
             sum = 1ull << (31 - (fp >> 3));       // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
             if (owner != nullptr) {               // Bloom pass A (Miekki.cpp:295-299)
