@@ -139,58 +139,7 @@ private:
     bool compressed_ = false, eof_ = false, z_done_ = false, first_plain_ = true;
 };
 
-// gzip level-1 writer (zstr::ofstream, zstr.hpp:82,230)
-class GzWriter {
-public:
-    explicit GzWriter(const std::string& path) : buf_(1 << 20) {
-        f_ = fopen(path.c_str(), "wb");
-        if (!f_) throw std::runtime_error("cannot open " + path);
-        memset(&zs_, 0, sizeof(zs_));
-        if (deflateInit2(&zs_, 1, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK)
-            throw std::runtime_error("deflateInit2 failed");
-    }
-    ~GzWriter() { close(); }
-    void write(const void* p, size_t n) {
-        const unsigned char* src = (const unsigned char*)p;
-        while (n) {
-            const size_t m = std::min<size_t>(n, 1u << 30);
-            zs_.next_in = const_cast<unsigned char*>(src);
-            zs_.avail_in = (uInt)m;
-            pump(Z_NO_FLUSH);
-            src += m;
-            n -= m;
-        }
-    }
-    void close() {
-        if (!f_) return;
-        zs_.next_in = nullptr;
-        zs_.avail_in = 0;
-        pump(Z_FINISH);
-        deflateEnd(&zs_);
-        fclose(f_);
-        f_ = nullptr;
-    }
-
-private:
-    void pump(int flush) {
-        for (;;) {
-            zs_.next_out = buf_.data();
-            zs_.avail_out = (uInt)buf_.size();
-            const int r = deflate(&zs_, flush);
-            fwrite(buf_.data(), 1, buf_.size() - zs_.avail_out, f_);
-            if (flush == Z_FINISH) {
-                if (r == Z_STREAM_END) return;
-            } else if (zs_.avail_in == 0 && zs_.avail_out != 0) {
-                return;
-            }
-        }
-    }
-    FILE* f_ = nullptr;
-    z_stream zs_;
-    std::vector<unsigned char> buf_;
-};
-
-// Parallel gzip-1 writer for the index dump: the payload is cut into 32 MiB chunks, each
+// Parallel gzip-1 writer for the index dump (zstr::ofstream writes gzip level 1, zstr.hpp:82,230): the payload is cut into 32 MiB chunks, each
 // deflated by its own thread into an independent gzip member, written in order.  Concatenated
 // members are a valid gzip file, and the reference's reader restarts its inflator at every
 // member end (zstr.hpp:193-197), so the dump stays loadable by the reference's -i.
