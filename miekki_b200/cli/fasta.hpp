@@ -139,8 +139,9 @@ private:
     bool compressed_ = false, eof_ = false, z_done_ = false, first_plain_ = true;
 };
 
-// Parallel gzip-1 writer for the index dump (zstr::ofstream writes gzip level 1, zstr.hpp:82,230): the payload is cut into 32 MiB chunks, each
-// deflated by its own thread into an independent gzip member, written in order.  Concatenated
+// Parallel gzip-1 writer for the index dump (zstr::ofstream writes gzip level 1,
+// zstr.hpp:82,230): the payload is cut into 32 MiB chunks, each deflated by its own thread
+// into an independent gzip member, written in order.  Concatenated
 // members are a valid gzip file, and the reference's reader restarts its inflator at every
 // member end (zstr.hpp:193-197), so the dump stays loadable by the reference's -i.
 class ParallelGzWriter {

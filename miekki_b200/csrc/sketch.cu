@@ -153,79 +153,151 @@ __device__ __forceinline__ uint32_t owner_key(uint32_t s, uint32_t bucket, uint3
     return (((s << h) | bucket) << 3) | i;
 }
 
+// The kernel is a chain of three dependent random look-ups per bucket (key -> plane words at
+// the winning position -> Bloom byte) and was purely latency bound with one bucket per thread
+// (ncu: 75 % long-scoreboard stalls, DRAM 8 %).  Each thread therefore walks RES_U buckets in
+// lock step, stage by stage, so that RES_U independent loads are in flight per stage.
+constexpr int RES_U = 4;
+
 __global__ void __launch_bounds__(256)
 resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __restrict__ planeF,
                const uint32_t* __restrict__ planeR, const uint64_t* __restrict__ woff, SketchParams p,
                uint8_t* __restrict__ fp_out, uint32_t* __restrict__ active,
                unsigned long long* __restrict__ ssum, const uint8_t* __restrict__ bloom,
                uint32_t* __restrict__ owner) {
+    (void)planeR;
     const uint32_t s = blockIdx.y;
     const uint32_t B = 1u << p.h;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint2* P = reinterpret_cast<const uint2*>(planeF) + woff[s];
+    const uint64_t row = (uint64_t)s << p.h;
+    const uint64_t claim_off = (uint64_t)gridDim.y << p.h;
+    const uint64_t kmask = (1ull << (2 * p.k)) - 1;
     uint32_t act = 0;
     unsigned long long sum = 0;
-    if (b < B) {
-        const uint64_t idx = ((uint64_t)s << p.h) + b;
-        const unsigned long long key = keys_anc[idx];
-        const uint32_t fp = (uint32_t)(key >> POS_BITS);
-        unsigned long long anc = EMPTY_ANC;
+
+    uint32_t b[RES_U];
+    unsigned long long key[RES_U];
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u) {                       // stage 1: keys (coalesced)
+        b[u] = (blockIdx.x * RES_U + u) * blockDim.x + threadIdx.x;
+        key[u] = b[u] < B ? keys_anc[row + b[u]] : EMPTY_KEY;
+    }
+    uint2 w0[RES_U], w1[RES_U], w2[RES_U];
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u) {                       // stage 2: plane words at the winning position
+        const uint64_t w = ((key[u] >> POS_BITS) != EMPTY_FP) ? ((key[u] & POS_MASK) >> 4) : 0;
+        w0[u] = P[w];
+        w1[u] = P[w + 1];
+        w2[u] = P[w + 2];
+    }
+    unsigned long long anc[RES_U];
+    uint64_t slot[RES_U][2];
+    uint32_t probe[RES_U][2];
+    int nd[RES_U];
+    uint8_t cell[RES_U][2];
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u) {                       // stage 3: hashes, Bloom bytes
+        const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
+        anc[u] = EMPTY_ANC;
+        nd[u] = 0;
+        cell[u][0] = cell[u][1] = 1;
         if (fp != EMPTY_FP) {
-            anc = hash_at(reinterpret_cast<const uint2*>(planeF) + woff[s], key & POS_MASK, p.k);
-            act = 1;
-            sum = 1ull << (31 - (fp >> 3));       // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
-            if (owner != nullptr) {               // Bloom pass A (Miekki.cpp:295-299)
-                BloomProbe pr(anc);
-                uint64_t slot[2];
-                uint32_t probe[2];
-                const int nd = bloom_first_probes(pr, p.bloom_log2, slot, probe);
-                uint8_t claimed = 0;
-                for (int j = 0; j < nd; ++j) {
-                    const uint64_t byte = slot[j] >> 3;
-                    if (byte < p.bloom_window && bloom[byte] == 0) {
-                        atomicMin(owner + byte, owner_key(s, b, probe[j], p.h));
-                        claimed = 1;
-                    }
+            const int j = (int)(key[u] & 15);
+            anc[u] = kmer_hash(w0[u].x, w1[u].x, w2[u].x, w0[u].y, w1[u].y, w2[u].y, j, p.k, kmask);
+            if (owner != nullptr) {
+                BloomProbe pr(anc[u]);
+                nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
+                for (int q = 0; q < nd[u]; ++q) {
+                    const uint64_t byte = slot[u][q] >> 3;
+                    cell[u][q] = byte < p.bloom_window ? bloom[byte] : (uint8_t)1;
                 }
-                // claim flags live behind the fp block: pass B only revisits claimants
-                fp_out[((uint64_t)gridDim.y << p.h) + idx] = claimed;
             }
         }
-        keys_anc[idx] = anc;
-        fp_out[idx] = (uint8_t)fp;
     }
-    // per-sequence statistics: warp reduce, one atomic per warp
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u) {                       // stage 4: claims and stores
+        if (b[u] >= B) continue;
+        const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
+        if (fp != EMPTY_FP) {
+            act += 1;
+            sum += 1ull << (31 - (fp >> 3));                // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
+            if (owner != nullptr) {                         // Bloom pass A (Miekki.cpp:295-299)
+                uint8_t claimed = 0;
+                for (int q = 0; q < nd[u]; ++q)
+                    if (cell[u][q] == 0) {
+                        atomicMin(owner + (slot[u][q] >> 3), owner_key(s, b[u], probe[u][q], p.h));
+                        claimed = 1;
+                    }
+                // claim flags live behind the fp block: pass B only revisits claimants
+                fp_out[claim_off + row + b[u]] = claimed;
+            }
+        }
+        keys_anc[row + b[u]] = anc[u];
+        fp_out[row + b[u]] = (uint8_t)fp;
+    }
+    // per-sequence statistics: warp shuffle, then one pair of atomics per block
+    __shared__ uint32_t s_act[8];
+    __shared__ unsigned long long s_sum[8];
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         act += __shfl_xor_sync(0xffffffffu, act, o);
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
     }
-    if ((threadIdx.x & 31) == 0 && act) {
-        atomicAdd(active + s, act);
-        atomicAdd(ssum + s, sum);
+    if ((threadIdx.x & 31) == 0) {
+        s_act[threadIdx.x >> 5] = act;
+        s_sum[threadIdx.x >> 5] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0;
+        unsigned long long t = 0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) { a += s_act[w]; t += s_sum[w]; }
+        if (a) {
+            atomicAdd(active + s, a);
+            atomicAdd(ssum + s, t);
+        }
     }
 }
 
 __global__ void __launch_bounds__(256)
 bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint8_t* __restrict__ fp,
                     SketchParams p, uint8_t* __restrict__ bloom, uint32_t* __restrict__ owner) {
+    // RES_U buckets per thread, stage by stage, like resolve_kernel (random owner look-ups)
     const uint32_t s = blockIdx.y;
     const uint32_t B = 1u << p.h;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const uint64_t idx = ((uint64_t)s << p.h) + b;
-    if (fp[idx] == EMPTY_FP) return;
-    if (fp[((uint64_t)gridDim.y << p.h) + idx] == 0) return;    // made no claim in pass A
-    BloomProbe pr(anc[idx]);
-    uint64_t slot[2];
-    uint32_t probe[2];
-    const int nd = bloom_first_probes(pr, p.bloom_log2, slot, probe);
-    for (int j = 0; j < nd; ++j) {
-        const uint64_t byte = slot[j] >> 3;
-        if (byte < p.bloom_window && owner[byte] == owner_key(s, b, probe[j], p.h)) {
-            bloom[byte] = (uint8_t)(1u << (slot[j] & 7));   // Miekki.cpp:128
-            owner[byte] = 0xFFFFFFFFu;                      // the winner also clears its claim
+    const uint64_t row = (uint64_t)s << p.h;
+    const uint64_t claim_off = (uint64_t)gridDim.y << p.h;
+    uint32_t b[RES_U];
+    bool live[RES_U];
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u) {
+        b[u] = (blockIdx.x * RES_U + u) * blockDim.x + threadIdx.x;
+        // claimants only: non-empty bucket that registered a claim in pass A
+        live[u] = b[u] < B && fp[row + b[u]] != EMPTY_FP && fp[claim_off + row + b[u]] != 0;
+    }
+    uint64_t slot[RES_U][2];
+    uint32_t probe[RES_U][2], own[RES_U][2];
+    int nd[RES_U];
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u) {
+        nd[u] = 0;
+        if (live[u]) {
+            BloomProbe pr(anc[row + b[u]]);
+            nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
+            for (int q = 0; q < nd[u]; ++q) {
+                const uint64_t byte = slot[u][q] >> 3;
+                own[u][q] = byte < p.bloom_window ? owner[byte] : 0xFFFFFFFFu;
+            }
         }
     }
+    #pragma unroll
+    for (int u = 0; u < RES_U; ++u)
+        for (int q = 0; q < nd[u]; ++q)
+            if (own[u][q] == owner_key(s, b[u], probe[u][q], p.h)) {
+                const uint64_t byte = slot[u][q] >> 3;
+                bloom[byte] = (uint8_t)(1u << (slot[u][q] & 7));   // Miekki.cpp:128
+                owner[byte] = 0xFFFFFFFFu;                          // the winner also clears its claim
+            }
 }
 
 // ---- bit-plane row layout (see scan.cu) ------------------------------------------------
@@ -554,14 +626,14 @@ void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const 
                     uint32_t* active, unsigned long long* ssum, const uint8_t* bloom,
                     uint32_t* owner, cudaStream_t st) {
     if (!n_seq) return;
-    dim3 grid(((1u << p.h) + 255) / 256, n_seq);
+    dim3 grid(((1u << p.h) + 256 * RES_U - 1) / (256 * RES_U), n_seq);
     resolve_kernel<<<grid, 256, 0, st>>>(keys_anc, planeF, planeR, woff, p, fp, active, ssum, bloom, owner);
 }
 
 void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
                          SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st) {
     if (!n_seq) return;
-    dim3 grid(((1u << p.h) + 255) / 256, n_seq);
+    dim3 grid(((1u << p.h) + 256 * RES_U - 1) / (256 * RES_U), n_seq);
     bloom_commit_kernel<<<grid, 256, 0, st>>>(anc, fp, p, bloom, owner);
 }
 
