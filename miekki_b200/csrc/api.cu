@@ -8,7 +8,9 @@
 //   owner       u32[window]: scratch for the order-exact Bloom insert (all ~0 between calls)
 // plus grow-only scratch for sequence planes, bucket keys, query lists and count tiles.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <future>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -85,6 +87,9 @@ struct mk_ctx {
     void* meta_pin[2] = {nullptr, nullptr};
     size_t meta_pin_cap[2] = {0, 0};
     int meta_flip = 0;
+    cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned upload ring
+    cudaStream_t copy_stream = nullptr;                              // uploads that overlap compute
+    std::atomic<uint64_t> h2d_meta{0};                               // bytes counted off the main thread
     cudaEvent_t meta_ev[2] = {nullptr, nullptr};
     unsigned long long* d_stat = nullptr;   // device work counters: rows, row bytes
 
@@ -273,19 +278,20 @@ void batch_layout(mk_batch* b, const uint64_t* lens, uint32_t n) {
 // Per-call buffers come from the stream-ordered pool (release threshold raised in
 // mk_create): cudaMalloc/cudaFree per query batch cost up to hundreds of ms on a GPU
 // that holds a multi-GB index.
-int batch_alloc(mk_ctx* c, mk_batch* b) {
-    b->stream = c->stream;
+int batch_alloc(mk_ctx* c, mk_batch* b, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
+    b->stream = st;
     // one allocation: chars | coff[n+1] | len[n]
     const size_t chars_bytes = (b->bytes + 255) / 256 * 256;
     const size_t total = chars_bytes + ((size_t)b->n + 1) * 8 + std::max<size_t>(1, b->n) * 8;
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&b->chars), total, c->stream));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&b->chars), total, st));
     b->d_coff = reinterpret_cast<uint64_t*>(b->chars + chars_bytes);
     b->d_len = b->d_coff + b->n + 1;
     CU(cudaMemcpyAsync(b->d_coff, b->h_coff.data(), ((size_t)b->n + 1) * 8, cudaMemcpyHostToDevice,
-                       c->stream));
+                       st));
     if (b->n)
-        CU(cudaMemcpyAsync(b->d_len, b->h_len.data(), (size_t)b->n * 8, cudaMemcpyHostToDevice, c->stream));
-    c->stats.h2d_bytes += ((size_t)b->n * 2 + 1) * 8;
+        CU(cudaMemcpyAsync(b->d_len, b->h_len.data(), (size_t)b->n * 8, cudaMemcpyHostToDevice, st));
+    c->h2d_meta.fetch_add(((size_t)b->n * 2 + 1) * 8, std::memory_order_relaxed);
     return MK_OK;
 }
 
@@ -298,7 +304,11 @@ void batch_release(mk_batch* b) {
 // memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 takes ~50)
 void parallel_memcpy(char* dst, const char* src, size_t n) {
     static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), n / (2u << 20));
+    static const unsigned cap = [] {
+        const char* e = getenv("MIEKKI_UPLOAD_THREADS");
+        return e ? (unsigned)std::max(1, atoi(e)) : std::min(8u, std::max(1u, hw / 2));
+    }();
+    const unsigned nt = (unsigned)std::min<size_t>(cap, n / (2u << 20));
     if (nt <= 1) {
         memcpy(dst, src, n);
         return;
@@ -315,60 +325,72 @@ void parallel_memcpy(char* dst, const char* src, size_t n) {
 }
 
 // gathers sequences [first, first+n) of (seqs, lens) into a new device batch
-int upload_range(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, mk_batch** out) {
+// `st`: stream to copy on (default: the ctx stream).  With an explicit stream the function may
+// run on a helper thread next to the main one (mk_index_add overlaps the upload of the next
+// genomes with the sketching of the current ones): it then touches only its own staging ring,
+// ring events and atomic counters.
+int upload_range(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, mk_batch** out,
+                 cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
     mk_batch* b = new mk_batch();
     batch_layout(b, lens, n);
-    int r = batch_alloc(c, b);
+    int r = batch_alloc(c, b, st);
     if (r != MK_OK) { batch_release(b); return r; }
     // zero the alignment gaps once so that padding bytes are deterministic
-    cudaError_t e = cudaMemsetAsync(b->chars, 0, b->bytes, c->stream);
+    cudaError_t e = cudaMemsetAsync(b->chars, 0, b->bytes, st);
     if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     const bool big = n && (b->bases / n) >= (1u << 20);
     if (big) {
         // few long sequences (genomes) in pageable memory: a ring of pinned pieces, filled by a
         // few host threads while the previous pieces are in flight over PCIe
-        constexpr size_t PIECE = 16u << 20;
+        static const size_t PIECE = [] {
+            const char* e = getenv("MIEKKI_UPLOAD_PIECE_MB");
+            return (size_t)(e ? std::max(1, atoi(e)) : 16) << 20;
+        }();
         constexpr int SLOTS = 4;
         r = reserve_pinned(c, PIECE * SLOTS);
         if (r != MK_OK) { batch_release(b); return r; }
-        char* st = static_cast<char*>(c->pinned);
-        cudaEvent_t ev[SLOTS];
+        char* ring = static_cast<char*>(c->pinned);
+        cudaEvent_t* ev = c->ring_ev;
         bool used[SLOTS] = {false, false, false, false};
-        for (int s = 0; s < SLOTS; ++s) ev[s] = get_event(c);
+        for (int s = 0; s < SLOTS; ++s)
+            if (!ev[s] && cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming) != cudaSuccess) {
+                batch_release(b);
+                return fail(c, MK_ERR_CUDA, "cudaEventCreate failed");
+            }
         int slot = 0;
         for (uint32_t i = 0; i < n && e == cudaSuccess; ++i) {
             for (uint64_t off = 0; off < lens[i] && e == cudaSuccess; off += PIECE) {
                 const size_t m = (size_t)std::min<uint64_t>(PIECE, lens[i] - off);
                 if (used[slot]) e = cudaEventSynchronize(ev[slot]);
                 if (e != cudaSuccess) break;
-                parallel_memcpy(st + (size_t)slot * PIECE, seqs[i] + off, m);
-                e = cudaMemcpyAsync(b->chars + b->h_coff[i] + off, st + (size_t)slot * PIECE, m,
-                                    cudaMemcpyHostToDevice, c->stream);
-                if (e == cudaSuccess) e = cudaEventRecord(ev[slot], c->stream);
+                parallel_memcpy(ring + (size_t)slot * PIECE, seqs[i] + off, m);
+                e = cudaMemcpyAsync(b->chars + b->h_coff[i] + off, ring + (size_t)slot * PIECE, m,
+                                    cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[slot], st);
                 used[slot] = true;
                 slot = (slot + 1) % SLOTS;
             }
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // staging is reused by the next call
-        for (int s = 0; s < SLOTS; ++s) c->ev_pool.push_back(ev[s]);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // staging is reused by the next call
         if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     } else if (n) {
         // many short sequences (reads): pack into pinned staging, one copy
         r = reserve_pinned(c, b->h_coff[n] + 64);
         if (r != MK_OK) { batch_release(b); return r; }
-        char* st = static_cast<char*>(c->pinned);
+        char* pin = static_cast<char*>(c->pinned);
         for (uint32_t i = 0; i < n; ++i) {
-            memcpy(st + b->h_coff[i], seqs[i], lens[i]);
+            memcpy(pin + b->h_coff[i], seqs[i], lens[i]);
             const uint64_t pad = b->h_coff[i + 1] - b->h_coff[i] - lens[i];
-            if (pad) memset(st + b->h_coff[i] + lens[i], 0, pad);
+            if (pad) memset(pin + b->h_coff[i] + lens[i], 0, pad);
         }
-        e = cudaMemcpyAsync(b->chars, st, b->h_coff[n], cudaMemcpyHostToDevice, c->stream);
+        e = cudaMemcpyAsync(b->chars, pin, b->h_coff[n], cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
         // the staging buffer is reused by the next call: wait for the copy
-        e = cudaStreamSynchronize(c->stream);
+        e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     }
-    c->stats.h2d_bytes += b->bases;
+    c->h2d_meta.fetch_add(b->bases, std::memory_order_relaxed);
     *out = b;
     return MK_OK;
 }
@@ -878,6 +900,7 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->bloom, ctx->window);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->owner, ctx->window * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work, 16);
@@ -918,6 +941,9 @@ void mk_destroy(mk_ctx* c) {
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (cudaEvent_t e : c->ring_ev)
+        if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -1048,25 +1074,42 @@ int mk_index_add(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint3
     Guard g(c);
     for (uint32_t i = 0; i < n; ++i)
         if (lens[i] < c->k) return fail(c, MK_ERR_ARG, "mk_index_add: sequence shorter than k");
-    // upload in slices of bounded size so that staging memory stays small
-    const uint64_t slice_bytes = 1ull << 30;
-    uint32_t first = 0;
-    while (first < n) {
+    // Slices of one dense chunk (<= 32 genomes, <= 1 GiB): while slice i is sketched on the main
+    // stream, a helper thread stages slice i+1 through the pinned ring on the copy stream.
+    const uint32_t chunk = dense_chunk(c);
+    std::vector<std::pair<uint32_t, uint32_t>> slices;
+    for (uint32_t first = 0; first < n;) {
         uint64_t bytes = 0;
         uint32_t m = 0;
-        while (first + m < n && (m == 0 || bytes + lens[first + m] <= slice_bytes) && m < 1024) {
+        while (first + m < n && m < chunk && (m == 0 || bytes + lens[first + m] <= (1ull << 30))) {
             bytes += lens[first + m];
             ++m;
         }
-        mk_batch* b = nullptr;
-        TRY(upload_range(c, seqs + first, lens + first, m, &b));
-        int r = index_add_view(c, b);
-        cudaStreamSynchronize(c->stream);
-        batch_release(b);
-        if (r != MK_OK) return r;
+        slices.push_back({first, m});
         first += m;
     }
-    return MK_OK;
+    TRY(ensure_capacity(c, c->n + n));
+    auto stage = [c, seqs, lens](uint32_t first, uint32_t m) {
+        cudaSetDevice(c->device);
+        mk_batch* b = nullptr;
+        const int r = upload_range(c, seqs + first, lens + first, m, &b, c->copy_stream);
+        return std::make_pair(r, b);
+    };
+    std::future<std::pair<int, mk_batch*>> next;
+    if (!slices.empty()) next = std::async(std::launch::async, stage, slices[0].first, slices[0].second);
+    int rc = MK_OK;
+    for (size_t i = 0; i < slices.size(); ++i) {
+        auto [r, b] = next.get();
+        if (i + 1 < slices.size())
+            next = std::async(std::launch::async, stage, slices[i + 1].first, slices[i + 1].second);
+        if (r == MK_OK && rc == MK_OK) r = index_add_view(c, b);
+        if (b) {
+            cudaStreamSynchronize(c->stream);
+            batch_release(b);
+        }
+        if (r != MK_OK && rc == MK_OK) rc = r;
+    }
+    return rc;
 }
 
 int mk_index_size(const mk_ctx* c, uint32_t* n_genomes) {
@@ -1387,6 +1430,7 @@ static int fold_device_stats(mk_ctx* c) {
     CU(cudaMemset(c->d_stat, 0, sizeof(st)));
     c->stats.scan_rows += st[0];
     c->stats.scan_row_bytes += st[1];
+    c->stats.h2d_bytes += c->h2d_meta.exchange(0, std::memory_order_relaxed);
     return MK_OK;
 }
 
