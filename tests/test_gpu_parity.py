@@ -174,6 +174,33 @@ def test_case_a_sharded_chain_equals_unsharded(mk, case_a):
         x.close()
 
 
+def test_case_a_concurrent_callers(mk, case_a):
+    """The C ABI serialises calls per context, so host threads may share one (the reference's
+    workflows call into a shared Miekki object from every OpenMP thread)."""
+    import threading
+    d, ix, _ = case_a
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    want = open(os.path.join(d, "hits_s200.txt")).read().split("\n")
+    out, errs = {}, []
+
+    def work(t):
+        try:
+            part = reads[t::4]
+            got = gpu_hit_lines(ix, part, 200, chunk=5).split("\n")
+            out[t] = got[:-1]
+        except Exception as e:          # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs
+    for t in range(4):
+        assert out[t] == want[t:len(reads):4]
+
+
 def test_case_a_read_slices_bound_list_memory(mk, case_a, monkeypatch):
     """mk_query cuts a batch into slices of reads so that list memory stays bounded; with a tiny
     budget (several slices, slices of one read) the lines must not change."""
