@@ -61,6 +61,9 @@ struct mk_ctx {
     size_t smem_optin = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t aux_stream = nullptr;     // top-k of one count tile overlaps the scan of the next
+    cudaStream_t sk_stream = nullptr;      // read sketch of the next tile overlaps the scan too
+    cudaStream_t bl_stream = nullptr;      // build_lists: stream override (nullptr = main stream)
+    int bl_set = 0;                        // build_lists: which list buffer set to fill
     std::mutex mu;
     std::string err;
 
@@ -76,7 +79,8 @@ struct mk_ctx {
     uint32_t* owner = nullptr;
     uint64_t window = 0;          // bytes, multiple of 16
 
-    DevBuf planeF, planeR, keys, fp, meta, list, list_len, counts, counts2, heap, heap_len, heap2, heap_len2, misc;
+    DevBuf planeF, planeR, keys, fp, meta, list, list_len, list2, list_len2, counts, counts2, heap, heap_len, heap2,
+        heap_len2, misc;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint32_t* d_work = nullptr;
@@ -540,7 +544,13 @@ int pinned_meta(mk_ctx* c, size_t bytes, void** out) {
 }
 
 // lists of reads [first, first + n) of a batch; all indices inside are relative to `first`
+// c->bl_stream / c->bl_set (set by the caller, default main stream / set 0) choose the stream the
+// sketch runs on and which of the two list buffers it fills, so that query_device can sketch the
+// next tile of reads beside the running scan.
 int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists* out) {
+    cudaStream_t st = c->bl_stream ? c->bl_stream : c->stream;
+    DevBuf& list_buf = c->bl_set ? c->list2 : c->list;
+    DevBuf& len_buf = c->bl_set ? c->list_len2 : c->list_len;
     const uint64_t* b_len = b->h_len.data() + first;
     const uint64_t* b_coff = b->h_coff.data() + first;
     const uint64_t* bd_coff = b->d_coff + first;
@@ -566,38 +576,40 @@ int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists*
         }
     }
     off[n] = total;
-    TRY(reserve(c, c->list, (total + 4) * 4));
+    TRY(reserve(c, list_buf, (total + 4) * 4));
     // list_len | list_off | read ids, all in one small buffer
     const size_t ll_bytes = ((size_t)n * 4 + 15) / 16 * 16;
     const size_t lo_bytes = ((size_t)n + 1) * 8;
     const size_t id_bytes = (size_t)n * 4 + 16;
-    TRY(reserve(c, c->list_len, ll_bytes + lo_bytes + id_bytes));
-    uint8_t* base = static_cast<uint8_t*>(c->list_len.p);
+    TRY(reserve(c, len_buf, ll_bytes + lo_bytes + id_bytes));
+    uint8_t* base = static_cast<uint8_t*>(len_buf.p);
     uint32_t* d_len = reinterpret_cast<uint32_t*>(base);
     uint64_t* d_off = reinterpret_cast<uint64_t*>(base + ll_bytes);
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(base + ll_bytes + lo_bytes);
-    CU(cudaMemsetAsync(d_len, 0, ll_bytes, c->stream));
-    CU(cudaMemcpyAsync(d_off, off, lo_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_len, 0, ll_bytes, st));
+    CU(cudaMemcpyAsync(d_off, off, lo_bytes, cudaMemcpyHostToDevice, st));
     c->stats.h2d_bytes += lo_bytes;
     const size_t n_ids = sparse_ids.size() + dense_ids.size();
     std::copy(sparse_ids.begin(), sparse_ids.end(), ids);
     std::copy(dense_ids.begin(), dense_ids.end(), ids + sparse_ids.size());
     if (n_ids) {
-        CU(cudaMemcpyAsync(d_ids, ids, n_ids * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_ids, ids, n_ids * 4, cudaMemcpyHostToDevice, st));
         c->stats.h2d_bytes += n_ids * 4;
     }
-    CU(cudaEventRecord(c->meta_ev[c->meta_flip], c->stream));   // pinned area free again after this
-    auto* list = static_cast<uint32_t*>(c->list.p);
-    PhaseTimer t(c, PH_READ_SKETCH);
+    CU(cudaEventRecord(c->meta_ev[c->meta_flip], st));   // pinned area free again after this
+    auto* list = static_cast<uint32_t*>(list_buf.p);
+    PhaseTimer t(c, PH_READ_SKETCH, st);
     if (!sparse_ids.empty()) {
         int r = launch_sketch_reads(b->chars, bd_coff, bd_len, d_ids, (uint32_t)sparse_ids.size(),
-                                    sparse_max, c->sp(), c->bloom, d_off, list, d_len, c->stream);
+                                    sparse_max, c->sp(), c->bloom, d_off, list, d_len, st);
         if (r != 0) return fail(c, MK_ERR_CUDA, "sketch_reads launch configuration failed");
         c->stats.kernel_launches += 1;
         CU(cudaGetLastError());
     }
     if (!dense_ids.empty()) {
-        // long reads: dense sketch of gathered views, a few at a time
+        // long reads: dense sketch of gathered views, a few at a time (main stream only: the
+        // dense scratch is shared with the build path)
+        if (st != c->stream) return fail(c, MK_ERR_STATE, "internal: long reads must be sketched on the main stream");
         const uint32_t chunk = dense_chunk(c);
         for (size_t first = 0; first < dense_ids.size(); first += chunk) {
             const uint32_t m = (uint32_t)std::min<size_t>(chunk, dense_ids.size() - first);
@@ -658,9 +670,9 @@ int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPl
 }
 
 // accumulates A(q) statistics from the device list lengths
-int account_lists(mk_ctx* c, const Lists& L, uint32_t n, uint32_t* surviving) {
+int account_lists(mk_ctx* c, const Lists& L, uint32_t n, uint32_t* surviving, cudaStream_t st = nullptr) {
     // device-side counters (fetched by mk_stats_get): no host round trip on the async path
-    launch_account_rows(L.list_len, n, c->n, c->d_stat, c->stream);
+    launch_account_rows(L.list_len, n, c->n, c->d_stat, st ? st : c->stream);
     c->stats.kernel_launches += 1;
     if (surviving) {
         if (n) CU(cudaMemcpyAsync(surviving, L.list_len, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -699,9 +711,13 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
         return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
     const uint64_t n_pad = (c->n + 31) / 32 * 32;
     cudaEvent_t scanned[2] = {get_event(c), get_event(c)}, done[2] = {get_event(c), get_event(c)};
-    bool busy[2] = {false, false};
+    cudaEvent_t sketched[2] = {get_event(c), get_event(c)}, lists_free[2] = {get_event(c), get_event(c)};
+    cudaEvent_t slice_start = get_event(c);
+    bool busy[2] = {false, false}, lists_busy[2] = {false, false};
     int rc = MK_OK;
     uint32_t tile_no = 0;
+    cudaEventRecord(slice_start, c->stream);
+    cudaEventRecord(lists_free[0], c->stream);
     for (uint32_t first = 0; first < n && rc == MK_OK;) {
         uint32_t cnt = 0;
         uint64_t entries = 0;
@@ -712,21 +728,61 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
             entries += e;
             ++cnt;
         }
-        // the lists of the previous slice are still read by its last scans: same stream, ordered
-        Lists L{};
-        rc = build_lists(c, b, first, cnt, &L);
-        if (rc != MK_OK) break;
+        // Tiles of the slice.  Reads that fit the shared-memory sketch are sketched tile by tile on
+        // the sketch stream, one tile ahead of the scan (two list buffer sets); a slice with long
+        // reads (dense sketch, main-stream scratch) is sketched at once on the main stream.
+        bool has_long = false;
+        for (uint32_t i = 0; i < cnt && !has_long; ++i)
+            has_long = b->h_len[first + i] > c->k + SPARSE_MAX_KMERS;
+        const uint32_t qb = c->n > 0 ? std::max<uint32_t>(1, scan_batch_reads(c, cnt) / 2) : cnt;
         if (c->n > 0) {
-            const uint32_t qb = std::max<uint32_t>(1, scan_batch_reads(c, cnt) / 2);
             rc = reserve(c, c->counts, (size_t)qb * n_pad * 4);
             if (rc == MK_OK) rc = reserve(c, c->counts2, (size_t)qb * n_pad * 4);
             if (rc != MK_OK) break;
-            uint32_t* tile[2] = {static_cast<uint32_t*>(c->counts.p), static_cast<uint32_t*>(c->counts2.p)};
-            for (uint32_t q0 = 0; q0 < cnt && rc == MK_OK; q0 += qb, ++tile_no) {
-                const uint32_t nq = std::min(qb, cnt - q0);
-                const int s = (int)(tile_no & 1);
-                if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);     // tile s is free again
-                rc = scan_reads(c, L, q0, nq, plan, tile[s]);
+        }
+        uint32_t* tile[2] = {static_cast<uint32_t*>(c->counts.p), static_cast<uint32_t*>(c->counts2.p)};
+        Lists L[2] = {};
+        // tile boundaries: a short first tile (its sketch is the only one not hidden by a scan)
+        std::vector<uint32_t> cut{0};
+        if (!has_long && cnt > qb / 4) cut.push_back(std::max<uint32_t>(1, qb / 8));
+        while (cut.back() < cnt) cut.push_back(std::min<uint64_t>(cnt, (uint64_t)cut.back() + qb));
+        auto sketch_tile = [&](size_t ti, int set) -> int {          // lists of reads [cut[ti], cut[ti+1])
+            const uint32_t q0 = cut[ti];
+            const uint32_t nq = cut[ti + 1] - q0;
+            if (lists_busy[set]) cudaStreamWaitEvent(c->sk_stream, lists_free[set], 0);   // last scan that read it
+            c->bl_stream = c->sk_stream;
+            c->bl_set = set;
+            int r = build_lists(c, b, first + q0, nq, &L[set]);
+            if (r == MK_OK) r = account_lists(c, L[set], nq, nullptr, c->sk_stream);
+            c->bl_stream = nullptr;
+            c->bl_set = 0;
+            cudaEventRecord(sketched[set], c->sk_stream);
+            return r;
+        };
+        if (has_long) {
+            cudaStreamWaitEvent(c->stream, lists_free[0], 0);
+            rc = build_lists(c, b, first, cnt, &L[0]);
+            if (rc == MK_OK) rc = account_lists(c, L[0], cnt, nullptr);
+        } else {
+            cudaStreamWaitEvent(c->sk_stream, slice_start, 0);   // heap init etc. precede everything
+            rc = sketch_tile(0, 0);
+        }
+        if (rc != MK_OK) break;
+        for (size_t ti = 0; ti + 1 < cut.size() && rc == MK_OK; ++ti, ++tile_no) {
+            const uint32_t q0 = cut[ti];
+            const uint32_t nq = cut[ti + 1] - q0;
+            const int s = (int)(tile_no & 1);
+            const int set = has_long ? 0 : (int)(ti & 1);
+            if (!has_long && ti + 2 < cut.size()) {              // sketch the next tile beside this scan
+                rc = sketch_tile(ti + 1, set ^ 1);
+                if (rc != MK_OK) break;
+            }
+            if (!has_long) cudaStreamWaitEvent(c->stream, sketched[set], 0);
+            if (c->n > 0) {
+                if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);     // count tile s is free again
+                Lists view = L[set];
+                const uint32_t rel = has_long ? q0 : 0;          // tile lists start at 0, slice lists at q0
+                rc = scan_reads(c, view, rel, nq, plan, tile[s]);
                 if (rc != MK_OK) break;
                 cudaEventRecord(scanned[s], c->stream);
                 cudaStreamWaitEvent(c->aux_stream, scanned[s], 0);
@@ -740,8 +796,9 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
                 busy[s] = true;
                 c->stats.kernel_launches += 1;
             }
+            cudaEventRecord(lists_free[set], c->stream);         // this list set may be refilled
+            lists_busy[set] = true;
         }
-        if (rc == MK_OK) rc = account_lists(c, L, cnt, nullptr);
         first += cnt;
     }
     for (int s = 0; s < 2; ++s)
@@ -752,10 +809,14 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
             le != cudaSuccess)
             rc = rc != MK_OK ? rc : fail(c, MK_ERR_CUDA, std::string("query pipeline: ") + cudaGetErrorString(le));
     }
+    cudaStreamSynchronize(c->sk_stream);
     for (int s = 0; s < 2; ++s) {
         c->ev_pool.push_back(scanned[s]);
         c->ev_pool.push_back(done[s]);
+        c->ev_pool.push_back(sketched[s]);
+        c->ev_pool.push_back(lists_free[s]);
     }
+    c->ev_pool.push_back(slice_start);
     if (rc != MK_OK) return rc;
     if (heap_io) {
         CU(cudaMemcpyAsync(heap_io, d_heap, (size_t)n * K * sizeof(HitDev), cudaMemcpyDeviceToHost, c->stream));
@@ -901,6 +962,7 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->sk_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->bloom, ctx->window);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->owner, ctx->window * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work, 16);
@@ -925,7 +987,7 @@ void mk_destroy(mk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
-                      &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc})
+                      &c->list2, &c->list_len2, &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc})
         if (b->p) cudaFree(b->p);
     for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->d_ratio, (void*)c->bloom,
                     (void*)c->owner, (void*)c->d_work, (void*)c->d_stat})
@@ -942,6 +1004,7 @@ void mk_destroy(mk_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->sk_stream) cudaStreamDestroy(c->sk_stream);
     for (cudaEvent_t e : c->ring_ev)
         if (e) cudaEventDestroy(e);
     delete c;
