@@ -88,6 +88,8 @@ struct mk_ctx {
     int next_slot = 0, last_slot = 0;
     uint32_t slot_reads[2] = {0, 0};
     cudaEvent_t slot_ev[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    cudaEvent_t sk_ev = nullptr;
     void* meta_pin[2] = {nullptr, nullptr};
     size_t meta_pin_cap[2] = {0, 0};
     int meta_flip = 0;
@@ -846,8 +848,33 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
         CU(cudaEventCreateWithFlags(&c->slot_ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->slot_ev[1], cudaEventDisableTiming));
     }
+    // The sketch runs on the sketch stream into the list buffers of this slot, so that it
+    // overlaps the scan of the previous batch (still running on the main stream).  Long reads
+    // need the main-stream dense scratch and are sketched in line.
+    bool has_long = false;
+    for (uint32_t i = 0; i < n && !has_long; ++i) has_long = b->h_len[i] > c->k + SPARSE_MAX_KMERS;
     Lists L{};
-    TRY(build_lists(c, b, 0, n, &L));
+    if (has_long) {
+        c->bl_set = slot;
+        int r = build_lists(c, b, 0, n, &L);
+        c->bl_set = 0;
+        TRY(r);
+        TRY(account_lists(c, L, n, nullptr));
+    } else {
+        if (!c->sk_ev) CU(cudaEventCreateWithFlags(&c->sk_ev, cudaEventDisableTiming));
+        if (c->slot_used[slot]) CU(cudaStreamWaitEvent(c->sk_stream, c->slot_ev[slot], 0));   // last scan of this slot
+        CU(cudaEventRecord(c->sk_ev, c->stream));                  // uploads etc. issued on the main stream
+        CU(cudaStreamWaitEvent(c->sk_stream, c->sk_ev, 0));
+        c->bl_stream = c->sk_stream;
+        c->bl_set = slot;
+        int r = build_lists(c, b, 0, n, &L);
+        if (r == MK_OK) r = account_lists(c, L, n, nullptr, c->sk_stream);
+        c->bl_stream = nullptr;
+        c->bl_set = 0;
+        TRY(r);
+        CU(cudaEventRecord(c->sk_ev, c->sk_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->sk_ev, 0));
+    }
     DevBuf& tile = slot ? c->counts2 : c->counts;
     if (c->n > 0) {
         ScanPlan plan{};
@@ -856,8 +883,8 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
         TRY(reserve(c, tile, (size_t)n * n_pad * 4));
         TRY(scan_reads(c, L, 0, n, plan, static_cast<uint32_t*>(tile.p)));
     }
-    TRY(account_lists(c, L, n, nullptr));
     CU(cudaEventRecord(c->slot_ev[slot], c->stream));
+    c->slot_used[slot] = true;
     c->slot_reads[slot] = n;
     return MK_OK;
 }
@@ -999,6 +1026,7 @@ void mk_destroy(mk_ctx* c) {
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->meta_ev)
         if (e) cudaEventDestroy(e);
+    if (c->sk_ev) cudaEventDestroy(c->sk_ev);
     for (auto& pe : c->ev_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
