@@ -268,7 +268,7 @@ def main():
     ix.set_shard(first)
     t0 = time.perf_counter()
     ix.stats_reset()
-    step_g = 32
+    step_g = 128
     for g0 in range(0, a.genomes, step_g):
         m = min(step_g, a.genomes - g0)
         b = ix.synth(SEED, first + g0, m, a.genome_len)

@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--genomes", type=int, default=1000)
 ap.add_argument("--genome-len", type=int, default=5_000_000)
 ap.add_argument("--host-genomes", type=int, default=64)
+ap.add_argument("--batch", type=int, default=128, help="genomes per mk_index_add_batch call")
 ap.add_argument("--hs", default="17,19,20")
 ap.add_argument("--ks", default="21,31")
 a = ap.parse_args()
@@ -47,8 +48,8 @@ for h in map(int, a.hs.split(",")):
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
-        for g0 in range(32, a.genomes, 32):
-            b = ix.synth(1, rank * a.genomes + g0, min(32, a.genomes - g0), a.genome_len)
+        for g0 in range(32, a.genomes, a.batch):
+            b = ix.synth(1, rank * a.genomes + g0, min(a.batch, a.genomes - g0), a.genome_len)
             ix.insert_batch(b)
             b.free()
         wall = time.perf_counter() - t0

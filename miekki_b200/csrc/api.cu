@@ -73,6 +73,8 @@ struct mk_ctx {
     uint32_t* d_sketch_size = nullptr;
     uint64_t* d_genome_size = nullptr;
     float* d_ratio = nullptr;     // float(genome_size / sketch_size), screen of the top-k kernel
+    // host mirrors of the two arrays above, valid for ids [0, h_sketch_size.size()) and
+    // completed from the device on demand (host_stats): the build never waits for them
     std::vector<uint32_t> h_sketch_size;
     std::vector<uint64_t> h_genome_size;
     uint8_t* bloom = nullptr;
@@ -80,7 +82,7 @@ struct mk_ctx {
     uint64_t window = 0;          // bytes, multiple of 16
 
     DevBuf planeF, planeR, keys, fp, meta, list, list_len, list2, list_len2, counts, counts2, heap, heap_len, heap2,
-        heap_len2, misc;
+        heap_len2, misc, pages;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint32_t* d_work = nullptr;
@@ -425,6 +427,8 @@ struct DenseOut {
     uint64_t* d_woff;
     uint32_t* d_active;
     unsigned long long* d_ssum;
+    uint32_t* d_claims;       // Bloom claimants of this chunk (seq << h | bucket), count in *d_n_claims
+    uint32_t* d_n_claims;
 };
 int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out) {
     const uint32_t n = v.n;
@@ -437,35 +441,56 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
     woff[n] = w;
     TRY(reserve(c, c->planeF, (w + 4) * 8));      // F and R words interleaved: {F, R} per 16 bases
     TRY(reserve(c, c->keys, (size_t)n * c->B * 8));
-    TRY(reserve(c, c->fp, (size_t)n * c->B * 2));     // fp[n][B] | Bloom claim flags[n][B]
-    const size_t meta_bytes = ((size_t)n + 1) * 8 + (size_t)n * 8 + (size_t)n * 8;
+    const size_t fp_bytes = ((size_t)n * c->B + 3) & ~(size_t)3;
+    TRY(reserve(c, c->fp, fp_bytes + (bloom_insert ? (size_t)n * c->B * 4 : 0)));   // fp[n][B] | claim list u32[n * B]
+    // woff[n+1] | ssum[n] | active[n] | claim counter  (ssum .. counter zeroed together below)
+    const size_t meta_bytes = ((size_t)n + 1) * 8 + (size_t)n * 8 + (size_t)n * 8 + 8;
     TRY(reserve(c, c->meta, meta_bytes));
     uint64_t* d_woff = static_cast<uint64_t*>(c->meta.p);
     unsigned long long* d_ssum = reinterpret_cast<unsigned long long*>(d_woff + n + 1);
     uint32_t* d_active = reinterpret_cast<uint32_t*>(d_ssum + n);
     CU(cudaMemcpyAsync(d_woff, woff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(d_ssum, 0, (size_t)n * 16, c->stream));
+    uint32_t* d_n_claims = d_active + n;
+    uint32_t* d_claims = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->fp.p) + fp_bytes);
+    CU(cudaMemsetAsync(d_ssum, 0, (size_t)n * 12 + 4, c->stream));
     auto* keys = static_cast<unsigned long long*>(c->keys.p);
+    // tagged keys whenever positions fit 32 bits (common.cuh: KEY_TAG_BITS)
+    const int ks = v.max_len < (1ull << 32) ? KEY_TAG_BITS : 0;
+    const uint32_t* pair_full = nullptr;
+    uint32_t pair_words = 0;
+    if (bloom_insert && ks) {
+        // which Bloom pages are already saturated (resolve_kernel's fast path)
+        const uint32_t n_pages = bloom_page_count(c->window);
+        const size_t off = ((size_t)n_pages + 3) & ~(size_t)3;
+        TRY(reserve(c, c->pages, off + ((size_t)n_pages + 31) / 32 * 4));
+        auto* full8 = static_cast<uint8_t*>(c->pages.p);
+        auto* pf = reinterpret_cast<uint32_t*>(full8 + off);
+        pair_words = launch_bloom_pages(c->bloom, c->window, full8, pf, c->stream);
+        pair_full = pf;
+        c->stats.kernel_launches += 2;
+    }
     launch_fill_u64(keys, (uint64_t)n * c->B, ~0ull, c->stream);
     launch_encode_planes(v.chars, v.d_coff, v.d_len, d_woff, n, v.max_len, (int)c->k,
                          static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, c->stream);
     launch_sketch_dense(static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, v.d_len,
-                        d_woff, n, v.max_len, (int)c->k, (int)c->h, keys, c->stream);
+                        d_woff, n, v.max_len, (int)c->k, (int)c->h, keys, ks, c->stream);
     launch_resolve(keys, static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, d_woff, n,
                    c->sp(), static_cast<uint8_t*>(c->fp.p), d_active, d_ssum, c->bloom,
-                   bloom_insert ? c->owner : nullptr, c->stream);
+                   bloom_insert ? c->owner : nullptr, pair_full, pair_words, ks, d_claims, d_n_claims, c->stream);
     c->stats.kernel_launches += 4;
     CU(cudaGetLastError());
     out->d_woff = d_woff;
     out->d_active = d_active;
     out->d_ssum = d_ssum;
+    out->d_claims = d_claims;
+    out->d_n_claims = d_n_claims;
     return MK_OK;
 }
 
 // genomes per dense chunk: bounded by the Bloom owner key (5 + h + 3 bits <= 32) and memory
 uint32_t dense_chunk(const mk_ctx* c) {
     uint32_t by_key = c->h <= 24 ? (1u << std::min<uint32_t>(29 - c->h, 6)) : 1;
-    uint64_t by_mem = (1ull << 30) / (c->B * 9) ;        // keys + fp <= 1 GiB
+    uint64_t by_mem = (1ull << 30) / (c->B * 13);       // keys + fp + claim list <= 1 GiB
     uint32_t ch = (uint32_t)std::min<uint64_t>(by_key, std::max<uint64_t>(1, by_mem));
     return std::max<uint32_t>(1, std::min<uint32_t>(ch, 32));
 }
@@ -477,6 +502,22 @@ uint64_t genome_size_of(uint32_t active, unsigned long long ssum31, uint64_t len
     const double card = (0.72134 * (double)sq) / S;
     if (card > (double)len) return len;
     return (uint64_t)card;
+}
+
+// completes the host mirrors of sketch_size / genome_size up to c->n
+int host_stats(mk_ctx* c) {
+    const size_t have = c->h_sketch_size.size();
+    if (have >= c->n) return MK_OK;
+    const size_t m = c->n - have;
+    c->h_sketch_size.resize(c->n);
+    c->h_genome_size.resize(c->n);
+    CU(cudaMemcpyAsync(c->h_sketch_size.data() + have, c->d_sketch_size + have, m * 4, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaMemcpyAsync(c->h_genome_size.data() + have, c->d_genome_size + have, m * 8, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += m * 12;
+    return MK_OK;
 }
 
 int index_add_view(mk_ctx* c, const mk_batch* b) {
@@ -492,28 +533,19 @@ int index_add_view(mk_ctx* c, const mk_batch* b) {
         {
             PhaseTimer t(c, PH_SKETCH);
             TRY(dense_sketch(c, v, true, &d));
-            launch_bloom_commit(static_cast<unsigned long long*>(c->keys.p), static_cast<uint8_t*>(c->fp.p), n,
-                                c->sp(), c->bloom, c->owner, c->stream);
+            launch_bloom_commit(static_cast<unsigned long long*>(c->keys.p), d.d_claims, d.d_n_claims, n, c->sp(),
+                                c->bloom, c->owner, c->stream);
             launch_scatter_planes(static_cast<uint8_t*>(c->fp.p), n, (int)c->h, c->rows, c->stride, c->n, c->stream);
             c->stats.kernel_launches += 2;
         }
-        std::vector<uint32_t> act(n);
-        std::vector<unsigned long long> ssum(n);
-        CU(cudaMemcpyAsync(act.data(), d.d_active, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(ssum.data(), d.d_ssum, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        std::vector<uint64_t> gs(n);
-        for (uint32_t i = 0; i < n; ++i) gs[i] = genome_size_of(act[i], ssum[i], v.h_len[i]);
-        CU(cudaMemcpyAsync(c->d_sketch_size + c->n, act.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->d_genome_size + c->n, gs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        c->h_sketch_size.insert(c->h_sketch_size.end(), act.begin(), act.end());
-        c->h_genome_size.insert(c->h_genome_size.end(), gs.begin(), gs.end());
-        TRY(upload_ratio(c, c->n, n));
+        // sketch_size / genome_size / ratio of the new ids, on the device (no host round trip)
+        launch_stats_finalize(d.d_active, d.d_ssum, v.d_len, n, c->d_sketch_size + c->n, c->d_genome_size + c->n,
+                              c->d_ratio + c->n, c->stream);
+        c->stats.kernel_launches += 1;
+        CU(cudaGetLastError());
         c->n += n;
         c->stats.bases_sketched += v.bases;
-        c->stats.d2h_bytes += (size_t)n * 12;
-        c->stats.h2d_bytes += (size_t)n * 12 + ((size_t)n + 1) * 8;
+        c->stats.h2d_bytes += ((size_t)n + 1) * 8;
     }
     return sync(c);
 }
@@ -1014,7 +1046,7 @@ void mk_destroy(mk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
-                      &c->list2, &c->list_len2, &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc})
+                      &c->list2, &c->list_len2, &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc, &c->pages})
         if (b->p) cudaFree(b->p);
     for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->d_ratio, (void*)c->bloom,
                     (void*)c->owner, (void*)c->d_work, (void*)c->d_stat})
@@ -1213,6 +1245,7 @@ int mk_index_stats(mk_ctx* c, uint32_t first, uint32_t n, uint32_t* sketch_size,
     if (!c) return MK_ERR_ARG;
     Guard g(c);
     if ((uint64_t)first + n > c->n) return fail(c, MK_ERR_ARG, "mk_index_stats: range exceeds the index");
+    TRY(host_stats(c));
     if (sketch_size) memcpy(sketch_size, c->h_sketch_size.data() + first, (size_t)n * 4);
     if (genome_size) memcpy(genome_size, c->h_genome_size.data() + first, (size_t)n * 8);
     return MK_OK;
@@ -1241,6 +1274,7 @@ int mk_index_export(mk_ctx* c, uint8_t* rows, uint64_t* genome_size, uint8_t* bl
         if (bloom_bytes > m) memset(bloom + m, 0, bloom_bytes - m);   // never touched for this k
         c->stats.d2h_bytes += m;
     }
+    if (genome_size || sketch_size) TRY(host_stats(c));
     if (genome_size) memcpy(genome_size, c->h_genome_size.data(), (size_t)c->n * 8);
     if (sketch_size) memcpy(sketch_size, c->h_sketch_size.data(), (size_t)c->n * 4);
     return sync(c);

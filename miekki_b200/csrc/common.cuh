@@ -4,13 +4,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernels.h"
+
 namespace mk {
 
 constexpr uint32_t EMPTY_FP = 255u;            // Miekki.cpp:29 maximal_minimizer
 constexpr uint64_t EMPTY_KEY = ~0ull;          // (fp=255, pos=max): "bucket never hit"
 constexpr uint64_t EMPTY_ANC = ~0ull;          // Miekki.cpp:30 maximal_hash
-constexpr int POS_BITS = 56;                   // key = fp << 56 | position
+constexpr int POS_BITS = 56;                   // key = fp << 56 | position << ks | tag
 constexpr uint64_t POS_MASK = (1ull << POS_BITS) - 1;
+// Tagged keys (sequences shorter than 2^32): ks = KEY_TAG_BITS and the low bits carry the top
+// KEY_TAG_BITS bits of the canonical k-mer (the whole k-mer when 2k <= KEY_TAG_BITS).
+// (KEY_TAG_BITS itself lives in kernels.h: the host picks the key format)
+constexpr uint64_t KEY_TAG_MASK = (1ull << KEY_TAG_BITS) - 1;
+__host__ __device__ __forceinline__ int key_tag_shift(int k) {
+    return 2 * k > KEY_TAG_BITS ? 2 * k - KEY_TAG_BITS : 0;
+}
+// Bloom pages (sketch.cu: bloom_pages_kernel): 2^BLOOM_PAGE_LOG2 table bytes each
+constexpr int BLOOM_PAGE_LOG2 = 12;
 
 // utils.cpp:179-184 revhash64.  (x >> 32) ^ x only touches the low word, and the 64-bit
 // product needs three 32-bit multiplies: lo*lo (wide), lo*hi, hi*lo.
@@ -125,13 +136,18 @@ __device__ __forceinline__ uint64_t rev_window(uint32_t r0, uint32_t r1, uint32_
     return ((uint64_t)hi << 32) | lo;
 }
 
-// canonical k-mer hash of the k-mer starting at base (16*w + j)
+// canonical k-mer (Miekki.cpp:167) of the k-mer starting at base (16*w + j), and its hash (:168)
+__device__ __forceinline__ uint64_t kmer_canon(uint32_t f0, uint32_t f1, uint32_t f2,
+                                               uint32_t r0, uint32_t r1, uint32_t r2,
+                                               int j, int k, uint64_t kmask) {
+    const uint64_t S = fwd_window(f0, f1, f2, j) >> (64 - 2 * k);
+    const uint64_t RC = rev_window(r0, r1, r2, j) & kmask;
+    return S < RC ? S : RC;
+}
 __device__ __forceinline__ uint64_t kmer_hash(uint32_t f0, uint32_t f1, uint32_t f2,
                                               uint32_t r0, uint32_t r1, uint32_t r2,
                                               int j, int k, uint64_t kmask) {
-    const uint64_t S = fwd_window(f0, f1, f2, j) >> (64 - 2 * k);
-    const uint64_t RC = rev_window(r0, r1, r2, j) & kmask;
-    return revhash64(S < RC ? S : RC);              // Miekki.cpp:167-168
+    return revhash64(kmer_canon(f0, f1, f2, r0, r1, r2, j, k, kmask));
 }
 
 }  // namespace mk

@@ -12,27 +12,42 @@ struct SketchParams {
 };
 
 // ---- sketch.cu ------------------------------------------------------------------
+constexpr int KEY_TAG_BITS = 24;    // tagged sketch keys, see launch_sketch_dense
 // Dense path (genomes, long reads): sequences -> 2-bit planes -> per-bucket min key.
 //   chars     : concatenated ASCII, sequence s at chars + coff[s] (16-byte aligned)
 //   woff[s]   : first plane word of sequence s (each sequence owns ceil(len/16)+2 words)
 //   planes    : interleaved, planeR == planeF + 1 and word w of a plane sits at index 2 w
-//   keys      : n_seq x 2^h u64, pre-set to ~0; afterwards fp << 56 | first position
+//   keys      : n_seq x 2^h u64, pre-set to ~0; afterwards fp << 56 | first position << ks | tag
+//   ks        : 0 (plain keys) or KEY_TAG_BITS (every sequence shorter than 2^32: the low bits
+//               carry the top bits of the canonical k-mer, see resolve_kernel)
 void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
                           const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k,
                           uint32_t* planeF, uint32_t* planeR, cudaStream_t st);
 void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const uint64_t* len,
                          const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k, int h,
-                         unsigned long long* keys, cudaStream_t st);
+                         unsigned long long* keys, int ks, cudaStream_t st);
 // keys -> fp[s][b] (u8) and anc written over keys[s][b]; per-sequence active count and
 // S = sum 2^(31 - (fp >> 3)).  If owner != nullptr, also registers Bloom candidates
-// (pass A of the order-exact insert) with key (seq_in_batch, bucket, probe).
+// (pass A of the order-exact insert) with key (seq_in_batch, bucket, probe); then anc is only
+// written for buckets that may still change the Bloom table (pair_full from launch_bloom_pages;
+// nullptr: every bucket is looked up).
 void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const uint32_t* planeR,
                     const uint64_t* woff, uint32_t n_seq, SketchParams p, uint8_t* fp,
                     uint32_t* active, unsigned long long* ssum, const uint8_t* bloom,
-                    uint32_t* owner, cudaStream_t st);
+                    uint32_t* owner, const uint32_t* pair_full, uint32_t pair_words, int ks,
+                    uint32_t* claims, uint32_t* n_claims, cudaStream_t st);
+// Bloom pages without a zero byte -> full8[n_pages], pair_full[ceil(n_pages / 32)]
+uint32_t bloom_page_count(uint64_t window);
+uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint8_t* full8, uint32_t* pair_full,
+                            cudaStream_t st);
+// Miekki.cpp:303-311: sketch_size, genome_size and the top-k screen ratio of n new genomes
+void launch_stats_finalize(const uint32_t* active, const unsigned long long* ssum, const uint64_t* len,
+                           uint32_t n, uint32_t* sketch_size, uint64_t* genome_size, float* ratio,
+                           cudaStream_t st);
 // pass B: the smallest (genome, bucket, probe) key of every still-zero Bloom byte writes it.
-void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
-                         SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st);
+// claims[0 .. *n_claims): (seq_in_batch << h | bucket) of the buckets that registered a claim in pass A
+void launch_bloom_commit(const unsigned long long* anc, const uint32_t* claims, const uint32_t* n_claims,
+                         uint32_t n_seq, SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st);
 // fp[s][b] -> bit-plane rows (layout: scan.cu), genome column col0 + s
 void launch_scatter_planes(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
                            uint32_t col0, cudaStream_t st);

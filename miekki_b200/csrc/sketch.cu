@@ -10,6 +10,7 @@
 //   * a fingerprint of 255 never registers (Miekki.cpp:172 with res[] preset to 255);
 //   * Bloom bytes: the byte value belongs to the smallest (genome, bucket, probe) that maps
 //     to it (order-independent restatement of Miekki.cpp:295-299).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -74,6 +75,32 @@ __device__ __forceinline__ void encode_word(const uint8_t* __restrict__ s, uint6
     R = r;
 }
 
+// Fast path of encode_word: all 16 characters are upper-case A/C/G/T and none lies in the
+// prefix zone, so both encoders agree (F digit = A0 C1 G2 T3, R digit = 3 - F digit) and the
+// word is packed arithmetically, four characters per 32-bit lane.  Returns false (F, R
+// untouched) when any other byte is present: the caller then takes the table path.
+__device__ __forceinline__ bool encode_word_acgt(const uint4 raw, uint32_t& F, uint32_t& R) {
+    const uint32_t q[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t bad = 0, f = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t x = (q[i] >> 1) & 0x03030303u;               // A0 C1 G3 T2
+        const uint32_t t = (x >> 1) & ~x & 0x01010101u;             // 1 per 'T'
+        const uint32_t expect = (0x41414141u | (x << 1)) ^ (t * 0x11u);   // 41 43 47 | 45^11 = 54
+        bad |= q[i] ^ expect;
+        const uint32_t code = x ^ ((x >> 1) & 0x01010101u);         // A0 C1 G2 T3
+        // bytes c0..c3 (c0 = first character) -> c0<<6 | c1<<4 | c2<<2 | c3 in the top byte
+        f |= ((code * 0x40100401u) >> 24) << (24 - 8 * i);
+    }
+    if (bad) return false;
+    F = f;
+    // R digit of base j (bits 2j) = 3 - F digit of base j (bits 30-2j): reverse the digit order
+    uint32_t r = __brev(f);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    R = ~r;
+    return true;
+}
+
 // ---- dense path ------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
@@ -91,8 +118,11 @@ encode_planes_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restri
          w += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t F = 0, R = 0;
         if (16 * w < n) {
-            const bool pv = (16 * w < (uint64_t)(k - 1)) ? prefix_valid(seq, n, k, lut) : true;
-            encode_word(seq, n, w, k, pv, lut, F, R);
+            const bool plain = 16 * w >= (uint64_t)(k - 1) && 16 * w + 16 <= n;
+            if (!plain || !encode_word_acgt(*reinterpret_cast<const uint4*>(seq + 16 * w), F, R)) {
+                const bool pv = (16 * w < (uint64_t)(k - 1)) ? prefix_valid(seq, n, k, lut) : true;
+                encode_word(seq, n, w, k, pv, lut, F, R);
+            }
         }
         // the two planes are interleaved word by word (planeR == planeF + 1): the three words a
         // k-mer needs from each plane are then 24 contiguous bytes, i.e. one or two sectors
@@ -103,10 +133,14 @@ encode_planes_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restri
 }
 
 // one thread = 16 consecutive k-mer start positions (one plane word + two neighbours)
+// key = fp << 56 | position << ks | tag.  ks = KEY_TAG_BITS when every position fits 32 bits:
+// the tag is then the top KEY_TAG_BITS bits of the canonical k-mer, which lets resolve_kernel
+// decide "every Bloom byte this k-mer can touch is already set" without looking the k-mer up
+// again.  The order of keys is still (fp, position): the tag sits below both.
 __global__ void __launch_bounds__(256)
 sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restrict__ planeR,
                     const uint64_t* __restrict__ len, const uint64_t* __restrict__ woff, int k, int h,
-                    unsigned long long* __restrict__ keys, int prefilter) {
+                    unsigned long long* __restrict__ keys, int prefilter, int ks) {
     const uint32_t s = blockIdx.y;
     const uint64_t n = len[s];
     if (n <= (uint64_t)k) return;
@@ -114,6 +148,7 @@ sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restr
     const uint64_t nwk = (nk + 15) / 16;
     const uint64_t kmask = (1ull << (2 * k)) - 1;
     const uint64_t pmask = (1ull << (64 - h)) - 1;
+    const int tag_shift = key_tag_shift(k);
     const uint2* P = reinterpret_cast<const uint2*>(planeF) + woff[s];   // .x = F word, .y = R word
     (void)planeR;
     unsigned long long* kz = keys + ((uint64_t)s << h);
@@ -126,11 +161,13 @@ sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restr
         for (int j = 0; j < 16; ++j) {
             const uint64_t pos = 16 * w + j;
             if (pos < nk) {
-                const uint64_t x = kmer_hash(f0, f1, f2, r0, r1, r2, j, k, kmask);
+                const uint64_t canon = kmer_canon(f0, f1, f2, r0, r1, r2, j, k, kmask);
+                const uint64_t x = revhash64(canon);
                 const uint32_t fp = mantis(x & pmask, h);
                 if (fp != EMPTY_FP) {
                     unsigned long long* slot = kz + (x >> (64 - h));
-                    const unsigned long long key = ((unsigned long long)fp << POS_BITS) | pos;
+                    unsigned long long key = ((unsigned long long)fp << POS_BITS) | (pos << ks);
+                    if (ks) key |= canon >> tag_shift;
                     // Keys only ever decrease, so a (possibly stale) read that is already <= key
                     // proves the atomic would change nothing: most k-mers of a bucket lose.
                     if (!prefilter || key < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, key);
@@ -157,38 +194,63 @@ __device__ __forceinline__ uint32_t owner_key(uint32_t s, uint32_t bucket, uint3
 // the winning position -> Bloom byte) and was purely latency bound with one bucket per thread
 // (ncu: 75 % long-scoreboard stalls, DRAM 8 %).  Each thread therefore walks RES_U buckets in
 // lock step, stage by stage, so that RES_U independent loads are in flight per stage.
+//
+// Build fast path (tagged keys, ks != 0): the reference's Bloom table only ever gains bytes
+// (Miekki.cpp:127-128 writes into zero bytes only), and for the default k = 31, b = 33 it has
+// just 2^26 reachable bytes, so after a few hundred genomes nearly every insert is a no-op.
+// `pair_full` has one bit per 4 KB page of the table: "this page and the next hold no zero
+// byte" (bloom_pages_kernel, recomputed before every launch).  The key's tag bounds the
+// canonical k-mer to a range whose five probes stay inside those two pages, so a set bit
+// proves the insert changes nothing: `anc` is not needed and all three look-ups are skipped.
 constexpr int RES_U = 4;
+constexpr uint32_t PAIR_WORDS_MAX = 1032;      // (2^27 + 16 window bytes) / 4096 / 32, rounded up
 
 __global__ void __launch_bounds__(256)
 resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __restrict__ planeF,
-               const uint32_t* __restrict__ planeR, const uint64_t* __restrict__ woff, SketchParams p,
-               uint8_t* __restrict__ fp_out, uint32_t* __restrict__ active,
-               unsigned long long* __restrict__ ssum, const uint8_t* __restrict__ bloom,
-               uint32_t* __restrict__ owner) {
-    (void)planeR;
+               const uint64_t* __restrict__ woff, SketchParams p, uint8_t* __restrict__ fp_out,
+               uint32_t* __restrict__ active, unsigned long long* __restrict__ ssum,
+               const uint8_t* __restrict__ bloom, uint32_t* __restrict__ owner,
+               const uint32_t* __restrict__ pair_full, uint32_t pair_words, int ks,
+               uint32_t* __restrict__ claims, uint32_t* __restrict__ n_claims) {
+    __shared__ uint32_t s_pair[PAIR_WORDS_MAX];
+    const bool tagged = owner != nullptr && pair_full != nullptr && ks != 0;
+    if (tagged) {
+        for (uint32_t i = threadIdx.x; i < pair_words; i += blockDim.x) s_pair[i] = pair_full[i];
+        __syncthreads();
+    }
     const uint32_t s = blockIdx.y;
     const uint32_t B = 1u << p.h;
     const uint2* P = reinterpret_cast<const uint2*>(planeF) + woff[s];
     const uint64_t row = (uint64_t)s << p.h;
-    const uint64_t claim_off = (uint64_t)gridDim.y << p.h;
     const uint64_t kmask = (1ull << (2 * p.k)) - 1;
+    const int tag_shift = key_tag_shift(p.k);
+    const int page_shift = (int)p.bloom_log2 + 3 + BLOOM_PAGE_LOG2;
     uint32_t act = 0;
     unsigned long long sum = 0;
 
     uint32_t b[RES_U];
     unsigned long long key[RES_U];
+    bool slow[RES_U];                                       // needs anc (and maybe a Bloom claim)
     #pragma unroll
     for (int u = 0; u < RES_U; ++u) {                       // stage 1: keys (coalesced)
         b[u] = (blockIdx.x * RES_U + u) * blockDim.x + threadIdx.x;
         key[u] = b[u] < B ? keys_anc[row + b[u]] : EMPTY_KEY;
+        slow[u] = (key[u] >> POS_BITS) != EMPTY_FP;
+        if (tagged && slow[u]) {
+            const uint32_t page = (uint32_t)(((key[u] & KEY_TAG_MASK) << tag_shift) >> page_shift);
+            if ((s_pair[page >> 5] >> (page & 31)) & 1u) slow[u] = false;
+        }
     }
     uint2 w0[RES_U], w1[RES_U], w2[RES_U];
     #pragma unroll
     for (int u = 0; u < RES_U; ++u) {                       // stage 2: plane words at the winning position
-        const uint64_t w = ((key[u] >> POS_BITS) != EMPTY_FP) ? ((key[u] & POS_MASK) >> 4) : 0;
-        w0[u] = P[w];
-        w1[u] = P[w + 1];
-        w2[u] = P[w + 2];
+        w0[u] = w1[u] = w2[u] = make_uint2(0u, 0u);
+        if (slow[u]) {
+            const uint64_t w = ((key[u] & POS_MASK) >> ks) >> 4;
+            w0[u] = P[w];
+            w1[u] = P[w + 1];
+            w2[u] = P[w + 2];
+        }
     }
     unsigned long long anc[RES_U];
     uint64_t slot[RES_U][2];
@@ -197,107 +259,205 @@ resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __rest
     uint8_t cell[RES_U][2];
     #pragma unroll
     for (int u = 0; u < RES_U; ++u) {                       // stage 3: hashes, Bloom bytes
-        const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
         anc[u] = EMPTY_ANC;
         nd[u] = 0;
         cell[u][0] = cell[u][1] = 1;
-        if (fp != EMPTY_FP) {
-            const int j = (int)(key[u] & 15);
+        if (slow[u]) {
+            const int j = (int)(((key[u] & POS_MASK) >> ks) & 15);
             anc[u] = kmer_hash(w0[u].x, w1[u].x, w2[u].x, w0[u].y, w1[u].y, w2[u].y, j, p.k, kmask);
             if (owner != nullptr) {
                 BloomProbe pr(anc[u]);
                 nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
-                for (int q = 0; q < nd[u]; ++q) {
-                    const uint64_t byte = slot[u][q] >> 3;
-                    cell[u][q] = byte < p.bloom_window ? bloom[byte] : (uint8_t)1;
-                }
+                #pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (q < nd[u]) {
+                        const uint64_t byte = slot[u][q] >> 3;
+                        cell[u][q] = byte < p.bloom_window ? bloom[byte] : (uint8_t)1;
+                    }
             }
         }
     }
+    uint32_t claim_bits = 0;
     #pragma unroll
     for (int u = 0; u < RES_U; ++u) {                       // stage 4: claims and stores
-        if (b[u] >= B) continue;
+        const bool in = b[u] < B;
         const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
-        if (fp != EMPTY_FP) {
+        bool claimed = false;
+        if (in && fp != EMPTY_FP) {
             act += 1;
             sum += 1ull << (31 - (fp >> 3));                // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
             if (owner != nullptr) {                         // Bloom pass A (Miekki.cpp:295-299)
-                uint8_t claimed = 0;
-                for (int q = 0; q < nd[u]; ++q)
-                    if (cell[u][q] == 0) {
+                #pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (q < nd[u] && cell[u][q] == 0) {
                         atomicMin(owner + (slot[u][q] >> 3), owner_key(s, b[u], probe[u][q], p.h));
-                        claimed = 1;
+                        claimed = true;
                     }
-                // claim flags live behind the fp block: pass B only revisits claimants
-                fp_out[claim_off + row + b[u]] = claimed;
             }
         }
-        keys_anc[row + b[u]] = anc[u];
+        claim_bits |= claimed ? (1u << u) : 0u;
+        if (!in) continue;
+        // during a build only claimants are looked at again (bloom_commit_kernel reads their anc)
+        if (owner == nullptr || slow[u]) keys_anc[row + b[u]] = anc[u];
         fp_out[row + b[u]] = (uint8_t)fp;
     }
-    // per-sequence statistics: warp shuffle, then one pair of atomics per block
-    __shared__ uint32_t s_act[8];
+    // per-sequence statistics and the claimant list (pass B only revisits claimants): warp
+    // shuffles, then one set of global atomics per block
+    __shared__ uint32_t s_act[8], s_claims[8], s_base;
     __shared__ unsigned long long s_sum[8];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t mine = __popc(claim_bits);
+    uint32_t before = mine;                                 // inclusive prefix sum over the warp
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, before, o);
+        if (lane >= (uint32_t)o) before += t;
+    }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         act += __shfl_xor_sync(0xffffffffu, act, o);
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        s_act[threadIdx.x >> 5] = act;
-        s_sum[threadIdx.x >> 5] = sum;
+    if (lane == 31) s_claims[warp] = before;
+    if (lane == 0) {
+        s_act[warp] = act;
+        s_sum[warp] = sum;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t a = 0;
+        uint32_t a = 0, cl = 0;
         unsigned long long t = 0;
-        for (unsigned w = 0; w < blockDim.x / 32; ++w) { a += s_act[w]; t += s_sum[w]; }
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) {
+            a += s_act[w];
+            t += s_sum[w];
+            const uint32_t x = s_claims[w];
+            s_claims[w] = cl;                               // -> exclusive offset of the warp
+            cl += x;
+        }
         if (a) {
             atomicAdd(active + s, a);
             atomicAdd(ssum + s, t);
         }
+        s_base = cl ? atomicAdd(n_claims, cl) : 0u;
+    }
+    if (owner == nullptr) return;
+    __syncthreads();
+    if (mine) {
+        uint32_t at = s_base + s_claims[warp] + before - mine;
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u)
+            if (claim_bits & (1u << u)) claims[at++] = (s << p.h) | b[u];
     }
 }
 
+// Which 4 KB pages of the Bloom table hold no zero byte?  One warp per page -> full8[page];
+// then pair bit j = full8[j] && full8[j + 1] (a k-mer's probes may cross into the next page).
 __global__ void __launch_bounds__(256)
-bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint8_t* __restrict__ fp,
-                    SketchParams p, uint8_t* __restrict__ bloom, uint32_t* __restrict__ owner) {
-    // RES_U buckets per thread, stage by stage, like resolve_kernel (random owner look-ups)
-    const uint32_t s = blockIdx.y;
-    const uint32_t B = 1u << p.h;
-    const uint64_t row = (uint64_t)s << p.h;
-    const uint64_t claim_off = (uint64_t)gridDim.y << p.h;
-    uint32_t b[RES_U];
-    bool live[RES_U];
-    #pragma unroll
-    for (int u = 0; u < RES_U; ++u) {
-        b[u] = (blockIdx.x * RES_U + u) * blockDim.x + threadIdx.x;
-        // claimants only: non-empty bucket that registered a claim in pass A
-        live[u] = b[u] < B && fp[row + b[u]] != EMPTY_FP && fp[claim_off + row + b[u]] != 0;
+bloom_pages_kernel(const uint8_t* __restrict__ bloom, uint64_t window, uint32_t n_pages,
+                   uint8_t* __restrict__ full8) {
+    const uint32_t page = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (page >= n_pages) return;
+    const uint64_t base = (uint64_t)page << BLOOM_PAGE_LOG2;
+    bool ok = base + (1ull << BLOOM_PAGE_LOG2) <= window;    // a partial last page is never "full"
+    if (ok) {
+        const uint4* src = reinterpret_cast<const uint4*>(bloom + base);
+        uint32_t zero = 0;
+        #pragma unroll
+        for (int i = 0; i < (1 << BLOOM_PAGE_LOG2) / 16 / 32; ++i) {
+            const uint4 v = src[i * 32 + lane];
+            zero |= (v.x - 0x01010101u) & ~v.x;
+            zero |= (v.y - 0x01010101u) & ~v.y;
+            zero |= (v.z - 0x01010101u) & ~v.z;
+            zero |= (v.w - 0x01010101u) & ~v.w;
+        }
+        ok = (zero & 0x80808080u) == 0;
     }
-    uint64_t slot[RES_U][2];
-    uint32_t probe[RES_U][2], own[RES_U][2];
-    int nd[RES_U];
-    #pragma unroll
-    for (int u = 0; u < RES_U; ++u) {
-        nd[u] = 0;
-        if (live[u]) {
-            BloomProbe pr(anc[row + b[u]]);
-            nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
-            for (int q = 0; q < nd[u]; ++q) {
-                const uint64_t byte = slot[u][q] >> 3;
-                own[u][q] = byte < p.bloom_window ? owner[byte] : 0xFFFFFFFFu;
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) full8[page] = ok ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+bloom_pairs_kernel(const uint8_t* __restrict__ full8, uint32_t n_pages, uint32_t n_words,
+                   uint32_t* __restrict__ pair_full) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t bits = 0;
+    for (uint32_t j = 0; j < 32; ++j) {
+        const uint32_t pg = 32 * w + j;
+        if (pg + 1 < n_pages && full8[pg] && full8[pg + 1]) bits |= 1u << j;
+    }
+    pair_full[w] = bits;
+}
+
+// Miekki.cpp:303-311 from the exact integer statistics: S = ssum31 * 2^-31 is exact, the
+// u32 product wraps (quirk G2), and mul / div are single IEEE roundings like the host code.
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const uint32_t* __restrict__ active, const unsigned long long* __restrict__ ssum,
+                      const uint64_t* __restrict__ len, uint32_t n, uint32_t* __restrict__ sketch_size,
+                      uint64_t* __restrict__ genome_size, float* __restrict__ ratio) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t a = active[i];
+    const double S = __dmul_rn(__ull2double_rn(ssum[i]), 4.656612873077392578125e-10);   // 2^-31
+    const uint32_t sq = a * a;
+    const double card = __ddiv_rn(__dmul_rn(0.72134, (double)sq), S);
+    const double dl = __ull2double_rn(len[i]);
+    uint64_t gs;
+    if (card > dl) gs = len[i];
+    else if (card != card) gs = 0x8000000000000000ull;      // 0/0: what cvttsd2si yields on x86
+    else gs = (uint64_t)card;
+    sketch_size[i] = a;
+    genome_size[i] = gs;
+    ratio[i] = (float)__ddiv_rn(__ull2double_rn(gs), (double)a);
+}
+
+__global__ void __launch_bounds__(256)
+bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint32_t* __restrict__ claims,
+                    const uint32_t* __restrict__ n_claims, SketchParams p, uint8_t* __restrict__ bloom,
+                    uint32_t* __restrict__ owner) {
+    // RES_U claimants per thread, stage by stage, like resolve_kernel (random owner look-ups)
+    const uint32_t total = *n_claims;
+    const uint32_t bmask = (1u << p.h) - 1;
+    const uint32_t step = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += RES_U * step) {
+        uint32_t id[RES_U];
+        bool live[RES_U];
+        unsigned long long a[RES_U];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {
+            const uint32_t i = i0 + u * step;
+            live[u] = i < total;
+            id[u] = live[u] ? claims[i] : 0u;
+        }
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) a[u] = live[u] ? anc[id[u]] : 0ull;
+        uint64_t slot[RES_U][2];
+        uint32_t probe[RES_U][2], own[RES_U][2];
+        int nd[RES_U];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {
+            nd[u] = 0;
+            if (live[u]) {
+                BloomProbe pr(a[u]);
+                nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
+                #pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (q < nd[u]) {
+                        const uint64_t byte = slot[u][q] >> 3;
+                        own[u][q] = byte < p.bloom_window ? owner[byte] : 0xFFFFFFFFu;
+                    }
             }
         }
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u)
+            #pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (q < nd[u] && own[u][q] == owner_key(id[u] >> p.h, id[u] & bmask, probe[u][q], p.h)) {
+                    const uint64_t byte = slot[u][q] >> 3;
+                    bloom[byte] = (uint8_t)(1u << (slot[u][q] & 7));   // Miekki.cpp:128
+                    owner[byte] = 0xFFFFFFFFu;                          // the winner also clears its claim
+                }
     }
-    #pragma unroll
-    for (int u = 0; u < RES_U; ++u)
-        for (int q = 0; q < nd[u]; ++q)
-            if (own[u][q] == owner_key(s, b[u], probe[u][q], p.h)) {
-                const uint64_t byte = slot[u][q] >> 3;
-                bloom[byte] = (uint8_t)(1u << (slot[u][q] & 7));   // Miekki.cpp:128
-                owner[byte] = 0xFFFFFFFFu;                          // the winner also clears its claim
-            }
 }
 
 // ---- bit-plane row layout (see scan.cu) ------------------------------------------------
@@ -456,7 +616,11 @@ sketch_reads_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restric
         const bool pv = prefix_valid(seq, n, k, lut);
         for (uint32_t w = threadIdx.x; w < nw + 2; w += blockDim.x) {
             uint32_t f = 0, r = 0;
-            if (w < nw) encode_word(seq, n, w, k, pv, lut, f, r);
+            if (w < nw) {
+                const bool plain = 16ull * w >= (uint64_t)(k - 1) && 16ull * w + 16 <= n;
+                if (!plain || !encode_word_acgt(*reinterpret_cast<const uint4*>(seq + 16ull * w), f, r))
+                    encode_word(seq, n, w, k, pv, lut, f, r);
+            }
             F[w] = f;
             R[w] = r;
         }
@@ -610,7 +774,7 @@ void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint
 
 void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const uint64_t* len,
                          const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k, int h,
-                         unsigned long long* keys, cudaStream_t st) {
+                         unsigned long long* keys, int ks, cudaStream_t st) {
     if (!n_seq || max_len <= (uint64_t)k) return;
     const uint64_t nwk = (max_len - k + 15) / 16;
     dim3 grid(blocks_for(nwk, 256, 148 * 16), n_seq);
@@ -618,23 +782,51 @@ void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const u
         const char* e = getenv("MIEKKI_SKETCH_PREFILTER");
         return e ? atoi(e) : 0;   // measured: no gain at -h 17, -13 % at -h 20 (a RED costs about a read)
     }();
-    sketch_dense_kernel<<<grid, 256, 0, st>>>(planeF, planeR, len, woff, k, h, keys, prefilter);
+    sketch_dense_kernel<<<grid, 256, 0, st>>>(planeF, planeR, len, woff, k, h, keys, prefilter, ks);
 }
 
 void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const uint32_t* planeR,
                     const uint64_t* woff, uint32_t n_seq, SketchParams p, uint8_t* fp,
                     uint32_t* active, unsigned long long* ssum, const uint8_t* bloom,
-                    uint32_t* owner, cudaStream_t st) {
+                    uint32_t* owner, const uint32_t* pair_full, uint32_t pair_words, int ks,
+                    uint32_t* claims, uint32_t* n_claims, cudaStream_t st) {
     if (!n_seq) return;
+    (void)planeR;
+    if (pair_words > PAIR_WORDS_MAX) pair_full = nullptr;
     dim3 grid(((1u << p.h) + 256 * RES_U - 1) / (256 * RES_U), n_seq);
-    resolve_kernel<<<grid, 256, 0, st>>>(keys_anc, planeF, planeR, woff, p, fp, active, ssum, bloom, owner);
+    resolve_kernel<<<grid, 256, 0, st>>>(keys_anc, planeF, woff, p, fp, active, ssum, bloom, owner, pair_full,
+                                         pair_words, ks, claims, n_claims);
 }
 
-void launch_bloom_commit(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
-                         SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st) {
+uint32_t bloom_page_count(uint64_t window) {
+    return (uint32_t)((window + (1ull << BLOOM_PAGE_LOG2) - 1) >> BLOOM_PAGE_LOG2);
+}
+
+// scratch: n_pages bytes (full8) followed, 4-byte aligned, by pair words; returns the word count
+uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint8_t* full8, uint32_t* pair_full,
+                            cudaStream_t st) {
+    const uint32_t n_pages = bloom_page_count(window);
+    const uint32_t n_words = (n_pages + 31) / 32;
+    if (!n_pages) return 0;
+    bloom_pages_kernel<<<(n_pages * 32 + 255) / 256, 256, 0, st>>>(bloom, window, n_pages, full8);
+    bloom_pairs_kernel<<<(n_words + 255) / 256, 256, 0, st>>>(full8, n_pages, n_words, pair_full);
+    return n_words;
+}
+
+void launch_stats_finalize(const uint32_t* active, const unsigned long long* ssum, const uint64_t* len,
+                           uint32_t n, uint32_t* sketch_size, uint64_t* genome_size, float* ratio,
+                           cudaStream_t st) {
+    if (!n) return;
+    stats_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(active, ssum, len, n, sketch_size, genome_size, ratio);
+}
+
+void launch_bloom_commit(const unsigned long long* anc, const uint32_t* claims, const uint32_t* n_claims,
+                         uint32_t n_seq, SketchParams p, uint8_t* bloom, uint32_t* owner, cudaStream_t st) {
     if (!n_seq) return;
-    dim3 grid(((1u << p.h) + 256 * RES_U - 1) / (256 * RES_U), n_seq);
-    bloom_commit_kernel<<<grid, 256, 0, st>>>(anc, fp, p, bloom, owner);
+    // the claim count lives on the device: a fixed grid strides over the list
+    const uint64_t most = ((uint64_t)n_seq << p.h) / (256 * RES_U) + 1;
+    bloom_commit_kernel<<<(unsigned)std::min<uint64_t>(most, 148 * 16), 256, 0, st>>>(anc, claims, n_claims, p, bloom,
+                                                                                   owner);
 }
 
 void launch_scatter_planes(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,

@@ -518,6 +518,40 @@ def test_empty_and_degenerate_inputs(mk):
     ix.close()
 
 
+def test_build_with_saturated_bloom_pages(mk):
+    """Build fast path (sketch.cu: resolve_kernel): once 4 KB pages of the Bloom table hold no zero
+    byte, buckets whose k-mer can only touch such pages skip the look-up.  k = 25, b = 32 has a
+    32 KiB window: after 16 genomes its first pages are full, the last ones never are, so later
+    inserts take both paths.  Everything the build leaves behind must still equal the oracle."""
+    k, h, b = 25, 14, 32
+    rng = np.random.default_rng(5)
+    genomes = [rand_seq(rng, 150_000, special=(g % 5 == 0)) for g in range(48)]
+    genomes.append(genomes[3][:k])                      # exactly k bases: no k-mer, sketch_size 0
+    genomes.append(genomes[7][1000:90_000])
+    ix = mk.Miekki(k=k, h=h, b=b, threshold=0)
+    o = orc.Oracle(k=k, h=h, b=b, cap=len(genomes))
+    for first in range(0, len(genomes), 16):
+        ix.insert_sequences(genomes[first:first + 16])
+        for s in genomes[first:first + 16]:
+            o.insert(s)
+        e = ix.export()
+        m = min(len(e["bloom"]), len(o.bloom))
+        assert np.array_equal(e["bloom"][:m], o.bloom[:m]), first
+        if first == 0:
+            pages = (np.asarray(e["bloom"][:32768]).reshape(8, 4096) != 0).all(axis=1)
+            assert pages[:3].all() and not pages[7], pages      # both paths are live from here on
+    assert np.array_equal(e["rows"], o.rows)
+    assert np.array_equal(e["sketch_size"], o.sketch_size)
+    assert np.array_equal(e["genome_size"], o.genome_size)
+    assert e["sketch_size"][48] == 0
+    reads = [genomes[40][500:2500], genomes[7][2000:4000], genomes[20][100_000:101_000]]
+    counts, surv = ix.query_counts(reads)
+    for i, s in enumerate(reads):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa and np.array_equal(counts[i], oc), i
+    ix.close()
+
+
 def test_errors(mk):
     with pytest.raises(mk.MiekkiError):
         mk.Miekki(k=32)
