@@ -48,6 +48,9 @@ def run(binary, args, cwd):
     r = subprocess.run([binary] + [str(x) for x in args], cwd=cwd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.exit("%s failed:\n%s\n%s" % (binary, r.stdout[-2000:], r.stderr[-2000:]))
+    for line in r.stderr.splitlines():
+        if line.startswith("[timing]"):
+            print(os.path.basename(binary), line, file=sys.stderr)
     return elapsed(r.stdout), time.perf_counter() - t0
 
 

@@ -191,6 +191,9 @@ int mk_sketch(mk_ctx *ctx, const char *seq, uint64_t len, uint8_t *fp, uint64_t 
 int mk_exact(mk_ctx *ctx, const char *const *records, const uint64_t *rec_lens, uint32_t n_records,
              const char *const *reads, const uint64_t *read_lens, uint32_t n_reads,
              uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct);
+/* Same with the records and the reads already in HBM (mk_batch_upload / mk_batch_synth). */
+int mk_exact_batch(mk_ctx *ctx, const mk_batch *records, const mk_batch *reads,
+                   uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct);
 
 /* ---- measurement ----------------------------------------------------------- */
 

@@ -81,6 +81,7 @@ SIGNATURES = {
     "mk_query_counts": (_i, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "mk_sketch": (_i, [_vp, C.c_char_p, _u64, _vp, _vp, C.POINTER(_u32)]),
     "mk_exact": (_i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, C.POINTER(_u64)]),
+    "mk_exact_batch": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u64)]),
     "mk_stats_get": (_i, [_vp, C.POINTER(Stats)]),
     "mk_stats_reset": (_i, [_vp]),
     "mk_sync": (_i, [_vp]),
@@ -361,6 +362,15 @@ class Miekki:
         self._ck(lib().mk_exact(self._ctx, ra, _ptr(rl), len(records), qa, _ptr(ql), len(reads),
                                 _ptr(inter), _ptr(uni), C.byref(nb)))
         return nb.value, inter[: len(reads)], uni[: len(reads)]
+
+    def exact_batch(self, records: Batch, reads: Batch):
+        """Same with both sides already in HBM (mk_exact_batch)."""
+        n = len(reads)
+        inter = np.zeros(max(1, n), np.uint64)
+        uni = np.zeros(max(1, n), np.uint64)
+        nb = C.c_uint64()
+        self._ck(lib().mk_exact_batch(self._ctx, records._h, reads._h, _ptr(inter), _ptr(uni), C.byref(nb)))
+        return nb.value, inter[:n], uni[:n]
 
     # ---- measurement -----------------------------------------------------------
     def stats(self) -> dict:

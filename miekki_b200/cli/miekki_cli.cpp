@@ -36,6 +36,23 @@ using namespace std;
 
 namespace {
 
+// MIEKKI_TIMING=1: phase timings on stderr (stdout stays what the reference prints)
+struct PhaseClock {
+    const char* what;
+    chrono::steady_clock::time_point t0 = chrono::steady_clock::now();
+    static bool on() {
+        static const bool v = getenv("MIEKKI_TIMING") != nullptr;
+        return v;
+    }
+    explicit PhaseClock(const char* w) : what(w) {}
+    ~PhaseClock() {
+        if (!on()) return;
+        const double s = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+        #pragma omp critical(msg)
+        cerr << "[timing] " << what << " " << s << " s" << endl;
+    }
+};
+
 bool exists_test(const string& name) {
     struct stat buffer;
     return stat(name.c_str(), &buffer) == 0;
@@ -166,6 +183,7 @@ void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo,
         vector<char> ok;
     };
     auto parse = [&](size_t w0) {
+        PhaseClock pc("parse wave");
         Wave w;
         const size_t m = min(wave, hi - w0);
         w.seqs.resize(m);
@@ -201,6 +219,7 @@ void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo,
             #pragma omp critical(msg)
             cout << "-" << flush;                                // :575
         }
+        PhaseClock pc("mk_index_add wave");
         if (!ptr.empty() && mk_index_add(ctx, ptr.data(), len.data(), (uint32_t)ptr.size()) != MK_OK)
             die(ctx, "mk_index_add");
     }
@@ -667,7 +686,10 @@ int main(int argc, char** argv) {
             cout << "not implemented" << endl;                   // Miekki.cpp:236-237 (quirk G12)
             exit(0);
         }
-        ix.create_shards();
+        {
+            PhaseClock pc("create_shards");
+            ix.create_shards();
+        }
         ix.out = new ofstream(output_file.c_str());
         cout << "I output results in " << output_file << endl;   // Miekki.h:75
         index_file_of_file(ix, list_file);

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <future>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -56,6 +57,7 @@ struct mk_batch {
 
 struct mk_ctx {
     uint32_t k, h, nbm, nbmant, b, threshold;
+    bool key_tags = true;         // MIEKKI_KEY_TAGS=0 forces the plain key format (used for >= 2^32-base sequences)
     uint64_t B;
     int device = 0, sm_count = 148;
     size_t smem_optin = 0;
@@ -455,7 +457,7 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
     CU(cudaMemsetAsync(d_ssum, 0, (size_t)n * 12 + 4, c->stream));
     auto* keys = static_cast<unsigned long long*>(c->keys.p);
     // tagged keys whenever positions fit 32 bits (common.cuh: KEY_TAG_BITS)
-    const int ks = v.max_len < (1ull << 32) ? KEY_TAG_BITS : 0;
+    const int ks = (c->key_tags && v.max_len < (1ull << 32)) ? KEY_TAG_BITS : 0;
     const uint32_t* pair_full = nullptr;
     uint32_t pair_words = 0;
     if (bloom_insert && ks) {
@@ -986,20 +988,33 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     if (h < 1 || h > 24) return fail(c, MK_ERR_ARG, "h must be in [1, 24]");
     if (bloom_log2 < 32 || bloom_log2 > 40)
         return fail(c, MK_ERR_ARG, "bloom_log2 must be in [32, 40]: below 32 the reference indexes out of bounds (Miekki.cpp:124)");
+    // MIEKKI_TIMING=1: where start-up time goes (driver initialisation dominates a short run)
+    const bool timing = getenv("MIEKKI_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[timing] mk_create: %s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(c, MK_ERR_CUDA, "no CUDA device: miekki_b200 has no CPU fallback");
     }
+    lap("driver initialisation (cudaGetDeviceCount)");
     if (device < 0 || device >= ndev) return fail(c, MK_ERR_ARG, "bad device ordinal");
     cudaDeviceProp prop{};
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
         return fail(c, MK_ERR_CUDA, "cudaSetDevice failed");
     if (prop.major < 10)
         return fail(c, MK_ERR_UNSUPPORTED, "miekki_b200 is built for sm_100a (B200) only");
+    cudaFree(nullptr);
+    lap("context (cudaSetDevice, properties)");
     mk_ctx* ctx = new mk_ctx();
     ctx->k = k; ctx->h = h; ctx->nbm = bits_per_min; ctx->nbmant = bits_mantis; ctx->b = bloom_log2;
     ctx->threshold = threshold;
+    if (const char* e = getenv("MIEKKI_KEY_TAGS")) ctx->key_tags = atoi(e) != 0;
     ctx->B = 1ull << h;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -1036,6 +1051,7 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     cudaMemsetAsync(ctx->bloom, 0, ctx->window, ctx->stream);
     launch_fill_u32(ctx->owner, ctx->window, 0xFFFFFFFFu, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
+    lap("streams, Bloom table, module load");
     *out = ctx;
     return MK_OK;
 }
@@ -1470,18 +1486,15 @@ int mk_sketch(mk_ctx* c, const char* seq, uint64_t len, uint8_t* fp, uint64_t* a
 
 // ---- exact mode ----------------------------------------------------------------------
 
-int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, uint32_t n_records,
-             const char* const* reads, const uint64_t* read_lens, uint32_t n_reads, uint64_t* nb_inter,
-             uint64_t* nb_union, uint64_t* genome_distinct) {
-    if (!c || (n_records && (!records || !rec_lens)) || (n_reads && (!reads || !read_lens || !nb_inter || !nb_union)))
-        return fail(c, MK_ERR_ARG, "mk_exact: NULL argument");
-    Guard g(c);
-    mk_batch *gb = nullptr, *rb = nullptr;
+// set B from the records of `gb`, then every read of `rb` against it (both resident in HBM)
+static int exact_device(mk_ctx* c, const mk_batch* gb, const mk_batch* rb, uint64_t* nb_inter, uint64_t* nb_union,
+                        uint64_t* genome_distinct) {
     unsigned long long *tableB = nullptr, *rtable = nullptr, *d_cnt = nullptr;
     uint64_t* d_toff = nullptr;
+    const uint32_t n_records = gb->n, n_reads = rb->n;
+    const uint64_t* rec_lens = gb->h_len.data();
+    const uint64_t* read_lens = rb->h_len.data();
     auto body = [&]() -> int {
-        TRY(upload_range(c, records, rec_lens, n_records, &gb));
-        TRY(upload_range(c, reads, read_lens, n_reads, &rb));
         const uint32_t k = c->k;
         uint64_t wins = 0;
         for (uint32_t i = 0; i < n_records; ++i)
@@ -1539,9 +1552,31 @@ int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, ui
     if (rtable) cudaFreeAsync(rtable, c->stream);
     if (d_cnt) cudaFreeAsync(d_cnt, c->stream);
     if (d_toff) cudaFreeAsync(d_toff, c->stream);
+    return r;
+}
+
+int mk_exact(mk_ctx* c, const char* const* records, const uint64_t* rec_lens, uint32_t n_records,
+             const char* const* reads, const uint64_t* read_lens, uint32_t n_reads, uint64_t* nb_inter,
+             uint64_t* nb_union, uint64_t* genome_distinct) {
+    if (!c || (n_records && (!records || !rec_lens)) || (n_reads && (!reads || !read_lens || !nb_inter || !nb_union)))
+        return fail(c, MK_ERR_ARG, "mk_exact: NULL argument");
+    Guard g(c);
+    mk_batch *gb = nullptr, *rb = nullptr;
+    int r = upload_range(c, records, rec_lens, n_records, &gb);
+    if (r == MK_OK) r = upload_range(c, reads, read_lens, n_reads, &rb);
+    if (r == MK_OK) r = exact_device(c, gb, rb, nb_inter, nb_union, genome_distinct);
+    cudaStreamSynchronize(c->stream);
     batch_release(gb);
     batch_release(rb);
     return r;
+}
+
+int mk_exact_batch(mk_ctx* c, const mk_batch* records, const mk_batch* reads, uint64_t* nb_inter,
+                   uint64_t* nb_union, uint64_t* genome_distinct) {
+    if (!c || !records || !reads || (reads->n && (!nb_inter || !nb_union)))
+        return fail(c, MK_ERR_ARG, "mk_exact_batch: NULL argument");
+    Guard g(c);
+    return exact_device(c, records, reads, nb_inter, nb_union, genome_distinct);
 }
 
 // ---- measurement ---------------------------------------------------------------------

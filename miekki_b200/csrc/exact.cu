@@ -11,6 +11,8 @@
 // The reference uses std::unordered_set; here both sets are exact open-addressing hash
 // sets of 64-bit keys in HBM/L2 (insert-if-absent with atomicCAS, empty = ~0, which is not
 // a k-mer for k <= 31).  |B| is the number of successful inserts.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,7 +21,18 @@ namespace mk {
 namespace {
 
 constexpr unsigned long long EMPTY = ~0ull;
-constexpr int RUN = 64;      // windows per thread in the genome kernel
+// Windows per thread in the genome kernel.  Every insert is a chain of two dependent random
+// accesses (probe, CAS) that only other threads can hide: ncu at 64 windows per thread showed
+// 24 % occupancy (306 CTAs for 5 Mbp), 14 % issue utilisation, 250 us per 5 Mbp genome.  Short
+// runs re-roll k - 1 characters more often but fill the machine.
+static int run_length() {
+    static const int v = [] {
+        const char* e = getenv("MIEKKI_EXACT_RUN");
+        const int r = e ? atoi(e) : 8;     // measured, 5 Mbp genome: 64 -> 250 us, 8 -> 158 us
+        return r < 1 ? 1 : r;
+    }();
+    return v;
+}
 
 // digit (0..3) of str2numstrand, 4 for a byte it rejects (utils.cpp:252-272)
 __device__ __forceinline__ uint32_t ci_code(uint32_t c) {
@@ -61,7 +74,7 @@ __device__ __forceinline__ bool set_contains(const unsigned long long* __restric
 __global__ void __launch_bounds__(256)
 exact_insert_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
                     const uint64_t* __restrict__ len, int k, unsigned long long* __restrict__ table,
-                    uint64_t slots, unsigned long long* __restrict__ distinct) {
+                    uint64_t slots, unsigned long long* __restrict__ distinct, int RUN) {
     const uint32_t s = blockIdx.y;
     const uint64_t n = len[s];
     uint32_t fresh = 0;
@@ -141,11 +154,12 @@ void launch_exact_insert(const uint8_t* chars, const uint64_t* coff, const uint6
                          uint32_t n_seq, uint64_t max_len, int k, unsigned long long* table,
                          uint64_t slots, unsigned long long* distinct, cudaStream_t st) {
     if (!n_seq || max_len < (uint64_t)k) return;
+    const int RUN = run_length();
     const uint64_t threads = (max_len - k + 1 + RUN - 1) / RUN;
     uint64_t bx = (threads + 255) / 256;
     if (bx > 148 * 16) bx = 148 * 16;
     dim3 grid((unsigned)bx, n_seq);
-    exact_insert_kernel<<<grid, 256, 0, st>>>(chars, coff, len, k, table, slots, distinct);
+    exact_insert_kernel<<<grid, 256, 0, st>>>(chars, coff, len, k, table, slots, distinct, RUN);
 }
 
 void launch_exact_reads(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,

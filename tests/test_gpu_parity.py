@@ -281,6 +281,12 @@ def test_exact_edge_cases(mk):
     assert [(int(a), int(u)) for a, u in zip(inter, uni)] == ores
     nB, inter, uni = ix.exact([], [g[:100]])
     assert nB == 0 and int(inter[0]) == 0 and int(uni[0]) == 70
+    # the same through batches that already sit in HBM (mk_exact_batch)
+    gb, rb = ix.upload(recs), ix.upload(reads)
+    nB, inter, uni = ix.exact_batch(gb, rb)
+    assert nB == onB and [(int(a), int(u)) for a, u in zip(inter, uni)] == ores
+    gb.free()
+    rb.free()
     ix.close()
 
 
@@ -515,6 +521,29 @@ def test_empty_and_degenerate_inputs(mk):
         assert np.array_equal(counts[i], oc), i
         oh = o.filter(oc, 10, 1, 0.0)
         assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+    ix.close()
+
+
+def test_plain_key_format_matches_oracle(mk, monkeypatch):
+    """Sequences of 2^32 bases or more cannot carry the k-mer tag in their sketch keys and take
+    the plain key format; MIEKKI_KEY_TAGS=0 forces that path on ordinary inputs."""
+    monkeypatch.setenv("MIEKKI_KEY_TAGS", "0")
+    k, h = 27, 12
+    rng = np.random.default_rng(77)
+    genomes = [rand_seq(rng, 60_000, special=True) for _ in range(5)] + [rand_seq(rng, k)]
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.insert_sequences(genomes)
+    o = orc.Oracle(k=k, h=h, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    e = ix.export()
+    assert np.array_equal(e["rows"], o.rows)
+    assert np.array_equal(e["sketch_size"], o.sketch_size) and np.array_equal(e["genome_size"], o.genome_size)
+    m = min(len(e["bloom"]), len(o.bloom))
+    assert np.array_equal(e["bloom"][:m], o.bloom[:m])
+    fp, anc, act = ix.sketch(genomes[0])
+    ofp, oanc, oact = orc.sketch(genomes[0], k, h)
+    assert act == oact and np.array_equal(fp, ofp) and np.array_equal(anc, oanc)
     ix.close()
 
 
