@@ -121,6 +121,20 @@ int mk_index_import(mk_ctx *ctx, uint32_t n, const uint8_t *rows, uint64_t rows_
                     const uint64_t *genome_size, const uint8_t *bloom, uint64_t bloom_bytes,
                     const uint32_t *sketch_size);
 
+/* Streaming forms of the two calls above, for indexes that should not sit in host memory as
+ * one block (a -h 20 index of 10,000 genomes is 10.5 GB): the dump is written / read a slab
+ * of bucket rows at a time, in the order of the file (rows, then statistics and Bloom table).
+ * export_rows: rows [row0, row0 + nrows) to dst, row r at dst + (r - row0) * dst_stride
+ * (dst_stride >= N lets several shards fill their columns of one host slab).
+ * import: begin(n) empties the index and sizes it for n genomes; rows arrive in any number
+ * of import_rows calls; end() installs statistics and Bloom bytes and publishes the index. */
+int mk_index_export_rows(mk_ctx *ctx, uint64_t row0, uint64_t nrows, uint8_t *dst, uint64_t dst_stride);
+int mk_index_import_begin(mk_ctx *ctx, uint32_t n);
+int mk_index_import_rows(mk_ctx *ctx, uint64_t row0, uint64_t nrows, const uint8_t *src,
+                         uint64_t src_stride);
+int mk_index_import_end(mk_ctx *ctx, const uint64_t *genome_size, const uint8_t *bloom,
+                        uint64_t bloom_bytes, const uint32_t *sketch_size);
+
 /* Bloom bytes only (multi-GPU merge): the window the device keeps is the
  * first mk_bloom_window() bytes of the 2^b/8-byte table; bytes past it are never touched
  * for this k.  merge: dst byte = (dst != 0) ? dst : src  ("lowest rank wins"). */

@@ -81,6 +81,10 @@ SIGNATURES = {
     "mk_query_counts": (_i, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "mk_sketch": (_i, [_vp, C.c_char_p, _u64, _vp, _vp, C.POINTER(_u32)]),
     "mk_exact": (_i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, C.POINTER(_u64)]),
+    "mk_index_export_rows": (_i, [_vp, _u64, _u64, _vp, _u64]),
+    "mk_index_import_begin": (_i, [_vp, _u32]),
+    "mk_index_import_rows": (_i, [_vp, _u64, _u64, _vp, _u64]),
+    "mk_index_import_end": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "mk_exact_batch": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u64)]),
     "mk_stats_get": (_i, [_vp, C.POINTER(Stats)]),
     "mk_stats_reset": (_i, [_vp]),
@@ -268,6 +272,32 @@ class Miekki:
         bl = np.ascontiguousarray(bloom, np.uint8)
         self._ck(lib().mk_index_import(self._ctx, n, _ptr(rows), rows.strides[0], _ptr(gs), _ptr(bl),
                                        len(bl), _ptr(ss)))
+
+    def export_rows(self, row0: int, nrows: int, out: np.ndarray | None = None, col0: int = 0) -> np.ndarray:
+        """Rows [row0, row0+nrows) of the dump payload.  With `out` (uint8 [nrows, width]) this
+        shard's columns land at out[:, col0 : col0 + n] (several shards fill one slab)."""
+        n = self.n
+        if out is None:
+            out = np.empty((nrows, n), np.uint8)
+        assert out.dtype == np.uint8 and out.shape[0] >= nrows and out.strides[1] == 1
+        self._ck(lib().mk_index_export_rows(self._ctx, row0, nrows, C.c_void_p(out.ctypes.data + col0),
+                                            out.strides[0]))
+        return out
+
+    def import_begin(self, n: int):
+        self._ck(lib().mk_index_import_begin(self._ctx, n))
+
+    def import_rows(self, row0: int, rows: np.ndarray, col0: int = 0):
+        """rows: uint8 [nrows, width]; this shard takes columns [col0, col0 + n)."""
+        assert rows.dtype == np.uint8 and rows.strides[1] == 1
+        self._ck(lib().mk_index_import_rows(self._ctx, row0, rows.shape[0], C.c_void_p(rows.ctypes.data + col0),
+                                            rows.strides[0]))
+
+    def import_end(self, genome_size, bloom, sketch_size):
+        gs = np.ascontiguousarray(genome_size, np.uint64)
+        ss = np.ascontiguousarray(sketch_size, np.uint32)
+        bl = np.ascontiguousarray(bloom, np.uint8)
+        self._ck(lib().mk_index_import_end(self._ctx, _ptr(gs), _ptr(bl), len(bl), _ptr(ss)))
 
     # ---- query (query_sequences + filter_results, Miekki.cpp:344,409) ----------
     def query(self, seqs, nresults=10, min_score=10, min_intersection=None):

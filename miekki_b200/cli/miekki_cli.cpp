@@ -251,30 +251,18 @@ void index_file_of_file(Index& ix, const string& list) {
 }
 
 // ---- dump / load: Miekki.cpp:649-719, SURVEY.md Appendix C -----------------------------------
+// Rows travel in slabs of about SLAB_BYTES so that neither side ever holds the whole matrix in
+// host memory (10.5 GB at -h 20 with 10,000 genomes); slab i+1 is exported / parsed while slab
+// i is deflated / converted.
+const uint64_t SLAB_BYTES = [] {
+    const char* e = getenv("MIEKKI_DUMP_SLAB_BYTES");        // tests shrink it to force many slabs
+    return e ? max<uint64_t>(1, strtoull(e, nullptr, 10)) : 256ull << 20;
+}();
+
 void dump_disk(Index& ix, const string& path) {
     const uint32_t n = ix.size();
     const uint64_t B = 1ull << ix.h;
     const uint64_t bloom_bits = 1ull << ix.b;
-    vector<uint8_t> rows(B * (uint64_t)n), bloom(bloom_bits / 8);
-    vector<uint64_t> gs(n);
-    vector<uint32_t> ss(n);
-    if (ix.shard.size() == 1) {
-        if (mk_index_export(ix.shard[0], rows.data(), gs.data(), bloom.data(), bloom.size(), ss.data()) != MK_OK)
-            die(ix.shard[0], "mk_index_export");
-    } else {
-        // shard r owns columns [first[r], first[r] + n_r) of every row
-        for (size_t r = 0; r < ix.shard.size(); ++r) {
-            uint32_t nr = 0;
-            mk_index_size(ix.shard[r], &nr);
-            vector<uint8_t> part(B * (uint64_t)nr);
-            if (mk_index_export(ix.shard[r], part.data(), gs.data() + ix.first[r], r == 0 ? bloom.data() : nullptr,
-                                r == 0 ? bloom.size() : 0, ss.data() + ix.first[r]) != MK_OK)
-                die(ix.shard[r], "mk_index_export");
-            #pragma omp parallel for num_threads(ix.threads) schedule(static)
-            for (uint64_t b = 0; b < B; ++b)
-                memcpy(rows.data() + b * n + ix.first[r], part.data() + b * nr, nr);
-        }
-    }
     mkcli::ParallelGzWriter w(path, ix.threads);   // gzip level 1 like zstr::ofstream, multi-member
     const uint8_t jaccard_estimation = 0;       // uninitialised in the reference (quirk G7)
     const uint8_t containment_estimation = 0;
@@ -290,7 +278,33 @@ void dump_disk(Index& ix, const string& path) {
     w.write(&containment_estimation, 1);
     w.write(&ix.threshold, 4);
     w.write(&compressed, 1);
-    w.write(rows.data(), rows.size());
+    if (n) {
+        // shard r owns columns [first[r], first[r] + n_r) of every row of the slab
+        const uint64_t slab = max<uint64_t>(1, min<uint64_t>(B, SLAB_BYTES / n));
+        vector<uint8_t> buf[2];
+        auto fetch = [&](uint64_t r0, vector<uint8_t>& dst) {
+            const uint64_t nr = min(slab, B - r0);
+            dst.resize(nr * n);
+            #pragma omp parallel for num_threads((int)ix.shard.size()) schedule(static, 1)
+            for (size_t r = 0; r < ix.shard.size(); ++r)
+                if (mk_index_export_rows(ix.shard[r], r0, nr, dst.data() + ix.first[r], n) != MK_OK)
+                    die(ix.shard[r], "mk_index_export_rows");
+        };
+        future<void> next = async(launch::async, fetch, (uint64_t)0, ref(buf[0]));
+        int cur = 0;
+        for (uint64_t r0 = 0; r0 < B; r0 += slab, cur ^= 1) {
+            next.get();
+            if (r0 + slab < B) next = async(launch::async, fetch, r0 + slab, ref(buf[cur ^ 1]));
+            w.write(buf[cur].data(), buf[cur].size());
+        }
+    }
+    vector<uint8_t> bloom(bloom_bits / 8);
+    vector<uint64_t> gs(n);
+    vector<uint32_t> ss(n);
+    for (size_t r = 0; r < ix.shard.size(); ++r)
+        if (mk_index_export(ix.shard[r], nullptr, gs.data() + ix.first[r], r == 0 ? bloom.data() : nullptr,
+                            r == 0 ? bloom.size() : 0, ss.data() + ix.first[r]) != MK_OK)
+            die(ix.shard[r], "mk_index_export");
     w.write(gs.data(), gs.size() * 8);
     w.write(bloom.data(), bloom.size());
     w.write(ss.data(), ss.size() * 4);
@@ -327,10 +341,35 @@ bool load_disk(Index& ix, const string& path) {
     if ((uint32_t)ix.gpus > max(1u, n)) ix.gpus = (int)max(1u, n);
     ix.create_shards();
     const uint64_t B = 1ull << ix.h;
-    vector<uint8_t> rows(B * (uint64_t)n), bloom(bloom_bits / 8);
+    const size_t R = ix.shard.size();
+    auto col = [&](size_t r) { return (uint32_t)(r * (uint64_t)n / R); };
+    for (size_t r = 0; r < R; ++r)
+        if (mk_index_import_begin(ix.shard[r], col(r + 1) - col(r)) != MK_OK) die(ix.shard[r], "mk_index_import_begin");
+    bool ok = true;
+    if (n) {
+        const uint64_t slab = max<uint64_t>(1, min<uint64_t>(B, SLAB_BYTES / n));
+        vector<uint8_t> buf[2];
+        auto parse = [&](uint64_t r0, vector<uint8_t>& dst) {
+            const uint64_t nr = min(slab, B - r0);
+            dst.resize(nr * n);
+            return in.read(dst.data(), dst.size()) == dst.size();
+        };
+        future<bool> next = async(launch::async, parse, (uint64_t)0, ref(buf[0]));
+        int cur = 0;
+        for (uint64_t r0 = 0; r0 < B && ok; r0 += slab, cur ^= 1) {
+            ok = next.get();
+            if (!ok) break;
+            if (r0 + slab < B) next = async(launch::async, parse, r0 + slab, ref(buf[cur ^ 1]));
+            const uint64_t nr = min(slab, B - r0);
+            #pragma omp parallel for num_threads((int)R) schedule(static, 1)
+            for (size_t r = 0; r < R; ++r)
+                if (mk_index_import_rows(ix.shard[r], r0, nr, buf[cur].data() + col(r), n) != MK_OK)
+                    die(ix.shard[r], "mk_index_import_rows");
+        }
+    }
+    vector<uint8_t> bloom(bloom_bits / 8);
     vector<uint64_t> gs(n);
     vector<uint32_t> ss(n);
-    bool ok = in.read(rows.data(), rows.size()) == rows.size();
     ok = ok && in.read(gs.data(), gs.size() * 8) == gs.size() * 8;
     if (bloom_bits != 0) ok = ok && in.read(bloom.data(), bloom.size()) == bloom.size();
     ok = ok && in.read(ss.data(), ss.size() * 4) == ss.size() * 4;
@@ -338,13 +377,9 @@ bool load_disk(Index& ix, const string& path) {
         cerr << "miekki: truncated index dump" << endl;
         return false;
     }
-    const size_t R = ix.shard.size();
-    for (size_t r = 0; r < R; ++r) {
-        const uint32_t lo = (uint32_t)(r * (uint64_t)n / R), hi = (uint32_t)((r + 1) * (uint64_t)n / R);
-        if (mk_index_import(ix.shard[r], hi - lo, rows.data() + lo, n, gs.data() + lo, bloom.data(), bloom.size(),
-                            ss.data() + lo) != MK_OK)
-            die(ix.shard[r], "mk_index_import");
-    }
+    for (size_t r = 0; r < R; ++r)
+        if (mk_index_import_end(ix.shard[r], gs.data() + col(r), bloom.data(), bloom.size(), ss.data() + col(r)) != MK_OK)
+            die(ix.shard[r], "mk_index_import_end");
     ix.seal_shards();      // every shard already holds the whole Bloom table: the fold is a no-op
     ix.compressed_flag = false;                                   // :705
     if (exists_test(path + ".names")) {      // side-car written by our -d: makes `-i ... -e` work

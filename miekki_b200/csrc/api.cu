@@ -72,6 +72,8 @@ struct mk_ctx {
     uint8_t* rows = nullptr;
     uint64_t stride = 0;
     uint32_t n = 0, cap = 0, first_id = 0;
+    uint32_t importing = 0;       // mk_index_import_begin .. _end: genomes of the index being loaded
+    bool import_open = false;
     uint32_t* d_sketch_size = nullptr;
     uint64_t* d_genome_size = nullptr;
     float* d_ratio = nullptr;     // float(genome_size / sketch_size), screen of the top-k kernel
@@ -1267,23 +1269,37 @@ int mk_index_stats(mk_ctx* c, uint32_t first, uint32_t n, uint32_t* sketch_size,
     return MK_OK;
 }
 
+// rows [row0, row0 + nrows) of the dump payload: bit-plane rows -> dense byte rows on the
+// device, a slab of buckets at a time, then to the caller with its own row pitch
+static int export_rows(mk_ctx* c, uint64_t row0, uint64_t nrows, uint8_t* dst, uint64_t dst_stride) {
+    if (!nrows || !c->n) return MK_OK;
+    const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / c->n);
+    TRY(reserve(c, c->misc, std::min<uint64_t>(slab, nrows) * c->n));
+    for (uint64_t r0 = 0; r0 < nrows; r0 += slab) {
+        const uint64_t nr = std::min<uint64_t>(slab, nrows - r0);
+        launch_planes_to_bytes(c->rows, c->stride, row0 + r0, nr, c->n, static_cast<uint8_t*>(c->misc.p), c->stream);
+        CU(cudaMemcpy2DAsync(dst + r0 * dst_stride, dst_stride, c->misc.p, c->n, c->n, nr, cudaMemcpyDeviceToHost,
+                             c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->stats.kernel_launches += 1;
+    }
+    c->stats.d2h_bytes += nrows * c->n;
+    return MK_OK;
+}
+
+int mk_index_export_rows(mk_ctx* c, uint64_t row0, uint64_t nrows, uint8_t* dst, uint64_t dst_stride) {
+    if (!c || (nrows && !dst)) return fail(c, MK_ERR_ARG, "mk_index_export_rows: NULL argument");
+    Guard g(c);
+    if (row0 + nrows > c->B) return fail(c, MK_ERR_ARG, "mk_index_export_rows: range exceeds 2^h rows");
+    if (nrows && dst_stride < c->n) return fail(c, MK_ERR_ARG, "mk_index_export_rows: dst_stride < n");
+    return export_rows(c, row0, nrows, dst, dst_stride);
+}
+
 int mk_index_export(mk_ctx* c, uint8_t* rows, uint64_t* genome_size, uint8_t* bloom, uint64_t bloom_bytes,
                     uint32_t* sketch_size) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
-    if (rows && c->n) {
-        // bit-plane rows -> the dump's dense byte rows, a slab of buckets at a time
-        const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / c->n);
-        TRY(reserve(c, c->misc, std::min<uint64_t>(slab, c->B) * c->n));
-        for (uint64_t r0 = 0; r0 < c->B; r0 += slab) {
-            const uint64_t nr = std::min<uint64_t>(slab, c->B - r0);
-            launch_planes_to_bytes(c->rows, c->stride, r0, nr, c->n, static_cast<uint8_t*>(c->misc.p), c->stream);
-            CU(cudaMemcpyAsync(rows + r0 * c->n, c->misc.p, nr * c->n, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            c->stats.kernel_launches += 1;
-        }
-        c->stats.d2h_bytes += c->B * c->n;
-    }
+    if (rows) TRY(export_rows(c, 0, c->B, rows, c->n));
     if (bloom) {
         const uint64_t m = std::min<uint64_t>(bloom_bytes, c->window);
         CU(cudaMemcpyAsync(bloom, c->bloom, m, cudaMemcpyDeviceToHost, c->stream));
@@ -1296,32 +1312,43 @@ int mk_index_export(mk_ctx* c, uint8_t* rows, uint64_t* genome_size, uint8_t* bl
     return sync(c);
 }
 
-int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_stride, const uint64_t* genome_size,
-                    const uint8_t* bloom, uint64_t bloom_bytes, const uint32_t* sketch_size) {
-    if (!c || (n && (!rows || !genome_size || !sketch_size)))
-        return fail(c, MK_ERR_ARG, "mk_index_import: NULL argument");
-    Guard g(c);
-    if (n && rows_stride < n) return fail(c, MK_ERR_ARG, "mk_index_import: rows_stride < n");
+// ---- load: begin(n) -> rows in any number of slabs -> end(statistics, Bloom) -----------------
+static int import_begin(mk_ctx* c, uint32_t n) {
     c->n = 0;
+    c->importing = 0;
     c->h_sketch_size.clear();
     c->h_genome_size.clear();
     TRY(ensure_capacity(c, std::max<uint32_t>(n, 1)));
     CU(cudaMemsetAsync(c->rows, 0xFF, c->B * c->stride, c->stream));
+    c->importing = n;
+    c->import_open = true;
+    return MK_OK;
+}
+
+static int import_rows(mk_ctx* c, uint64_t row0, uint64_t nrows, const uint8_t* src, uint64_t src_stride) {
+    const uint32_t n = c->importing;
+    if (!n || !nrows) return MK_OK;
+    // dense byte rows (dump layout) -> bit-plane rows, a slab of buckets at a time
+    const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / n);
+    TRY(reserve(c, c->misc, std::min<uint64_t>(slab, nrows) * n));
+    for (uint64_t r0 = 0; r0 < nrows; r0 += slab) {
+        const uint64_t nr = std::min<uint64_t>(slab, nrows - r0);
+        CU(cudaMemcpy2DAsync(c->misc.p, n, src + r0 * src_stride, src_stride, n, nr, cudaMemcpyHostToDevice, c->stream));
+        launch_bytes_to_planes(static_cast<uint8_t*>(c->misc.p), n, row0 + r0, nr, n, c->rows, c->stride, c->stream);
+        CU(cudaStreamSynchronize(c->stream));
+        c->stats.kernel_launches += 1;
+    }
+    c->stats.h2d_bytes += nrows * n;
+    return MK_OK;
+}
+
+static int import_end(mk_ctx* c, const uint64_t* genome_size, const uint8_t* bloom, uint64_t bloom_bytes,
+                      const uint32_t* sketch_size) {
+    const uint32_t n = c->importing;
     if (n) {
-        // dense byte rows (dump layout) -> bit-plane rows, a slab of buckets at a time
-        const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / n);
-        TRY(reserve(c, c->misc, std::min<uint64_t>(slab, c->B) * n));
-        for (uint64_t r0 = 0; r0 < c->B; r0 += slab) {
-            const uint64_t nr = std::min<uint64_t>(slab, c->B - r0);
-            CU(cudaMemcpy2DAsync(c->misc.p, n, rows + r0 * rows_stride, rows_stride, n, nr, cudaMemcpyHostToDevice,
-                                 c->stream));
-            launch_bytes_to_planes(static_cast<uint8_t*>(c->misc.p), n, r0, nr, n, c->rows, c->stride, c->stream);
-            CU(cudaStreamSynchronize(c->stream));
-            c->stats.kernel_launches += 1;
-        }
         CU(cudaMemcpyAsync(c->d_sketch_size, sketch_size, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_genome_size, genome_size, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-        c->stats.h2d_bytes += c->B * n + (size_t)n * 12;
+        c->stats.h2d_bytes += (size_t)n * 12;
     }
     CU(cudaMemsetAsync(c->bloom, 0, c->window, c->stream));
     if (bloom && bloom_bytes) {
@@ -1334,7 +1361,45 @@ int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_st
     c->h_genome_size.assign(genome_size, genome_size + n);
     TRY(upload_ratio(c, 0, n));
     c->n = n;
+    c->importing = 0;
+    c->import_open = false;
     return MK_OK;
+}
+
+int mk_index_import_begin(mk_ctx* c, uint32_t n) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    return import_begin(c, n);
+}
+
+int mk_index_import_rows(mk_ctx* c, uint64_t row0, uint64_t nrows, const uint8_t* src, uint64_t src_stride) {
+    if (!c || (nrows && !src)) return fail(c, MK_ERR_ARG, "mk_index_import_rows: NULL argument");
+    Guard g(c);
+    if (!c->import_open) return fail(c, MK_ERR_STATE, "mk_index_import_rows: call mk_index_import_begin first");
+    if (row0 + nrows > c->B) return fail(c, MK_ERR_ARG, "mk_index_import_rows: range exceeds 2^h rows");
+    if (nrows && src_stride < c->importing) return fail(c, MK_ERR_ARG, "mk_index_import_rows: src_stride < n");
+    return import_rows(c, row0, nrows, src, src_stride);
+}
+
+int mk_index_import_end(mk_ctx* c, const uint64_t* genome_size, const uint8_t* bloom, uint64_t bloom_bytes,
+                        const uint32_t* sketch_size) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    if (!c->import_open) return fail(c, MK_ERR_STATE, "mk_index_import_end: call mk_index_import_begin first");
+    if (c->importing && (!genome_size || !sketch_size))
+        return fail(c, MK_ERR_ARG, "mk_index_import_end: NULL argument");
+    return import_end(c, genome_size, bloom, bloom_bytes, sketch_size);
+}
+
+int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_stride, const uint64_t* genome_size,
+                    const uint8_t* bloom, uint64_t bloom_bytes, const uint32_t* sketch_size) {
+    if (!c || (n && (!rows || !genome_size || !sketch_size)))
+        return fail(c, MK_ERR_ARG, "mk_index_import: NULL argument");
+    Guard g(c);
+    if (n && rows_stride < n) return fail(c, MK_ERR_ARG, "mk_index_import: rows_stride < n");
+    TRY(import_begin(c, n));
+    TRY(import_rows(c, 0, c->B, rows, rows_stride));
+    return import_end(c, genome_size, bloom, bloom_bytes, sketch_size);
 }
 
 uint64_t mk_bloom_window(const mk_ctx* c) { return c ? c->window : 0; }

@@ -16,9 +16,10 @@ pytestmark = pytest.mark.gpu
 CLI = os.path.join(H.ROOT, "miekki_b200", "cli", "miekki")
 
 
-def run_cli(args, cwd):
+def run_cli(args, cwd, env=None):
     assert os.path.exists(CLI), "build the CLI first: make"
-    r = subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, **env) if env else None)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
 
@@ -47,6 +48,20 @@ def test_cli_build_query_dump(tmp_path, s):
         stdout = run_cli(["-i", dump, "-a", os.path.join(d, "reads.fa"), "-o", out2, "-k", 21, "-s", 1], d)
         assert "Load sucessful" in stdout
         assert out2.read_text() == open(os.path.join(d, "hits_s200.txt")).read()
+
+
+@pytest.mark.parametrize("devices", ["0", "0,0,0"])
+def test_cli_dump_and_load_in_many_slabs(tmp_path, devices):
+    """-d / -i stream the matrix a slab of bucket rows at a time (256 MB by default).  A 1,000-byte
+    slab cuts this 4,096 x 14 matrix into 58 slabs: the payload and the answers must not change."""
+    d = os.path.join(H.GOLDEN, "caseA")
+    env = {"MIEKKI_DUMP_SLAB_BYTES": "1000"}
+    run_cli(["-l", "list.txt", "-k", 31, "-h", 12, "-t", 4, "-d", tmp_path / "whole.gz"], d)
+    run_cli(["-l", "list.txt", "-k", 31, "-h", 12, "-t", 4, "-d", tmp_path / "slabs.gz", "--devices", devices], d, env)
+    assert orc.read_payload(str(tmp_path / "whole.gz")) == orc.read_payload(str(tmp_path / "slabs.gz"))
+    out = tmp_path / "hits.txt"
+    run_cli(["-i", tmp_path / "slabs.gz", "-a", os.path.join(d, "reads.fa"), "-o", out, "--devices", devices], d, env)
+    assert out.read_text() == open(os.path.join(d, "hits_s200.txt")).read()
 
 
 @pytest.mark.parametrize("s,fname", [(200, "exact.txt"), (0, "exact_s0.txt")])

@@ -141,6 +141,41 @@ def test_case_a_export_import_roundtrip(mk, case_a):
     ix2.close()
 
 
+def test_case_a_streamed_export_import(mk, case_a):
+    """mk_index_export_rows / mk_index_import_{begin,rows,end}: the matrix in slabs, two shards
+    filling their columns of one host slab, equals the one-shot calls."""
+    d, ix, _ = case_a
+    whole = ix.export()
+    B, n = whole["rows"].shape
+    got = np.concatenate([ix.export_rows(r0, min(1000, B - r0)) for r0 in range(0, B, 1000)])
+    assert np.array_equal(got, whole["rows"])
+    assert np.array_equal(got, H.load_dump_npz(os.path.join(d, "dump.npz"))["rows"])
+    split = 5
+    a, b = mk.Miekki(k=31, h=12), mk.Miekki(k=31, h=12)
+    a.import_begin(split)
+    b.import_begin(n - split)
+    for r0 in range(0, B, 700):
+        slab = np.ascontiguousarray(whole["rows"][r0:r0 + 700])
+        a.import_rows(r0, slab, 0)
+        b.import_rows(r0, slab, split)
+    a.import_end(whole["genome_size"][:split], whole["bloom"], whole["sketch_size"][:split])
+    b.import_end(whole["genome_size"][split:], whole["bloom"], whole["sketch_size"][split:])
+    b.set_shard(split)
+    out = np.zeros((B, n), np.uint8)
+    for r0 in range(0, B, 512):
+        a.export_rows(r0, 512, out[r0:r0 + 512], 0)
+        b.export_rows(r0, 512, out[r0:r0 + 512], split)
+    assert np.array_equal(out, whole["rows"])
+    ea, eb = a.export(rows=False), b.export(rows=False)
+    assert np.array_equal(np.concatenate([ea["genome_size"], eb["genome_size"]]), whole["genome_size"])
+    assert np.array_equal(np.concatenate([ea["sketch_size"], eb["sketch_size"]]), whole["sketch_size"])
+    assert np.array_equal(ea["bloom"], whole["bloom"]) and np.array_equal(eb["bloom"], whole["bloom"])
+    with pytest.raises(mk.MiekkiError):
+        mk.Miekki(k=31, h=12).import_rows(0, whole["rows"][:4].copy())    # no import_begin
+    a.close()
+    b.close()
+
+
 def test_case_a_sharded_chain_equals_unsharded(mk, case_a):
     """Two genome shards (ids 0-5 and 6-13), Bloom merged "lowest rank wins", heap chained
     in ascending id order: identical lines to the single-index run."""
