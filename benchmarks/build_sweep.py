@@ -24,6 +24,7 @@ ap.add_argument("--host-genomes", type=int, default=64)
 ap.add_argument("--batch", type=int, default=128, help="genomes per mk_index_add_batch call")
 ap.add_argument("--hs", default="17,19,20")
 ap.add_argument("--ks", default="21,31")
+ap.add_argument("--trace", action="store_true", help="per-batch wall and device times on stderr")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -41,17 +42,27 @@ for h in map(int, a.hs.split(",")):
     for k in map(int, a.ks.split(",")):
         ix = miekki_b200.Miekki(k=k, h=h, device=local)
         ix.reserve(a.genomes)
-        b = ix.synth(1, 0, 32, a.genome_len)
-        ix.insert_batch(b)                       # warm-up: allocates scratch
+        b = ix.synth(1, 0, 64, a.genome_len)
+        ix.insert_batch(b)                       # warm-up: one full 64-genome chunk sizes all scratch
         b.free()
         ix.stats_reset()
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
-        for g0 in range(32, a.genomes, a.batch):
+        trace = []
+        for g0 in range(64, a.genomes, a.batch):
+            t1 = time.perf_counter()
             b = ix.synth(1, rank * a.genomes + g0, min(a.batch, a.genomes - g0), a.genome_len)
+            t2 = time.perf_counter()
             ix.insert_batch(b)
+            t3 = time.perf_counter()
             b.free()
+            if a.trace:
+                trace.append((g0, round((t2 - t1) * 1e3, 2), round((t3 - t2) * 1e3, 2), round(ix.stats()["sketch_ms"], 2)))
+        if a.trace and rank == 0:
+            print("g0, synth ms, insert ms, cumulative device ms:", file=sys.stderr)
+            for row in trace[:12] + trace[-12:]:
+                print(row, file=sys.stderr)
         wall = time.perf_counter() - t0
         st = ix.stats()
         bases = st["bases_sketched"]

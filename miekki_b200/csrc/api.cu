@@ -478,9 +478,20 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
                          static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, c->stream);
     launch_sketch_dense(static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, v.d_len,
                         d_woff, n, v.max_len, (int)c->k, (int)c->h, keys, ks, c->stream);
-    launch_resolve(keys, static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, d_woff, n,
-                   c->sp(), static_cast<uint8_t*>(c->fp.p), d_active, d_ssum, c->bloom,
-                   bloom_insert ? c->owner : nullptr, pair_full, pair_words, ks, d_claims, d_n_claims, c->stream);
+    static const bool split = [] {
+        const char* e = getenv("MIEKKI_RESOLVE_SPLIT");
+        return !e || atoi(e) != 0;
+    }();
+    if (split && bloom_insert && ks && pair_full && resolve_tagged_ok((int)c->h, pair_words)) {
+        launch_resolve_tagged(keys, static_cast<uint32_t*>(c->planeF.p), d_woff, n, c->sp(),
+                              static_cast<uint8_t*>(c->fp.p), d_active, d_ssum, c->bloom, c->owner, pair_full, pair_words,
+                              ks, d_claims, d_n_claims, c->stream);
+        c->stats.kernel_launches += 1;
+    } else {
+        launch_resolve(keys, static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, d_woff, n,
+                       c->sp(), static_cast<uint8_t*>(c->fp.p), d_active, d_ssum, c->bloom,
+                       bloom_insert ? c->owner : nullptr, pair_full, pair_words, ks, d_claims, d_n_claims, c->stream);
+    }
     c->stats.kernel_launches += 4;
     CU(cudaGetLastError());
     out->d_woff = d_woff;
@@ -491,12 +502,18 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
     return MK_OK;
 }
 
-// genomes per dense chunk: bounded by the Bloom owner key (5 + h + 3 bits <= 32) and memory
+// genomes per dense chunk: bounded by the Bloom owner key (6 + h + 3 bits <= 32) and memory.
+// 64 genomes are two whole 32-genome groups, i.e. full 32-byte sectors of a row per scatter.
 uint32_t dense_chunk(const mk_ctx* c) {
+    static const uint32_t want = [] {
+        const char* e = getenv("MIEKKI_BUILD_CHUNK");
+        return (uint32_t)std::max(1, std::min(64, e ? atoi(e) : 64));
+    }();
     uint32_t by_key = c->h <= 24 ? (1u << std::min<uint32_t>(29 - c->h, 6)) : 1;
-    uint64_t by_mem = (1ull << 30) / (c->B * 13);       // keys + fp + claim list <= 1 GiB
+    uint64_t by_mem = (2ull << 30) / (c->B * 13);       // keys + fp + claim list <= 2 GiB
     uint32_t ch = (uint32_t)std::min<uint64_t>(by_key, std::max<uint64_t>(1, by_mem));
-    return std::max<uint32_t>(1, std::min<uint32_t>(ch, 32));
+    ch = std::max<uint32_t>(1, std::min<uint32_t>(ch, want));
+    return ch >= 32 ? ch / 32 * 32 : ch;                // whole groups keep every chunk group-aligned
 }
 
 // Miekki.cpp:303-311 on the host, from the device's exact integer statistics

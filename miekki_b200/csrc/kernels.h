@@ -36,6 +36,14 @@ void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const 
                     uint32_t* active, unsigned long long* ssum, const uint8_t* bloom,
                     uint32_t* owner, const uint32_t* pair_full, uint32_t pair_words, int ks,
                     uint32_t* claims, uint32_t* n_claims, cudaStream_t st);
+// The same for a build with tagged keys (ks != 0) and a page bitmap, as two kernels: a streaming
+// pass over all keys (fp, statistics, list of buckets on unsaturated pages) and a look-up pass
+// over that list, which leaves the claimants in it (other entries become 0xFFFFFFFF).
+bool resolve_tagged_ok(int h, uint32_t pair_words);
+void launch_resolve_tagged(unsigned long long* keys_anc, const uint32_t* planeF, const uint64_t* woff,
+                           uint32_t n_seq, SketchParams p, uint8_t* fp, uint32_t* active, unsigned long long* ssum,
+                           const uint8_t* bloom, uint32_t* owner, const uint32_t* pair_full, uint32_t pair_words,
+                           int ks, uint32_t* list, uint32_t* n_list, cudaStream_t st);
 // Bloom pages without a zero byte -> full8[n_pages], pair_full[ceil(n_pages / 32)]
 uint32_t bloom_page_count(uint64_t window);
 uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint8_t* full8, uint32_t* pair_full,

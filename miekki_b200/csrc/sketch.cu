@@ -203,9 +203,10 @@ __device__ __forceinline__ uint32_t owner_key(uint32_t s, uint32_t bucket, uint3
 // canonical k-mer to a range whose five probes stay inside those two pages, so a set bit
 // proves the insert changes nothing: `anc` is not needed and all three look-ups are skipped.
 constexpr int RES_U = 4;
+constexpr uint32_t NO_CLAIM = 0xFFFFFFFFu;     // claim-list entry struck off by resolve_slow_kernel
 constexpr uint32_t PAIR_WORDS_MAX = 1032;      // (2^27 + 16 window bytes) / 4096 / 32, rounded up
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __restrict__ planeF,
                const uint64_t* __restrict__ woff, SketchParams p, uint8_t* __restrict__ fp_out,
                uint32_t* __restrict__ active, unsigned long long* __restrict__ ssum,
@@ -213,6 +214,8 @@ resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __rest
                const uint32_t* __restrict__ pair_full, uint32_t pair_words, int ks,
                uint32_t* __restrict__ claims, uint32_t* __restrict__ n_claims) {
     __shared__ uint32_t s_pair[PAIR_WORDS_MAX];
+    __shared__ uint32_t s_act[8], s_claims[8], s_base;
+    __shared__ unsigned long long s_sum[8];
     const bool tagged = owner != nullptr && pair_full != nullptr && ks != 0;
     if (tagged) {
         for (uint32_t i = threadIdx.x; i < pair_words; i += blockDim.x) s_pair[i] = pair_full[i];
@@ -225,48 +228,295 @@ resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __rest
     const uint64_t kmask = (1ull << (2 * p.k)) - 1;
     const int tag_shift = key_tag_shift(p.k);
     const int page_shift = (int)p.bloom_log2 + 3 + BLOOM_PAGE_LOG2;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t act = 0;
     unsigned long long sum = 0;
 
-    uint32_t b[RES_U];
-    unsigned long long key[RES_U];
-    bool slow[RES_U];                                       // needs anc (and maybe a Bloom claim)
+    // A CTA walks several tiles of 256 * RES_U buckets: the page bitmap is loaded once, and a
+    // short-lived CTA per tile spent most of its life in the launch / drain latency chain.
+    const uint32_t n_tiles = (B + 256 * RES_U - 1) / (256 * RES_U);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t b[RES_U];
+        unsigned long long key[RES_U];
+        bool slow[RES_U];                                       // needs anc (and maybe a Bloom claim)
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 1: keys (coalesced)
+            b[u] = (tile * RES_U + u) * blockDim.x + threadIdx.x;
+            key[u] = b[u] < B ? keys_anc[row + b[u]] : EMPTY_KEY;
+            slow[u] = (key[u] >> POS_BITS) != EMPTY_FP;
+            if (tagged && slow[u]) {
+                const uint32_t page = (uint32_t)(((key[u] & KEY_TAG_MASK) << tag_shift) >> page_shift);
+                if ((s_pair[page >> 5] >> (page & 31)) & 1u) slow[u] = false;
+            }
+        }
+        uint2 w0[RES_U], w1[RES_U], w2[RES_U];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 2: plane words at the winning position
+            w0[u] = w1[u] = w2[u] = make_uint2(0u, 0u);
+            if (slow[u]) {
+                const uint64_t w = ((key[u] & POS_MASK) >> ks) >> 4;
+                w0[u] = P[w];
+                w1[u] = P[w + 1];
+                w2[u] = P[w + 2];
+            }
+        }
+        unsigned long long anc[RES_U];
+        uint64_t slot[RES_U][2];
+        uint32_t probe[RES_U][2];
+        int nd[RES_U];
+        uint8_t cell[RES_U][2];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 3: hashes, Bloom bytes
+            anc[u] = EMPTY_ANC;
+            nd[u] = 0;
+            cell[u][0] = cell[u][1] = 1;
+            if (slow[u]) {
+                const int j = (int)(((key[u] & POS_MASK) >> ks) & 15);
+                anc[u] = kmer_hash(w0[u].x, w1[u].x, w2[u].x, w0[u].y, w1[u].y, w2[u].y, j, p.k, kmask);
+                if (owner != nullptr) {
+                    BloomProbe pr(anc[u]);
+                    nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (q < nd[u]) {
+                            const uint64_t byte = slot[u][q] >> 3;
+                            cell[u][q] = byte < p.bloom_window ? bloom[byte] : (uint8_t)1;
+                        }
+                }
+            }
+        }
+        uint32_t claim_bits = 0;
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 4: claims and stores
+            const bool in = b[u] < B;
+            const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
+            bool claimed = false;
+            if (in && fp != EMPTY_FP) {
+                act += 1;
+                sum += 1ull << (31 - (fp >> 3));                // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
+                if (owner != nullptr) {                         // Bloom pass A (Miekki.cpp:295-299)
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (q < nd[u] && cell[u][q] == 0) {
+                            atomicMin(owner + (slot[u][q] >> 3), owner_key(s, b[u], probe[u][q], p.h));
+                            claimed = true;
+                        }
+                }
+            }
+            claim_bits |= claimed ? (1u << u) : 0u;
+            if (!in) continue;
+            // during a build only claimants are looked at again (bloom_commit_kernel reads their anc)
+            if (owner == nullptr || slow[u]) keys_anc[row + b[u]] = anc[u];
+            fp_out[row + b[u]] = (uint8_t)fp;
+        }
+        if (owner == nullptr) continue;
+        // the claimant list (pass B only revisits claimants): one global atomic per tile, and
+        // none at all once the Bloom table is saturated
+        if (!__syncthreads_or((int)claim_bits)) continue;
+        const uint32_t mine = __popc(claim_bits);
+        uint32_t before = mine;                                 // inclusive prefix sum over the warp
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, before, o);
+            if (lane >= (uint32_t)o) before += t;
+        }
+        if (lane == 31) s_claims[warp] = before;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cl = 0;
+            for (unsigned w = 0; w < blockDim.x / 32; ++w) {
+                const uint32_t x = s_claims[w];
+                s_claims[w] = cl;                               // -> exclusive offset of the warp
+                cl += x;
+            }
+            s_base = atomicAdd(n_claims, cl);
+        }
+        __syncthreads();
+        if (mine) {
+            uint32_t at = s_base + s_claims[warp] + before - mine;
+            #pragma unroll
+            for (int u = 0; u < RES_U; ++u)
+                if (claim_bits & (1u << u)) claims[at++] = (s << p.h) | b[u];
+        }
+        __syncthreads();                                        // s_claims / s_base are reused by the next tile
+    }
+    // per-sequence statistics: warp shuffles, then one pair of global atomics per block
     #pragma unroll
-    for (int u = 0; u < RES_U; ++u) {                       // stage 1: keys (coalesced)
-        b[u] = (blockIdx.x * RES_U + u) * blockDim.x + threadIdx.x;
-        key[u] = b[u] < B ? keys_anc[row + b[u]] : EMPTY_KEY;
-        slow[u] = (key[u] >> POS_BITS) != EMPTY_FP;
-        if (tagged && slow[u]) {
-            const uint32_t page = (uint32_t)(((key[u] & KEY_TAG_MASK) << tag_shift) >> page_shift);
-            if ((s_pair[page >> 5] >> (page & 31)) & 1u) slow[u] = false;
+    for (int o = 16; o > 0; o >>= 1) {
+        act += __shfl_xor_sync(0xffffffffu, act, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) {
+        s_act[warp] = act;
+        s_sum[warp] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0;
+        unsigned long long t = 0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) { a += s_act[w]; t += s_sum[w]; }
+        if (a) {
+            atomicAdd(active + s, a);
+            atomicAdd(ssum + s, t);
         }
     }
-    uint2 w0[RES_U], w1[RES_U], w2[RES_U];
-    #pragma unroll
-    for (int u = 0; u < RES_U; ++u) {                       // stage 2: plane words at the winning position
-        w0[u] = w1[u] = w2[u] = make_uint2(0u, 0u);
-        if (slow[u]) {
-            const uint64_t w = ((key[u] & POS_MASK) >> ks) >> 4;
-            w0[u] = P[w];
-            w1[u] = P[w + 1];
-            w2[u] = P[w + 2];
+}
+
+// ---- build with tagged keys: the same work as resolve_kernel, split in two ------------------
+// resolve_fast_kernel streams every key once (32 bytes per thread and tile, two tiles in
+// flight): fingerprint bytes, per-genome statistics, and the list of buckets whose k-mer may
+// still change the Bloom table (page bitmap says "not saturated").  resolve_slow_kernel then
+// looks only those buckets up (key -> plane words -> anc -> Bloom bytes), registers claims and
+// keeps the claimants in the list for bloom_commit_kernel.  Once the table is saturated the
+// list is almost empty and the build no longer does any random look-up per bucket.
+__global__ void __launch_bounds__(256)
+resolve_fast_kernel(const unsigned long long* __restrict__ keys, SketchParams p, uint8_t* __restrict__ fp_out,
+                    uint32_t* __restrict__ active, unsigned long long* __restrict__ ssum,
+                    const uint32_t* __restrict__ pair_full, uint32_t pair_words,
+                    uint32_t* __restrict__ slow_list, uint32_t* __restrict__ n_slow) {
+    __shared__ uint32_t s_pair[PAIR_WORDS_MAX];
+    __shared__ uint32_t s_act[8], s_cnt[8], s_base;
+    __shared__ unsigned long long s_sum[8];
+    for (uint32_t i = threadIdx.x; i < pair_words; i += blockDim.x) s_pair[i] = pair_full[i];
+    __syncthreads();
+    const uint32_t s = blockIdx.y;
+    const uint32_t B = 1u << p.h;                               // multiple of 1024 (host: h >= 10)
+    const uint64_t row = (uint64_t)s << p.h;
+    const int tag_shift = key_tag_shift(p.k);
+    const int page_shift = (int)p.bloom_log2 + 3 + BLOOM_PAGE_LOG2;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = B >> 10;
+    uint32_t act = 0;
+    unsigned long long sum = 0;
+    constexpr int T = 2;                                        // tiles in flight per CTA
+    for (uint32_t tile0 = blockIdx.x * T; tile0 < n_tiles; tile0 += gridDim.x * T) {
+        ulonglong2 k01[T], k23[T];
+        #pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint32_t b4 = (tile0 + t < n_tiles) ? ((tile0 + t) << 10) + 4 * threadIdx.x : 0xFFFFFFFFu;
+            if (b4 != 0xFFFFFFFFu) {
+                const ulonglong2* src = reinterpret_cast<const ulonglong2*>(keys + row + b4);
+                k01[t] = src[0];
+                k23[t] = src[1];
+            } else {
+                k01[t] = k23[t] = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
+            }
+        }
+        #pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (tile0 + t >= n_tiles) break;                    // uniform over the CTA
+            const uint32_t b4 = ((tile0 + t) << 10) + 4 * threadIdx.x;
+            const unsigned long long key[4] = {k01[t].x, k01[t].y, k23[t].x, k23[t].y};
+            uint32_t packed = 0, slow_bits = 0;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
+                packed |= fp << (8 * u);
+                if (fp != EMPTY_FP) {
+                    act += 1;
+                    sum += 1ull << (31 - (fp >> 3));            // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
+                    const uint32_t page = (uint32_t)(((key[u] & KEY_TAG_MASK) << tag_shift) >> page_shift);
+                    if (!((s_pair[page >> 5] >> (page & 31)) & 1u)) slow_bits |= 1u << u;
+                }
+            }
+            *reinterpret_cast<uint32_t*>(fp_out + row + b4) = packed;
+            if (!__syncthreads_or((int)slow_bits)) continue;
+            const uint32_t mine = __popc(slow_bits);
+            uint32_t before = mine;                             // inclusive prefix sum over the warp
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, before, o);
+                if (lane >= (uint32_t)o) before += x;
+            }
+            if (lane == 31) s_cnt[warp] = before;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t cl = 0;
+                for (unsigned w = 0; w < blockDim.x / 32; ++w) {
+                    const uint32_t x = s_cnt[w];
+                    s_cnt[w] = cl;
+                    cl += x;
+                }
+                s_base = atomicAdd(n_slow, cl);
+            }
+            __syncthreads();
+            if (mine) {
+                uint32_t at = s_base + s_cnt[warp] + before - mine;
+                #pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (slow_bits & (1u << u)) slow_list[at++] = (s << p.h) | (b4 + u);
+            }
+            __syncthreads();
         }
     }
-    unsigned long long anc[RES_U];
-    uint64_t slot[RES_U][2];
-    uint32_t probe[RES_U][2];
-    int nd[RES_U];
-    uint8_t cell[RES_U][2];
     #pragma unroll
-    for (int u = 0; u < RES_U; ++u) {                       // stage 3: hashes, Bloom bytes
-        anc[u] = EMPTY_ANC;
-        nd[u] = 0;
-        cell[u][0] = cell[u][1] = 1;
-        if (slow[u]) {
-            const int j = (int)(((key[u] & POS_MASK) >> ks) & 15);
-            anc[u] = kmer_hash(w0[u].x, w1[u].x, w2[u].x, w0[u].y, w1[u].y, w2[u].y, j, p.k, kmask);
-            if (owner != nullptr) {
-                BloomProbe pr(anc[u]);
+    for (int o = 16; o > 0; o >>= 1) {
+        act += __shfl_xor_sync(0xffffffffu, act, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) {
+        s_act[warp] = act;
+        s_sum[warp] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0;
+        unsigned long long t = 0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) { a += s_act[w]; t += s_sum[w]; }
+        if (a) {
+            atomicAdd(active + s, a);
+            atomicAdd(ssum + s, t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+resolve_slow_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __restrict__ planeF,
+                    const uint64_t* __restrict__ woff, SketchParams p, const uint8_t* __restrict__ bloom,
+                    uint32_t* __restrict__ owner, uint32_t* __restrict__ list,
+                    const uint32_t* __restrict__ n_list, int ks) {
+    const uint32_t total = *n_list;
+    const uint32_t bmask = (1u << p.h) - 1;
+    const uint64_t kmask = (1ull << (2 * p.k)) - 1;
+    const uint32_t step = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += RES_U * step) {
+        uint32_t id[RES_U];
+        bool live[RES_U];
+        unsigned long long key[RES_U];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 0: list entries (coalesced)
+            const uint32_t i = i0 + u * step;
+            live[u] = i < total;
+            id[u] = live[u] ? list[i] : 0u;
+        }
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) key[u] = live[u] ? keys_anc[id[u]] : 0ull;     // stage 1
+        uint2 w0[RES_U], w1[RES_U], w2[RES_U];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 2: plane words at the winning position
+            w0[u] = w1[u] = w2[u] = make_uint2(0u, 0u);
+            if (live[u]) {
+                const uint2* P = reinterpret_cast<const uint2*>(planeF) + woff[id[u] >> p.h];
+                const uint64_t w = ((key[u] & POS_MASK) >> ks) >> 4;
+                w0[u] = P[w];
+                w1[u] = P[w + 1];
+                w2[u] = P[w + 2];
+            }
+        }
+        uint64_t slot[RES_U][2];
+        uint32_t probe[RES_U][2];
+        int nd[RES_U];
+        uint8_t cell[RES_U][2];
+        #pragma unroll
+        for (int u = 0; u < RES_U; ++u) {                       // stage 3: anc, Bloom bytes
+            nd[u] = 0;
+            cell[u][0] = cell[u][1] = 1;
+            if (live[u]) {
+                const int j = (int)(((key[u] & POS_MASK) >> ks) & 15);
+                const unsigned long long anc =
+                    kmer_hash(w0[u].x, w1[u].x, w2[u].x, w0[u].y, w1[u].y, w2[u].y, j, p.k, kmask);
+                keys_anc[id[u]] = anc;                          // bloom_commit_kernel reads it
+                BloomProbe pr(anc);
                 nd[u] = bloom_first_probes(pr, p.bloom_log2, slot[u], probe[u]);
                 #pragma unroll
                 for (int q = 0; q < 2; ++q)
@@ -276,77 +526,18 @@ resolve_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* __rest
                     }
             }
         }
-    }
-    uint32_t claim_bits = 0;
-    #pragma unroll
-    for (int u = 0; u < RES_U; ++u) {                       // stage 4: claims and stores
-        const bool in = b[u] < B;
-        const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
-        bool claimed = false;
-        if (in && fp != EMPTY_FP) {
-            act += 1;
-            sum += 1ull << (31 - (fp >> 3));                // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
-            if (owner != nullptr) {                         // Bloom pass A (Miekki.cpp:295-299)
-                #pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    if (q < nd[u] && cell[u][q] == 0) {
-                        atomicMin(owner + (slot[u][q] >> 3), owner_key(s, b[u], probe[u][q], p.h));
-                        claimed = true;
-                    }
-            }
-        }
-        claim_bits |= claimed ? (1u << u) : 0u;
-        if (!in) continue;
-        // during a build only claimants are looked at again (bloom_commit_kernel reads their anc)
-        if (owner == nullptr || slow[u]) keys_anc[row + b[u]] = anc[u];
-        fp_out[row + b[u]] = (uint8_t)fp;
-    }
-    // per-sequence statistics and the claimant list (pass B only revisits claimants): warp
-    // shuffles, then one set of global atomics per block
-    __shared__ uint32_t s_act[8], s_claims[8], s_base;
-    __shared__ unsigned long long s_sum[8];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t mine = __popc(claim_bits);
-    uint32_t before = mine;                                 // inclusive prefix sum over the warp
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, before, o);
-        if (lane >= (uint32_t)o) before += t;
-    }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        act += __shfl_xor_sync(0xffffffffu, act, o);
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    if (lane == 31) s_claims[warp] = before;
-    if (lane == 0) {
-        s_act[warp] = act;
-        s_sum[warp] = sum;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t a = 0, cl = 0;
-        unsigned long long t = 0;
-        for (unsigned w = 0; w < blockDim.x / 32; ++w) {
-            a += s_act[w];
-            t += s_sum[w];
-            const uint32_t x = s_claims[w];
-            s_claims[w] = cl;                               // -> exclusive offset of the warp
-            cl += x;
-        }
-        if (a) {
-            atomicAdd(active + s, a);
-            atomicAdd(ssum + s, t);
-        }
-        s_base = cl ? atomicAdd(n_claims, cl) : 0u;
-    }
-    if (owner == nullptr) return;
-    __syncthreads();
-    if (mine) {
-        uint32_t at = s_base + s_claims[warp] + before - mine;
         #pragma unroll
-        for (int u = 0; u < RES_U; ++u)
-            if (claim_bits & (1u << u)) claims[at++] = (s << p.h) | b[u];
+        for (int u = 0; u < RES_U; ++u) {                       // stage 4: claims (Miekki.cpp:295-299, pass A)
+            if (!live[u]) continue;
+            bool claimed = false;
+            #pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (q < nd[u] && cell[u][q] == 0) {
+                    atomicMin(owner + (slot[u][q] >> 3), owner_key(id[u] >> p.h, id[u] & bmask, probe[u][q], p.h));
+                    claimed = true;
+                }
+            if (!claimed) list[i0 + u * step] = NO_CLAIM;       // pass B skips it
+        }
     }
 }
 
@@ -426,8 +617,8 @@ bloom_commit_kernel(const unsigned long long* __restrict__ anc, const uint32_t* 
         #pragma unroll
         for (int u = 0; u < RES_U; ++u) {
             const uint32_t i = i0 + u * step;
-            live[u] = i < total;
-            id[u] = live[u] ? claims[i] : 0u;
+            id[u] = i < total ? claims[i] : NO_CLAIM;
+            live[u] = id[u] != NO_CLAIM;                        // resolve_slow_kernel struck it off
         }
         #pragma unroll
         for (int u = 0; u < RES_U; ++u) a[u] = live[u] ? anc[id[u]] : 0ull;
@@ -469,36 +660,46 @@ __device__ __forceinline__ uint4* plane_ptr(uint8_t* rows, uint64_t stride, uint
     return reinterpret_cast<uint4*>(rows + b * stride + (half ? (stride >> 1) : 0) + 16ull * group);
 }
 
-// fp[s][b] (s = genome col0 + s) -> plane bits.  One thread per bucket: reads along b are
-// contiguous across the warp; the read-modify-write touches the <= 2 groups the chunk spans.
+// fp[s][b] (s = genome col0 + s) -> plane bits.  One thread per (bucket, 32-genome group the
+// chunk touches): the <= 32 fingerprint loads are independent (contiguous along b across the
+// warp) and fully unrolled.  A group whose first genome belongs to this chunk has never been
+// written (genomes are appended in id order, untouched cells are all ones), so it is stored
+// without reading the row; only a chunk that starts inside a group merges with what is there.
 __global__ void __launch_bounds__(256)
 scatter_planes_kernel(const uint8_t* __restrict__ fp, uint32_t n_seq, int h, uint8_t* __restrict__ rows,
                       uint64_t stride, uint32_t col0) {
+    // neighbouring lanes own the two groups of one 32-byte sector of a row half
     const uint64_t B = 1ull << h;
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const uint32_t g_first = col0 >> 5, g_last = (col0 + n_seq - 1) >> 5;
-    for (uint32_t grp = g_first; grp <= g_last; ++grp) {
-        const uint32_t lo = max(col0, grp << 5), hi = min(col0 + n_seq, (grp + 1) << 5);
-        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint32_t mask = 0;
-        for (uint32_t g = lo; g < hi; ++g) {
-            const uint32_t f = fp[((uint64_t)(g - col0) << h) + b];
-            const uint32_t bit = g & 31u;
-            mask |= 1u << bit;
-            #pragma unroll
-            for (int p = 0; p < 8; ++p) w[p] |= ((f >> p) & 1u) << bit;
-        }
+    const uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t grp = (col0 >> 5) + 2 * blockIdx.y + (threadIdx.x & 1u);
+    if (b >= B || grp > ((col0 + n_seq - 1) >> 5)) return;
+    const uint32_t lo = max(col0, grp << 5), hi = min(col0 + n_seq, (grp + 1) << 5);
+    const uint32_t bit0 = lo & 31u, cnt = hi - lo;
+    const uint8_t* src = fp + ((uint64_t)(lo - col0) << h) + b;
+    uint32_t f[32];
+    #pragma unroll
+    for (uint32_t i = 0; i < 32; ++i) f[i] = i < cnt ? src[(uint64_t)i << h] : 0xFFu;
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    #pragma unroll
+    for (uint32_t i = 0; i < 32; ++i) {
         #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint4* q = plane_ptr(rows, stride, b, grp, half);
-            uint4 v = *q;
-            v.x = (v.x & ~mask) | w[4 * half + 0];
-            v.y = (v.y & ~mask) | w[4 * half + 1];
-            v.z = (v.z & ~mask) | w[4 * half + 2];
-            v.w = (v.w & ~mask) | w[4 * half + 3];
-            *q = v;
+        for (int p = 0; p < 8; ++p) w[p] |= ((f[i] >> p) & 1u) << i;
+    }
+    // bits [bit0, bit0 + cnt) of the group are ours; slots past cnt were filled with 255
+    const uint32_t keep = bit0 ? ((1u << bit0) - 1u) : 0u;      // genomes of earlier chunks
+    #pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint4* q = plane_ptr(rows, stride, b, grp, half);
+        uint4 v = make_uint4(w[4 * half + 0] << bit0, w[4 * half + 1] << bit0, w[4 * half + 2] << bit0,
+                             w[4 * half + 3] << bit0);
+        if (keep) {
+            const uint4 old = *q;
+            v.x |= old.x & keep;
+            v.y |= old.y & keep;
+            v.z |= old.z & keep;
+            v.w |= old.w & keep;
         }
+        *q = v;
     }
 }
 
@@ -793,10 +994,31 @@ void launch_resolve(unsigned long long* keys_anc, const uint32_t* planeF, const 
     if (!n_seq) return;
     (void)planeR;
     if (pair_words > PAIR_WORDS_MAX) pair_full = nullptr;
-    dim3 grid(((1u << p.h) + 256 * RES_U - 1) / (256 * RES_U), n_seq);
+    // up to 8 tiles per CTA, as long as the grid still fills the machine a few times over
+    const uint32_t n_tiles = ((1u << p.h) + 256 * RES_U - 1) / (256 * RES_U);
+    uint32_t per_cta = (uint32_t)(((uint64_t)n_tiles * n_seq) / (148u * 8u * 3u));
+    per_cta = per_cta < 1 ? 1 : per_cta > 8 ? 8 : per_cta;
+    dim3 grid((n_tiles + per_cta - 1) / per_cta, n_seq);
     resolve_kernel<<<grid, 256, 0, st>>>(keys_anc, planeF, woff, p, fp, active, ssum, bloom, owner, pair_full,
                                          pair_words, ks, claims, n_claims);
 }
+
+void launch_resolve_tagged(unsigned long long* keys_anc, const uint32_t* planeF, const uint64_t* woff,
+                           uint32_t n_seq, SketchParams p, uint8_t* fp, uint32_t* active, unsigned long long* ssum,
+                           const uint8_t* bloom, uint32_t* owner, const uint32_t* pair_full, uint32_t pair_words,
+                           int ks, uint32_t* list, uint32_t* n_list, cudaStream_t st) {
+    if (!n_seq) return;
+    const uint32_t n_tiles = (1u << p.h) >> 10;
+    uint32_t gx = (n_tiles + 1) / 2;                            // two tiles per CTA and loop trip
+    const uint32_t cap = std::max(1u, 148u * 8u * 4u / n_seq);
+    if (gx > cap) gx = cap;
+    resolve_fast_kernel<<<dim3(gx, n_seq), 256, 0, st>>>(keys_anc, p, fp, active, ssum, pair_full, pair_words, list,
+                                                        n_list);
+    const uint64_t most = ((uint64_t)n_seq << p.h) / (256 * RES_U) + 1;
+    resolve_slow_kernel<<<(unsigned)std::min<uint64_t>(most, 148 * 16), 256, 0, st>>>(keys_anc, planeF, woff, p, bloom,
+                                                                                   owner, list, n_list, ks);
+}
+bool resolve_tagged_ok(int h, uint32_t pair_words) { return h >= 10 && pair_words > 0 && pair_words <= PAIR_WORDS_MAX; }
 
 uint32_t bloom_page_count(uint64_t window) {
     return (uint32_t)((window + (1ull << BLOOM_PAGE_LOG2) - 1) >> BLOOM_PAGE_LOG2);
@@ -832,7 +1054,9 @@ void launch_bloom_commit(const unsigned long long* anc, const uint32_t* claims, 
 void launch_scatter_planes(const uint8_t* fp, uint32_t n_seq, int h, uint8_t* rows, uint64_t stride,
                            uint32_t col0, cudaStream_t st) {
     if (!n_seq) return;
-    scatter_planes_kernel<<<(unsigned)(((1ull << h) + 255) / 256), 256, 0, st>>>(fp, n_seq, h, rows, stride, col0);
+    const uint32_t groups = ((col0 + n_seq - 1) >> 5) - (col0 >> 5) + 1;
+    dim3 grid((unsigned)(((2ull << h) + 255) / 256), (groups + 1) / 2);
+    scatter_planes_kernel<<<grid, 256, 0, st>>>(fp, n_seq, h, rows, stride, col0);
 }
 
 void launch_planes_to_bytes(const uint8_t* rows, uint64_t stride, uint64_t row0, uint64_t nrows, uint32_t n,
