@@ -97,6 +97,8 @@ struct ScanPlan {
     uint32_t row_bytes; // pitch of a row inside a stage
     size_t smem;
     int grid;
+    int sm_count;
+    int narrow_gp;      // != 0: warp-per-read kernel for narrow shards, lanes per row
 };
 int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, ScanPlan* out);
 // counts[q * n_genomes + g] = #{entries e of read q : rows[bucket(e)][g] == fp(e)}

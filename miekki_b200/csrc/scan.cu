@@ -368,6 +368,113 @@ scan_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups
     }
 }
 
+// ---- narrow shards (<= 1,024 genomes): one warp per read, no shared-memory ring -----------------
+// A row of a narrow shard is a few hundred bytes: the ring kernel above then issues one bulk
+// copy per row and is bound by the copy issue rate (measured 34 SM cycles per row at N = 64,
+// 8.3 G rows/s on the whole GPU), not by bytes.  Here a warp owns a read; its lanes split into
+// S = 32 / GP row slots x GP groups (GP = groups per row rounded up to a power of two), so one
+// warp-wide 16-byte load fetches plane words of S different rows straight from L2 / HBM, four
+// rows per lane in flight.  Every lane keeps carry-save counters over its own rows; at the end
+// of the read the S partial counts of a group are summed with shuffles.
+template <int GP>
+__global__ void __launch_bounds__(256, 2)
+scan_narrow_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n_groups, uint32_t n_pad,
+                   const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
+                   const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t* __restrict__ counts,
+                   uint32_t* __restrict__ work_counter) {
+    constexpr int S = 32 / GP;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t g = lane & (GP - 1), rs = lane / GP;
+    const bool has_group = g < n_groups;
+    const uint8_t* base0 = rows + 16u * (has_group ? g : 0u);
+    const uint8_t* base1 = base0 + (stride >> 1);
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(work_counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= n_reads) break;
+        const uint32_t L = list_len[q];
+        const uint32_t* lst = list + list_off[q];
+        Counters cnt;
+        cnt.reset();
+        uint32_t nblk = 0;
+        bool flushed = false;
+        // counts of this lane's rows -> summed over the S row slots -> counts[q][32 g ..]
+        auto flush = [&]() {
+            uint32_t P[32];
+            cnt.planes(nblk, P);
+            transpose32(P);
+            #pragma unroll
+            for (int o = GP; o < 32; o <<= 1) {
+                #pragma unroll
+                for (int i = 0; i < 32; ++i) P[i] += __shfl_xor_sync(0xffffffffu, P[i], o);
+            }
+            if (rs == 0 && has_group) {
+                uint4* o = reinterpret_cast<uint4*>(counts + (uint64_t)q * n_pad + 32ull * g);
+                #pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    uint4 w = make_uint4(P[4 * v], P[4 * v + 1], P[4 * v + 2], P[4 * v + 3]);
+                    if (flushed) {
+                        const uint4 old = o[v];
+                        w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                    }
+                    o[v] = w;
+                }
+            }
+            flushed = true;
+            cnt.reset();
+            nblk = 0;
+        };
+        // entries of the next block are fetched while the rows of this one are in flight
+        uint32_t en[R];
+        #pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const uint32_t idx = (uint32_t)u * S + rs;
+            en[u] = idx < L ? __ldg(lst + idx) : 0xFFFFFFFFu;   // bucket < 2^24: never all ones
+        }
+        for (uint32_t e0 = 0; e0 < L; e0 += S * R) {
+            uint32_t e[R];
+            uint4 a[R], b[R];
+            #pragma unroll
+            for (int u = 0; u < R; ++u) {
+                e[u] = en[u];
+                a[u] = b[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (e[u] != 0xFFFFFFFFu) {
+                    const uint64_t roff = (uint64_t)(e[u] >> 8) * stride;
+                    a[u] = __ldg(reinterpret_cast<const uint4*>(base0 + roff));
+                    b[u] = __ldg(reinterpret_cast<const uint4*>(base1 + roff));
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const uint32_t idx = e0 + S * R + (uint32_t)u * S + rs;
+                en[u] = idx < L ? __ldg(lst + idx) : 0xFFFFFFFFu;
+            }
+            uint32_t x[R];
+            #pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const uint32_t fp = e[u] & 0xFFu;
+                uint32_t m[8];
+                #pragma unroll
+                for (int p = 0; p < 8; ++p) m[p] = ((fp >> p) & 1u) ? 0u : 0xFFFFFFFFu;
+                uint32_t t = a[u].x ^ m[0];
+                t = (a[u].y ^ m[1]) & t;
+                t = (a[u].z ^ m[2]) & t;
+                t = (a[u].w ^ m[3]) & t;
+                t = (b[u].x ^ m[4]) & t;
+                t = (b[u].y ^ m[5]) & t;
+                t = (b[u].z ^ m[6]) & t;
+                t = (b[u].w ^ m[7]) & t;
+                x[u] = e[u] != 0xFFFFFFFFu ? t : 0u;
+            }
+            cnt.add4(x[0], x[1], x[2], x[3], nblk);
+            ++nblk;
+            if (nblk == CHUNK_ROWS / R) flush();                // 16-plane counters are about to overflow
+        }
+        flush();
+    }
+}
+
 }  // namespace
 
 int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, ScanPlan* out) {
@@ -387,6 +494,16 @@ int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_opt
         if (waste < best_waste) { best_waste = waste; best_t = (int)t; best_j = j; }
     }
     if (!best_t) return -2;
+    // narrow shards take the warp-per-read kernel (scan_narrow_kernel)
+    // (MIEKKI_SCAN_NARROW_GROUPS=0 keeps the ring kernel; read per call so that tests can switch)
+    const char* narrow_env = getenv("MIEKKI_SCAN_NARROW_GROUPS");
+    const uint32_t narrow_max = (uint32_t)(narrow_env ? atoi(narrow_env) : 32);
+    out->narrow_gp = 0;
+    if (G <= narrow_max && G <= 32) {
+        int gp = 1;
+        while ((uint32_t)gp < G) gp <<= 1;
+        out->narrow_gp = gp;
+    }
     out->threads = best_t;
     out->J = best_j;
     out->tile_w = tg * 32;
@@ -428,6 +545,7 @@ int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_opt
     out->stages = stages;
     out->smem = (size_t)stages * per_stage + 128;
     out->grid = sm_count * ctas;
+    out->sm_count = sm_count;
     return 0;
 }
 
@@ -456,10 +574,33 @@ static int launch_scan_j(const ScanPlan& plan, const uint8_t* rows, uint64_t str
     return 0;
 }
 
+template <int GP>
+static int launch_narrow(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes,
+                         const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len,
+                         uint32_t n_reads, uint32_t* counts, uint32_t* work_counter, cudaStream_t st) {
+    const uint32_t n_groups = (n_genomes + 31) / 32;
+    const uint64_t warps = n_reads;                             // one read per warp and trip
+    uint64_t grid = (warps + 7) / 8;
+    const uint64_t cap = (uint64_t)(plan.grid > 0 ? plan.sm_count : 148) * 2;
+    if (grid > cap) grid = cap;
+    scan_narrow_kernel<GP><<<(unsigned)grid, 256, 0, st>>>(rows, stride, n_groups, n_groups * 32, list, list_off,
+                                                           list_len, n_reads, counts, work_counter);
+    return 0;
+}
+
 int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes,
                 const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len,
                 uint32_t n_reads, uint32_t* counts, uint32_t* work_counter, cudaStream_t st) {
     if (!n_reads) return 0;
+    switch (plan.narrow_gp) {
+        case 1: return launch_narrow<1>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
+        case 2: return launch_narrow<2>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
+        case 4: return launch_narrow<4>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
+        case 8: return launch_narrow<8>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
+        case 16: return launch_narrow<16>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
+        case 32: return launch_narrow<32>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
+        default: break;
+    }
     switch (plan.J) {
         case 1: return launch_scan_j<1>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);
         case 2: return launch_scan_j<2>(plan, rows, stride, n_genomes, list, list_off, list_len, n_reads, counts, work_counter, st);

@@ -362,7 +362,13 @@ def test_case_c_saturated_sketch_all_ties(mk):
 
 # ---- seeded random parity at sizes the oracle finishes in seconds ---------------------------
 
-def test_random_index_and_long_reads_vs_oracle(mk):
+@pytest.mark.parametrize("narrow", ["32", "0"])
+def test_random_index_and_long_reads_vs_oracle(mk, monkeypatch, narrow):
+    monkeypatch.setenv("MIEKKI_SCAN_NARROW_GROUPS", narrow)
+    _random_index_and_long_reads(mk)
+
+
+def _random_index_and_long_reads(mk):
     """40 genomes (more than one dense chunk), reads of 60 bp .. 40 kbp: the long ones take the
     dense read path, the short ones the shared-memory path."""
     rng = np.random.default_rng(11)
@@ -405,9 +411,13 @@ def test_random_index_and_long_reads_vs_oracle(mk):
     ix.close()
 
 
-def test_whole_genome_query_crosses_counter_chunks(mk):
+@pytest.mark.parametrize("narrow", ["32", "0"])
+def test_whole_genome_query_crosses_counter_chunks(mk, monkeypatch, narrow):
     """A query with more than 65,504 surviving buckets (a 1.2 Mbp sequence at -h 17) makes the scan
-    spill its 16-plane carry-save counters and accumulate across chunks (F_ACCUM path)."""
+    spill its 16-plane carry-save counters and accumulate across chunks (F_ACCUM path).  narrow=0
+    keeps the shared-memory ring kernel on this 6-genome shard, the default is the warp-per-read
+    kernel (whose own spill needs > 65,504 rows per lane: next test)."""
+    monkeypatch.setenv("MIEKKI_SCAN_NARROW_GROUPS", narrow)
     rng = np.random.default_rng(21)
     k, h = 31, 17
     base = np.frombuffer(rand_seq(rng, 1_200_000), np.uint8)
@@ -434,6 +444,30 @@ def test_whole_genome_query_crosses_counter_chunks(mk):
     for i, s in enumerate(q):
         oh = o.query(s, 10, 10, 0.0)
         assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+    ix.close()
+
+
+@pytest.mark.parametrize("n_genomes", [600, 40])
+def test_narrow_scan_spills_counters(mk, n_genomes):
+    """scan_narrow_kernel: 600 genomes = 19 groups -> 32 lanes per row, one row slot, so a query
+    with more than 65,504 surviving buckets overflows the lane's 16-plane counters and takes the
+    flush-and-accumulate path; 40 genomes (2 lanes per row, 16 row slots) do not, same answers."""
+    rng = np.random.default_rng(33)
+    k, h = 31, 17
+    big = rand_seq(rng, 900_000)
+    genomes = [big] + [rand_seq(rng, 3_000) for _ in range(n_genomes - 2)] + [big[:400_000] + rand_seq(rng, 1000)]
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.insert_sequences(genomes)
+    o = orc.Oracle(k=k, h=h, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    q = [big, genomes[-1], genomes[5], big[100_000:100_500]]
+    counts, surv = ix.query_counts(q)
+    assert surv[0] > 65_504
+    for i, s in enumerate(q):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa
+        assert np.array_equal(counts[i], oc), i
     ix.close()
 
 
