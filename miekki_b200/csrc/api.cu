@@ -84,6 +84,7 @@ struct mk_ctx {
     uint8_t* bloom = nullptr;
     uint32_t* owner = nullptr;
     uint64_t window = 0;          // bytes, multiple of 16
+    uint64_t bloom_reach = 0;     // bytes [bloom_reach, window) can never be probed (see mk_create)
 
     DevBuf planeF, planeR, keys, fp, meta, list, list_len, list2, list_len2, counts, counts2, heap, heap_len, heap2,
         heap_len2, misc, pages;
@@ -469,7 +470,7 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
         TRY(reserve(c, c->pages, off + ((size_t)n_pages + 31) / 32 * 4));
         auto* full8 = static_cast<uint8_t*>(c->pages.p);
         auto* pf = reinterpret_cast<uint32_t*>(full8 + off);
-        pair_words = launch_bloom_pages(c->bloom, c->window, full8, pf, c->stream);
+        pair_words = launch_bloom_pages(c->bloom, c->window, c->bloom_reach, full8, pf, c->stream);
         pair_full = pf;
         c->stats.kernel_launches += 2;
     }
@@ -558,6 +559,13 @@ int index_add_view(mk_ctx* c, const mk_batch* b) {
                                 c->bloom, c->owner, c->stream);
             launch_scatter_planes(static_cast<uint8_t*>(c->fp.p), n, (int)c->h, c->rows, c->stride, c->n, c->stream);
             c->stats.kernel_launches += 2;
+        }
+        if (getenv("MIEKKI_TRACE_BUILD")) {      // debugging aid (synchronises): buckets that took the look-up path
+            uint32_t slow = 0;
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaMemcpy(&slow, d.d_n_claims, 4, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[trace] chunk of %u genomes at id %u: %u of %llu buckets looked up for the Bloom table\n", n,
+                    c->n, slow, (unsigned long long)n * c->B);
         }
         // sketch_size / genome_size / ratio of the new ids, on the device (no host round trip)
         launch_stats_finalize(d.d_active, d.d_ssum, v.d_len, n, c->d_sketch_size + c->n, c->d_genome_size + c->n,
@@ -1044,6 +1052,14 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     uint64_t window = ((top >> bloom_log2) >> 3) + 1;
     window = std::min<uint64_t>(window, (1ull << bloom_log2) / 8);
     ctx->window = (window + 15) / 16 * 16;
+    // A canonical k-mer min(S, RC) is < M = 4^k - 4^(ceil(k/2)-1): a digit 3 of S comes from a
+    // 'T', whose reverse-strand digit is 0, so S >= 4^k - 4^j forces RC <= 4^k - 4^(k-j), and both
+    // can hold only for j >= k/2.  Table bytes past ((M - 1 + 1023) >> (b + 3)) are therefore
+    // never probed; the build's "page is saturated" test ignores them.
+    {
+        const uint64_t M = (1ull << (2 * k)) - (1ull << (2 * ((k + 1) / 2 - 1)));
+        ctx->bloom_reach = std::min<uint64_t>(ctx->window, (((M - 1 + 1023) >> bloom_log2) >> 3) + 1);
+    }
     {   // keep freed per-call buffers in the stream-ordered pool instead of returning them
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -46,8 +46,9 @@ void launch_resolve_tagged(unsigned long long* keys_anc, const uint32_t* planeF,
                            int ks, uint32_t* list, uint32_t* n_list, cudaStream_t st);
 // Bloom pages without a zero byte -> full8[n_pages], pair_full[ceil(n_pages / 32)]
 uint32_t bloom_page_count(uint64_t window);
-uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint8_t* full8, uint32_t* pair_full,
-                            cudaStream_t st);
+// reach: bytes [reach, window) can never be probed and do not count
+uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint64_t reach, uint8_t* full8,
+                            uint32_t* pair_full, cudaStream_t st);
 // Miekki.cpp:303-311: sketch_size, genome_size and the top-k screen ratio of n new genomes
 void launch_stats_finalize(const uint32_t* active, const unsigned long long* ssum, const uint64_t* len,
                            uint32_t n, uint32_t* sketch_size, uint64_t* genome_size, float* ratio,

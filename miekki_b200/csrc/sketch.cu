@@ -543,28 +543,30 @@ resolve_slow_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* _
 
 // Which 4 KB pages of the Bloom table hold no zero byte?  One warp per page -> full8[page];
 // then pair bit j = full8[j] && full8[j + 1] (a k-mer's probes may cross into the next page).
+// Only bytes below `reach` can ever be probed (api.cu: bloom_reach), so bytes from there on do
+// not count, and a page that starts at or past `reach` is vacuously full.
 __global__ void __launch_bounds__(256)
-bloom_pages_kernel(const uint8_t* __restrict__ bloom, uint64_t window, uint32_t n_pages,
+bloom_pages_kernel(const uint8_t* __restrict__ bloom, uint64_t reach, uint32_t n_pages,
                    uint8_t* __restrict__ full8) {
     const uint32_t page = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (page >= n_pages) return;
     const uint64_t base = (uint64_t)page << BLOOM_PAGE_LOG2;
-    bool ok = base + (1ull << BLOOM_PAGE_LOG2) <= window;    // a partial last page is never "full"
-    if (ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(bloom + base);
-        uint32_t zero = 0;
-        #pragma unroll
-        for (int i = 0; i < (1 << BLOOM_PAGE_LOG2) / 16 / 32; ++i) {
-            const uint4 v = src[i * 32 + lane];
+    uint32_t zero = 0;
+    #pragma unroll
+    for (int i = 0; i < (1 << BLOOM_PAGE_LOG2) / 16 / 32; ++i) {
+        const uint64_t off = base + 16ull * (i * 32 + lane);
+        if (off + 16 <= reach) {
+            const uint4 v = *reinterpret_cast<const uint4*>(bloom + off);
             zero |= (v.x - 0x01010101u) & ~v.x;
             zero |= (v.y - 0x01010101u) & ~v.y;
             zero |= (v.z - 0x01010101u) & ~v.z;
             zero |= (v.w - 0x01010101u) & ~v.w;
+        } else {
+            for (uint64_t o = off; o < reach; ++o) zero |= bloom[o] == 0 ? 0x80u : 0u;
         }
-        ok = (zero & 0x80808080u) == 0;
     }
-    ok = __all_sync(0xffffffffu, ok);
+    const bool ok = __all_sync(0xffffffffu, (zero & 0x80808080u) == 0);
     if (lane == 0) full8[page] = ok ? 1 : 0;
 }
 __global__ void __launch_bounds__(256)
@@ -575,7 +577,8 @@ bloom_pairs_kernel(const uint8_t* __restrict__ full8, uint32_t n_pages, uint32_t
     uint32_t bits = 0;
     for (uint32_t j = 0; j < 32; ++j) {
         const uint32_t pg = 32 * w + j;
-        if (pg + 1 < n_pages && full8[pg] && full8[pg + 1]) bits |= 1u << j;
+        // no page after the last one: nothing there can be probed
+        if (pg < n_pages && full8[pg] && (pg + 1 >= n_pages || full8[pg + 1])) bits |= 1u << j;
     }
     pair_full[w] = bits;
 }
@@ -1025,12 +1028,13 @@ uint32_t bloom_page_count(uint64_t window) {
 }
 
 // scratch: n_pages bytes (full8) followed, 4-byte aligned, by pair words; returns the word count
-uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint8_t* full8, uint32_t* pair_full,
-                            cudaStream_t st) {
+uint32_t launch_bloom_pages(const uint8_t* bloom, uint64_t window, uint64_t reach, uint8_t* full8,
+                            uint32_t* pair_full, cudaStream_t st) {
     const uint32_t n_pages = bloom_page_count(window);
     const uint32_t n_words = (n_pages + 31) / 32;
     if (!n_pages) return 0;
-    bloom_pages_kernel<<<(n_pages * 32 + 255) / 256, 256, 0, st>>>(bloom, window, n_pages, full8);
+    if (reach > window) reach = window;
+    bloom_pages_kernel<<<(n_pages * 32 + 255) / 256, 256, 0, st>>>(bloom, reach, n_pages, full8);
     bloom_pairs_kernel<<<(n_words + 255) / 256, 256, 0, st>>>(full8, n_pages, n_words, pair_full);
     return n_words;
 }

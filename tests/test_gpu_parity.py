@@ -650,6 +650,31 @@ def test_build_with_saturated_bloom_pages(mk):
     ix.close()
 
 
+def test_build_with_tiny_saturated_bloom_window(mk):
+    """-k 21 -b 33 (a BASELINE sweep point) probes only 64 table bytes: they are all set after the
+    first genomes, the padding behind them never is, and the build must still recognise the page
+    as saturated (bytes no k-mer can reach do not count) without changing any result."""
+    k, h, b = 21, 12, 33
+    rng = np.random.default_rng(9)
+    genomes = [rand_seq(rng, 50_000, special=(g % 3 == 0)) for g in range(12)]
+    ix = mk.Miekki(k=k, h=h, b=b, threshold=0)
+    o = orc.Oracle(k=k, h=h, b=b, cap=len(genomes))
+    for first in range(0, len(genomes), 4):
+        ix.insert_sequences(genomes[first:first + 4])
+        for s in genomes[first:first + 4]:
+            o.insert(s)
+        e = ix.export()
+        m = min(len(e["bloom"]), len(o.bloom))
+        assert np.array_equal(e["bloom"][:m], o.bloom[:m]), first
+        assert (e["bloom"][:64] != 0).all() and not e["bloom"][64:m].any()
+    assert np.array_equal(e["rows"], o.rows)
+    assert np.array_equal(e["sketch_size"], o.sketch_size) and np.array_equal(e["genome_size"], o.genome_size)
+    counts, surv = ix.query_counts([genomes[3][100:3000]])
+    oc, oa = o.counts(genomes[3][100:3000])
+    assert surv[0] == oa and np.array_equal(counts[0], oc)
+    ix.close()
+
+
 def test_errors(mk):
     with pytest.raises(mk.MiekkiError):
         mk.Miekki(k=32)
