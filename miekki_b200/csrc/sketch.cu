@@ -382,8 +382,8 @@ resolve_fast_kernel(const unsigned long long* __restrict__ keys, SketchParams p,
     const uint32_t s = blockIdx.y;
     const uint32_t B = 1u << p.h;                               // multiple of 1024 (host: h >= 10)
     const uint64_t row = (uint64_t)s << p.h;
-    const int tag_shift = key_tag_shift(p.k);
-    const int page_shift = (int)p.bloom_log2 + 3 + BLOOM_PAGE_LOG2;
+    // page_shift (>= 47) always exceeds tag_shift (<= 38)
+    const int tag_to_page = (int)p.bloom_log2 + 3 + BLOOM_PAGE_LOG2 - key_tag_shift(p.k);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = B >> 10;
     uint32_t act = 0;
@@ -408,17 +408,23 @@ resolve_fast_kernel(const unsigned long long* __restrict__ keys, SketchParams p,
             const uint32_t b4 = ((tile0 + t) << 10) + 4 * threadIdx.x;
             const unsigned long long key[4] = {k01[t].x, k01[t].y, k23[t].x, k23[t].y};
             uint32_t packed = 0, slow_bits = 0;
+            uint32_t part = 0;                                  // <= 4 * 2^31 overflows 32 bits: folded below
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t fp = (uint32_t)(key[u] >> POS_BITS);
                 packed |= fp << (8 * u);
                 if (fp != EMPTY_FP) {
                     act += 1;
-                    sum += 1ull << (31 - (fp >> 3));            // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
-                    const uint32_t page = (uint32_t)(((key[u] & KEY_TAG_MASK) << tag_shift) >> page_shift);
+                    const uint32_t term = 1u << (31 - (fp >> 3));  // 2^-(fp>>3) in units of 2^-31 (Miekki.cpp:293)
+                    sum += part + term < part ? (1ull << 32) : 0ull;
+                    part += term;
+                    // page of the k-mer range the tag stands for: (tag << tag_shift) >> page_shift
+                    const uint32_t tag = (uint32_t)key[u] & (uint32_t)KEY_TAG_MASK;
+                    const uint32_t page = tag_to_page < 32 ? tag >> tag_to_page : 0u;
                     if (!((s_pair[page >> 5] >> (page & 31)) & 1u)) slow_bits |= 1u << u;
                 }
             }
+            sum += part;
             *reinterpret_cast<uint32_t*>(fp_out + row + b4) = packed;
             if (!__syncthreads_or((int)slow_bits)) continue;
             const uint32_t mine = __popc(slow_bits);
