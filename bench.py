@@ -261,7 +261,9 @@ def main():
 
     # ---- setup (untimed): the index, like weights, is state ------------------------------
     ix = miekki_b200.Miekki(k=a.k, h=a.hbits, b=33, threshold=a.threshold, device=local)
-    stream = torch.cuda.current_stream()
+    # a high-priority stream: the scan outranks the top-k / NCCL kernels that run beside it
+    stream = torch.cuda.Stream(priority=-1)
+    torch.cuda.set_stream(stream)
     ix.set_stream(stream.cuda_stream)
     ix.reserve(a.genomes)
     first = rank * a.genomes if a.impl == "ours" else 0

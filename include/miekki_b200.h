@@ -70,6 +70,11 @@ int mk_set_stream(mk_ctx *ctx, void *cuda_stream);
  * [first_id, first_id + mk_index_size).  Hits carry global ids. */
 int mk_set_shard(mk_ctx *ctx, uint32_t first_id);
 
+/* The scan is a persistent kernel that fills every SM.  A sharded run passes the heap from GPU
+ * to GPU (NCCL send/recv) while the next batch is being scanned: leave n SMs out of the scan's
+ * grid so that those kernels are scheduled at once instead of after the scan (default 0). */
+int mk_set_scan_spare_sms(mk_ctx *ctx, int n);
+
 /* parameters as stored in a dump header (Miekki.cpp:651-661) */
 int mk_get_params(const mk_ctx *ctx, uint32_t *k, uint32_t *h, uint32_t *bits_per_min,
                   uint32_t *bits_mantis, uint32_t *bloom_log2, uint32_t *threshold);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mk_destroy": (None, [_vp]),
     "mk_last_error": (C.c_char_p, [_vp]),
     "mk_set_stream": (_i, [_vp, _vp]),
+    "mk_set_scan_spare_sms": (_i, [_vp, _i]),
     "mk_set_shard": (_i, [_vp, _u32]),
     "mk_get_params": (_i, [_vp] + [C.POINTER(_u32)] * 6),
     "mk_batch_upload": (_i, [_vp, _vp, _vp, _u32, _pp]),
@@ -181,6 +182,9 @@ class Miekki:
     # ---- plumbing ------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None):
         self._ck(lib().mk_set_stream(self._ctx, cuda_stream))
+
+    def set_scan_spare_sms(self, n: int):
+        self._ck(lib().mk_set_scan_spare_sms(self._ctx, n))
 
     def set_shard(self, first_id: int):
         self._ck(lib().mk_set_shard(self._ctx, first_id))

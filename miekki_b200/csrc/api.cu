@@ -60,6 +60,7 @@ struct mk_ctx {
     bool key_tags = true;         // MIEKKI_KEY_TAGS=0 forces the plain key format (used for >= 2^32-base sequences)
     uint64_t B;
     int device = 0, sm_count = 148;
+    int scan_spare_sms = 0;       // SMs the persistent scan leaves to concurrent kernels (mk_set_scan_spare_sms)
     size_t smem_optin = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t aux_stream = nullptr;     // top-k of one count tile overlaps the scan of the next
@@ -770,7 +771,7 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     uint64_t LIST_BUDGET = 768ull << 20;                       // entries (3 GiB)
     if (const char* e = getenv("MIEKKI_LIST_BUDGET_ENTRIES")) LIST_BUDGET = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
     ScanPlan plan{};
-    if (c->n > 0 && scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
+    if (c->n > 0 && scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, c->scan_spare_sms, &plan) != 0)
         return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
     const uint64_t n_pad = (c->n + 31) / 32 * 32;
     cudaEvent_t scanned[2] = {get_event(c), get_event(c)}, done[2] = {get_event(c), get_event(c)};
@@ -924,8 +925,9 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
     } else {
         if (!c->sk_ev) CU(cudaEventCreateWithFlags(&c->sk_ev, cudaEventDisableTiming));
         if (c->slot_used[slot]) CU(cudaStreamWaitEvent(c->sk_stream, c->slot_ev[slot], 0));   // last scan of this slot
-        CU(cudaEventRecord(c->sk_ev, c->stream));                  // uploads etc. issued on the main stream
-        CU(cudaStreamWaitEvent(c->sk_stream, c->sk_ev, 0));
+        // No wait on the main stream: it may hold the previous batch's scan, beside which this
+        // sketch is meant to run.  The reads themselves are complete: every call that creates a
+        // batch returns only after its copies have finished.
         c->bl_stream = c->sk_stream;
         c->bl_set = slot;
         int r = build_lists(c, b, 0, n, &L);
@@ -939,7 +941,7 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
     DevBuf& tile = slot ? c->counts2 : c->counts;
     if (c->n > 0) {
         ScanPlan plan{};
-        if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
+        if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, c->scan_spare_sms, &plan) != 0)
             return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
         TRY(reserve(c, tile, (size_t)n * n_pad * 4));
         TRY(scan_reads(c, L, 0, n, plan, static_cast<uint32_t*>(tile.p)));
@@ -1068,7 +1070,12 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
         }
         cudaGetLastError();
     }
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    // The scan's stream outranks the helper streams: when a scan and the top-k of the previous
+    // tile become runnable together, the persistent scan CTAs are placed first and the top-k
+    // fills what is left of each SM instead of delaying the scan by its whole duration.
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    cudaError_t e = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->sk_stream, cudaStreamNonBlocking);
@@ -1130,6 +1137,14 @@ int mk_set_stream(mk_ctx* c, void* cuda_stream) {
     return MK_OK;
 }
 
+int mk_set_scan_spare_sms(mk_ctx* c, int n) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    if (n < 0 || n >= c->sm_count) return fail(c, MK_ERR_ARG, "mk_set_scan_spare_sms: out of range");
+    c->scan_spare_sms = n;
+    return MK_OK;
+}
+
 int mk_set_shard(mk_ctx* c, uint32_t first_id) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
@@ -1165,7 +1180,9 @@ int mk_batch_upload_flat(mk_ctx* c, const char* data, const uint64_t* offsets, c
     Guard g(c);
     mk_batch* b = new mk_batch();
     batch_layout(b, lens, n);
-    int r = batch_alloc(c, b);
+    // on the copy stream: the upload must not queue behind a scan running on the main stream
+    cudaStream_t st = c->copy_stream;
+    int r = batch_alloc(c, b, st);
     if (r != MK_OK) { batch_release(b); return r; }
     cudaError_t e = cudaSuccess;
     uint64_t span = 0;
@@ -1177,19 +1194,20 @@ int mk_batch_upload_flat(mk_ctx* c, const char* data, const uint64_t* offsets, c
     if (same) {
         // the caller's layout already is ours (every start 16-byte aligned, packed): one copy.
         // Gap bytes come from the caller's buffer; kernels never interpret bytes past a length.
-        e = cudaMemsetAsync(b->chars + span, 0, b->bytes - span, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(b->chars, data, span, cudaMemcpyHostToDevice, c->stream);
+        e = cudaMemsetAsync(b->chars + span, 0, b->bytes - span, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->chars, data, span, cudaMemcpyHostToDevice, st);
     } else {
-        e = cudaMemsetAsync(b->chars, 0, b->bytes, c->stream);
+        e = cudaMemsetAsync(b->chars, 0, b->bytes, st);
         for (uint32_t i = 0; i < n && e == cudaSuccess; ++i)
             if (lens[i])
                 e = cudaMemcpyAsync(b->chars + b->h_coff[i], data + offsets[i], lens[i], cudaMemcpyHostToDevice,
-                                    c->stream);
+                                    st);
     }
     if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     c->stats.h2d_bytes += b->bases;
     *out = b;
-    return sync(c);
+    CU(cudaStreamSynchronize(st));
+    return MK_OK;
 }
 
 int mk_batch_synth(mk_ctx* c, uint64_t seed, uint32_t first_g, uint32_t n, uint64_t len, mk_batch** out) {
@@ -1222,7 +1240,23 @@ void mk_batch_free(mk_ctx* c, mk_batch* b) {
     if (!b) return;
     if (c) {
         Guard g(c);
-        cudaStreamSynchronize(c->stream);
+        // The memory goes back to the pool in stream order, after everything enqueued so far that
+        // may read it (scan lists on the main stream, the read sketch on its own stream): the
+        // host does not wait for a running scan.
+        bool ordered = b->stream != nullptr;
+        for (cudaStream_t user : {c->stream, c->sk_stream}) {
+            if (!ordered || user == b->stream || !user) continue;
+            cudaEvent_t ev = nullptr;
+            ordered = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventRecord(ev, user) == cudaSuccess &&
+                      cudaStreamWaitEvent(b->stream, ev, 0) == cudaSuccess;
+            if (ev) cudaEventDestroy(ev);       // released once the recorded work has completed
+        }
+        if (!ordered) {
+            cudaGetLastError();
+            cudaStreamSynchronize(c->stream);
+            cudaStreamSynchronize(c->sk_stream);
+        }
         batch_release(b);
     } else {
         batch_release(b);
@@ -1534,7 +1568,7 @@ int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, ui
         TRY(build_lists(c, b, 0, n, &L));
         if (c->n) {
             ScanPlan plan{};
-            if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, &plan) != 0)
+            if (scan_plan(c->n, c->stride, c->sm_count, c->smem_optin, c->scan_spare_sms, &plan) != 0)
                 return fail(c, MK_ERR_CUDA, "no scan plan for this index width");
             const uint32_t qb = scan_batch_reads(c, n);
             const uint64_t n_pad = (c->n + 31) / 32 * 32;

@@ -101,7 +101,7 @@ struct ScanPlan {
     int sm_count;
     int narrow_gp;      // != 0: warp-per-read kernel for narrow shards, lanes per row
 };
-int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, ScanPlan* out);
+int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, int spare_sms, ScanPlan* out);
 // counts[q * n_genomes + g] = #{entries e of read q : rows[bucket(e)][g] == fp(e)}
 int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes,
                 const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len,

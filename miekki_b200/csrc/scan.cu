@@ -477,7 +477,7 @@ scan_narrow_kernel(const uint8_t* __restrict__ rows, uint64_t stride, uint32_t n
 
 }  // namespace
 
-int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, ScanPlan* out) {
+int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_optin, int spare_sms, ScanPlan* out) {
     if (n_genomes == 0) return -1;
     const uint32_t MAXG = 512;                     // widest tile: 512 groups = 16,384 genomes
     const uint32_t G = (n_genomes + 31) / 32;      // 32-genome groups per row
@@ -544,7 +544,12 @@ int scan_plan(uint32_t n_genomes, uint64_t stride, int sm_count, size_t smem_opt
     if (stages < 2) return -3;
     out->stages = stages;
     out->smem = (size_t)stages * per_stage + 128;
-    out->grid = sm_count * ctas;
+    // The persistent grid fills every SM's shared memory.  A sharded run needs a few SMs for the
+    // kernels that must make progress beside it (NCCL send/recv of the heap chain): they are
+    // left out of the grid (mk_set_scan_spare_sms; MIEKKI_SCAN_SPARE_SMS overrides).
+    if (const char* e = getenv("MIEKKI_SCAN_SPARE_SMS")) spare_sms = atoi(e);
+    const int use_sms = std::max(1, sm_count - std::max(0, spare_sms));
+    out->grid = use_sms * ctas;
     out->sm_count = sm_count;
     return 0;
 }
