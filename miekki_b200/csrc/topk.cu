@@ -3,9 +3,9 @@
 // The hit list of a read is order dependent: genomes are visited in ascending id, the heap
 // is libstdc++'s (push_heap / pop_heap / sort_heap, bits/stl_heap.h), a candidate replaces
 // the minimum when "front > x" is false, so ties are kept or dropped by heap position
-// (quirk G5).  One warp per read reproduces this exactly: 32 genomes are scored per step,
-// a ballot finds the ones that may enter the heap, and lane 0 replays those in id order
-// with the same sift operations.  A candidate the sequential code would skip never changes
+// (quirk G5).  One warp per read reproduces this exactly: 128 genomes are scored per step
+// (four consecutive ids per lane), a ballot finds the lanes holding ids that may enter the
+// heap, and lane 0 replays those in id order with the same sift operations.  A candidate the sequential code would skip never changes
 // the heap, so skipping it early (with a possibly stale minimum, which can only be lower)
 // is exact.
 //
@@ -74,14 +74,25 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
     double hmin = len ? hp[0].intersection : 0.0;
     const uint32_t* cq = counts + (uint64_t)q * n_pad;
 
-    for (uint32_t g0 = 0; g0 < n_genomes; g0 += 32) {
-        const uint32_t g = g0 + lane;
-        bool cand = false;
-        uint32_t sc = 0;
-        double jac = 0.0, x = 0.0;
-        if (g < n_genomes) {
-            sc = cq[g];
-            if (sc >= min_score) {                                     // :381
+    // 128 genomes per step: every lane scores four consecutive ids from one 16-byte load, and
+    // the next step's load is issued before this step is evaluated (one 4-byte load per lane and
+    // step left the kernel latency bound: 1 TB/s over the count tile).
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    auto load4 = [&](uint32_t g0) {
+        const uint32_t base = g0 + 4u * lane;                          // n_pad is a multiple of 32
+        return base < n_pad ? *reinterpret_cast<const uint4*>(cq + base) : zero4;
+    };
+    uint4 cur = load4(0);
+    for (uint32_t g0 = 0; g0 < n_genomes; g0 += 128) {
+        const uint4 nxt = g0 + 128 < n_genomes ? load4(g0 + 128) : zero4;
+        const uint32_t base = g0 + 4u * lane;
+        const uint32_t scv[4] = {cur.x, cur.y, cur.z, cur.w};
+        double jac[4] = {0.0, 0.0, 0.0, 0.0}, x[4] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t mine = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t g = base + j, sc = scv[j];
+            if (g < n_genomes && sc >= min_score) {                    // :381
                 // Cheap exact-safe screen: ratio[g] = float(genome_size / sketch_size), so
                 // sc * ratio is within 3 * 2^-24 of the f64 value below.  A candidate whose
                 // upper bound is still under the heap minimum would be skipped at :387 and
@@ -89,39 +100,44 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
                 // (NaN / inf ratios fail the test and take the exact path).
                 const double ub = (double)((float)sc * ratio[g]) * 1.000001;
                 if (!(len >= K && ub < hmin)) {
-                    jac = (double)sc / (double)sketch_size[g];         // :382
-                    x = jac * (double)genome_size[g];                  // :383
-                    cand = !(x < min_intersection);                    // :384
+                    jac[j] = (double)sc / (double)sketch_size[g];      // :382
+                    x[j] = jac[j] * (double)genome_size[g];            // :383
+                    // :384, and :386-387 with the heap as it stood at the start of this step
+                    if (!(x[j] < min_intersection) && (len < K || !(hmin > x[j]))) mine |= 1u << j;
                 }
             }
         }
-        // :386-387 with the heap as it stood at the start of this step
-        const bool maybe = cand && (len < K || !(hmin > x));
-        uint32_t m = __ballot_sync(0xffffffffu, maybe);
-        while (m) {
+        uint32_t m = __ballot_sync(0xffffffffu, mine != 0);
+        while (m) {                                                    // lanes, then ids within a lane: ascending id
             const int src = __ffs((int)m) - 1;
             m &= m - 1;
-            const uint32_t g_s = __shfl_sync(0xffffffffu, g, src);
-            const uint32_t sc_s = __shfl_sync(0xffffffffu, sc, src);
-            const double j_s = __shfl_sync(0xffffffffu, jac, src);
-            const double x_s = __shfl_sync(0xffffffffu, x, src);
-            if (lane == 0) {
-                bool skip = false;
-                if (len >= K) {                                        // :386
-                    if (hp[0].intersection > x_s) skip = true;         // :387
-                    else { pop(hp, (int)len); --len; }                 // :388-389
+            const uint32_t cm = __shfl_sync(0xffffffffu, mine, src);
+            const uint32_t base_s = __shfl_sync(0xffffffffu, base, src);
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!((cm >> j) & 1u)) continue;                       // uniform over the warp
+                const uint32_t sc_s = __shfl_sync(0xffffffffu, scv[j], src);
+                const double j_s = __shfl_sync(0xffffffffu, jac[j], src);
+                const double x_s = __shfl_sync(0xffffffffu, x[j], src);
+                if (lane == 0) {
+                    bool skip = false;
+                    if (len >= K) {                                    // :386
+                        if (hp[0].intersection > x_s) skip = true;     // :387
+                        else { pop(hp, (int)len); --len; }             // :388-389
+                    }
+                    if (!skip) {
+                        const HitDev v{first_id + base_s + (uint32_t)j, sc_s, j_s, x_s};   // :392
+                        hp[len] = v;
+                        ++len;
+                        sift_up(hp, (int)len - 1, 0, v);               // :393
+                    }
+                    hmin = hp[0].intersection;
                 }
-                if (!skip) {
-                    const HitDev v{first_id + g_s, sc_s, j_s, x_s};    // :392
-                    hp[len] = v;
-                    ++len;
-                    sift_up(hp, (int)len - 1, 0, v);                   // :393
-                }
-                hmin = hp[0].intersection;
+                len = __shfl_sync(0xffffffffu, len, 0);
+                hmin = __shfl_sync(0xffffffffu, hmin, 0);
             }
-            len = __shfl_sync(0xffffffffu, len, 0);
-            hmin = __shfl_sync(0xffffffffu, hmin, 0);
         }
+        cur = nxt;
     }
     if (lane == 0 && finalize)                                         // :396 sort_heap
         for (int n = (int)len; n > 1; --n) pop(hp, n);
