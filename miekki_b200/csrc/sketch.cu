@@ -177,14 +177,6 @@ sketch_dense_kernel(const uint32_t* __restrict__ planeF, const uint32_t* __restr
     }
 }
 
-// hash of the k-mer starting at `pos`, from the planes in global memory
-__device__ __forceinline__ uint64_t hash_at(const uint2* __restrict__ P, uint64_t pos, int k) {
-    const uint64_t w = pos >> 4;
-    const int j = (int)(pos & 15);
-    const uint2 a = P[w], b = P[w + 1], c = P[w + 2];
-    return kmer_hash(a.x, b.x, c.x, a.y, b.y, c.y, j, k, (1ull << (2 * k)) - 1);
-}
-
 // key = (seq_in_batch, bucket, probe) packed so that u32 order == lexicographic order
 __device__ __forceinline__ uint32_t owner_key(uint32_t s, uint32_t bucket, uint32_t i, int h) {
     return (((s << h) | bucket) << 3) | i;
