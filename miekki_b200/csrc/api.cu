@@ -101,7 +101,6 @@ struct mk_ctx {
     void* meta_pin[2] = {nullptr, nullptr};
     size_t meta_pin_cap[2] = {0, 0};
     int meta_flip = 0;
-    cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned upload ring
     cudaStream_t copy_stream = nullptr;                              // uploads that overlap compute
     std::atomic<uint64_t> h2d_meta{0};                               // bytes counted off the main thread
     cudaEvent_t meta_ev[2] = {nullptr, nullptr};
@@ -315,29 +314,6 @@ void batch_release(mk_batch* b) {
     delete b;
 }
 
-// memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 takes ~50)
-void parallel_memcpy(char* dst, const char* src, size_t n) {
-    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    static const unsigned cap = [] {
-        const char* e = getenv("MIEKKI_UPLOAD_THREADS");
-        return e ? (unsigned)std::max(1, atoi(e)) : std::min(8u, std::max(1u, hw / 2));
-    }();
-    const unsigned nt = (unsigned)std::min<size_t>(cap, n / (2u << 20));
-    if (nt <= 1) {
-        memcpy(dst, src, n);
-        return;
-    }
-    std::vector<std::thread> th;
-    const size_t per = (n / nt + 63) & ~(size_t)63;
-    for (unsigned t = 1; t < nt; ++t) {
-        const size_t o = (size_t)t * per;
-        if (o >= n) break;
-        th.emplace_back([=] { memcpy(dst + o, src + o, std::min(per, n - o)); });
-    }
-    memcpy(dst, src, std::min(per, n));
-    for (auto& x : th) x.join();
-}
-
 // gathers sequences [first, first+n) of (seqs, lens) into a new device batch
 // `st`: stream to copy on (default: the ctx stream).  With an explicit stream the function may
 // run on a helper thread next to the main one (mk_index_add overlaps the upload of the next
@@ -355,37 +331,61 @@ int upload_range(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint3
     if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     const bool big = n && (b->bases / n) >= (1u << 20);
     if (big) {
-        // few long sequences (genomes) in pageable memory: a ring of pinned pieces, filled by a
-        // few host threads while the previous pieces are in flight over PCIe
+        // Few long sequences (genomes) in pageable memory.  One host thread copies ~14 GB/s into
+        // pinned memory and PCIe 5 x16 takes 55 GB/s (measured on this pool), so a small team
+        // stages pieces of different sequences concurrently: every worker owns two pinned pieces
+        // (copy into one while the other is in flight over PCIe) and issues its own async copies.
         static const size_t PIECE = [] {
             const char* e = getenv("MIEKKI_UPLOAD_PIECE_MB");
-            return (size_t)(e ? std::max(1, atoi(e)) : 16) << 20;
+            return (size_t)(e ? std::max(1, atoi(e)) : 8) << 20;
         }();
-        constexpr int SLOTS = 4;
-        r = reserve_pinned(c, PIECE * SLOTS);
+        static const unsigned TEAM = [] {
+            const char* e = getenv("MIEKKI_UPLOAD_THREADS");
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            return (unsigned)std::min(16, std::max(1, e ? atoi(e) : (int)std::min(6u, std::max(1u, hw / 2))));
+        }();
+        struct Piece { uint32_t seq; uint64_t off; size_t bytes; };
+        std::vector<Piece> pieces;
+        for (uint32_t i = 0; i < n; ++i)
+            for (uint64_t off = 0; off < lens[i]; off += PIECE)
+                pieces.push_back({i, off, (size_t)std::min<uint64_t>(PIECE, lens[i] - off)});
+        const unsigned team = (unsigned)std::min<size_t>(TEAM, std::max<size_t>(1, pieces.size()));
+        r = reserve_pinned(c, PIECE * 2 * team);
         if (r != MK_OK) { batch_release(b); return r; }
         char* ring = static_cast<char*>(c->pinned);
-        cudaEvent_t* ev = c->ring_ev;
-        bool used[SLOTS] = {false, false, false, false};
-        for (int s = 0; s < SLOTS; ++s)
-            if (!ev[s] && cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming) != cudaSuccess) {
-                batch_release(b);
-                return fail(c, MK_ERR_CUDA, "cudaEventCreate failed");
-            }
-        int slot = 0;
-        for (uint32_t i = 0; i < n && e == cudaSuccess; ++i) {
-            for (uint64_t off = 0; off < lens[i] && e == cudaSuccess; off += PIECE) {
-                const size_t m = (size_t)std::min<uint64_t>(PIECE, lens[i] - off);
-                if (used[slot]) e = cudaEventSynchronize(ev[slot]);
-                if (e != cudaSuccess) break;
-                parallel_memcpy(ring + (size_t)slot * PIECE, seqs[i] + off, m);
-                e = cudaMemcpyAsync(b->chars + b->h_coff[i] + off, ring + (size_t)slot * PIECE, m,
-                                    cudaMemcpyHostToDevice, st);
-                if (e == cudaSuccess) e = cudaEventRecord(ev[slot], st);
+        std::atomic<size_t> next{0};
+        std::atomic<int> cuda_err{(int)cudaSuccess};
+        auto worker = [&](unsigned t) {
+            cudaSetDevice(c->device);
+            cudaEvent_t ev[2] = {nullptr, nullptr};
+            bool used[2] = {false, false};
+            cudaError_t err = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+            int slot = 0;
+            while (err == cudaSuccess && cuda_err.load(std::memory_order_relaxed) == (int)cudaSuccess) {
+                const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= pieces.size()) break;
+                const Piece& pc = pieces[i];
+                char* stage = ring + ((size_t)2 * t + slot) * PIECE;
+                if (used[slot]) err = cudaEventSynchronize(ev[slot]);      // its previous copy has left
+                if (err != cudaSuccess) break;
+                memcpy(stage, seqs[pc.seq] + pc.off, pc.bytes);
+                err = cudaMemcpyAsync(b->chars + b->h_coff[pc.seq] + pc.off, stage, pc.bytes, cudaMemcpyHostToDevice, st);
+                if (err == cudaSuccess) err = cudaEventRecord(ev[slot], st);
                 used[slot] = true;
-                slot = (slot + 1) % SLOTS;
+                slot ^= 1;
             }
-        }
+            for (int s2 = 0; s2 < 2; ++s2) {
+                if (used[s2] && err == cudaSuccess) err = cudaEventSynchronize(ev[s2]);
+                if (ev[s2]) cudaEventDestroy(ev[s2]);
+            }
+            if (err != cudaSuccess) cuda_err.store((int)err, std::memory_order_relaxed);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < team; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& x : th) x.join();
+        e = (cudaError_t)cuda_err.load();
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // staging is reused by the next call
         if (e != cudaSuccess) { batch_release(b); return fail(c, MK_ERR_CUDA, cudaGetErrorString(e)); }
     } else if (n) {
@@ -1123,8 +1123,6 @@ void mk_destroy(mk_ctx* c) {
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->sk_stream) cudaStreamDestroy(c->sk_stream);
-    for (cudaEvent_t e : c->ring_ev)
-        if (e) cudaEventDestroy(e);
     delete c;
 }
 
