@@ -18,6 +18,9 @@ Cases
          Outputs: full dump contents, hit lines at -s 200 / -s 0 / -s 5000,
          exact-mode lines.
   caseB  same genomes, -k 21 -h 10 -b 34 (other k, h and Bloom geometry).
+  caseD  70 genomes x 40 kbp (5 founders, 65 relatives at 0.3 % .. 3.5 %), -k 31 -h 12: ids cross
+         the 32-genome groups of a row and the 64-genome build chunk; lists hold more than ten
+         candidates spread over all of them.  Inputs regenerated from seeds (sha256 recorded).
   caseC  14 related genomes x 1.5 Mbp at -h 16: every sketch saturated -> genome_size 0
          (quirk G2) -> empty hit lists at -s 200 and the all-ties heap order at
          -s 0.  Inputs are regenerated from seeds (sha256 recorded); the dump is
@@ -234,6 +237,50 @@ def case_c():
         json.dump(meta, f, indent=1)
 
 
+def case_d_genomes(L=40_000):
+    rng = np.random.default_rng(81)
+    founders = [synth.genome(200 + g, L) for g in range(5)]
+    genomes = list(founders)
+    for j in range(65):                       # families of 14: more candidates than the 10 heap slots
+        src = np.frombuffer(founders[j % 5], np.uint8)
+        genomes.append(synth.substitute(src, 0.003 + 0.0005 * j, rng).tobytes())
+    return genomes
+
+
+def case_d():
+    d = os.path.join(HERE, "caseD")
+    os.makedirs(d, exist_ok=True)
+    genomes = case_d_genomes()
+    reads = synth.sample_reads(genomes, 48, 1500, sub_rate=0.01, block=11)
+    reads += synth.sample_reads(genomes[:5], 12, 4000, sub_rate=0.0, block=12)
+    synth.write_reads(os.path.join(d, "reads.fa"), reads)
+    meta = {"recipe": "see make_golden.py:case_d", "genome_sha256": [hashlib.sha256(s).hexdigest() for s in genomes]}
+    with tempfile.TemporaryDirectory() as tmp:
+        names = []
+        for g, s in enumerate(genomes):
+            p = os.path.join(tmp, "gD%d.fa" % g)
+            synth.write_fasta(p, ">gD%d" % g, s)
+            names.append(p)
+        with open(os.path.join(tmp, "list.txt"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        for s in (200, 0):
+            run_ref(tmp, ["-l", "list.txt", "-a", os.path.join(d, "reads.fa"), "-k", 31, "-h", 12, "-t", 1, "-s", s,
+                          "-o", "hits.txt", "-d", "dump.gz"])
+            shutil.copy(os.path.join(tmp, "hits.txt"), os.path.join(d, "hits_s%d.txt" % s))
+        dump_to_npz(os.path.join(tmp, "dump.gz"), os.path.join(d, "dump.npz"))
+        run_ref(tmp, ["-l", "list.txt", "-a", os.path.join(d, "reads.fa"), "-k", 31, "-h", 12, "-t", 1, "-e",
+                      "-o", "exact.txt"])
+        # exact lines end with the genome file path: keep the base name only
+        with open(os.path.join(tmp, "exact.txt")) as f, open(os.path.join(d, "exact.txt"), "w") as g:
+            for line in f:
+                parts = line.rstrip("\n").split("\t")
+                if len(parts) > 1:
+                    parts[-1] = os.path.basename(parts[-1])
+                g.write("\t".join(parts) + "\n")
+    with open(os.path.join(d, "meta.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+
+
 if __name__ == "__main__":
     if not REF.available:
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
@@ -241,4 +288,5 @@ if __name__ == "__main__":
     case_a_whole_files()
     case_b()
     case_c()
+    case_d()
     print("golden vectors written under", HERE)

@@ -67,3 +67,25 @@ def fmt_g(x: float) -> str:
 def exact_line(real_jax, jac_est, inter, inter_est, header, fname) -> str:
     """Miekki.cpp:853"""
     return "\t".join([fmt_g(real_jax), fmt_g(jac_est), fmt_g(inter), fmt_g(inter_est), header, fname])
+
+
+def case_d(tmp_dir: str | None = None):
+    """Golden case D (70 genomes, regenerated from seeds and checked against the recorded
+    sha256).  -> (case dir, genomes); with tmp_dir also writes gD<i>.fa + list.txt there."""
+    import hashlib
+    import json
+    d = os.path.join(GOLDEN, "caseD")
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    genomes = golden_module().case_d_genomes()
+    assert [hashlib.sha256(s).hexdigest() for s in genomes] == meta["genome_sha256"], \
+        "numpy stream changed: regenerate tests/golden with make_golden.py"
+    if tmp_dir is not None:
+        names = []
+        for g, s in enumerate(genomes):
+            name = "gD%d.fa" % g
+            with open(os.path.join(tmp_dir, name), "wb") as f:
+                f.write(b">gD%d\n" % g + s + b"\n")
+            names.append(name)
+        with open(os.path.join(tmp_dir, "list.txt"), "w") as f:
+            f.write("\n".join(names) + "\n")
+    return d, genomes

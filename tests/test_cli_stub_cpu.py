@@ -104,6 +104,32 @@ def test_sharded_hit_lines_with_all_ties(cli, tmp_path):
     assert out.read_text() == open(os.path.join(D, "hits_s0.txt")).read()
 
 
+def test_case_d_seventy_genomes_over_shards(cli, tmp_path):
+    """70 genome files (more than one parse wave of the build), 1 and 4 shards: hit lines, dump
+    and exact-mode lines against the reference's."""
+    d, _ = H.case_d(str(tmp_path))
+    z = H.load_dump_npz(os.path.join(d, "dump.npz"))
+    want_exact = Counter(l for l in open(os.path.join(d, "exact.txt")).read().split("\n") if l)
+    for devices in ("0", "0,0,0,0"):
+        out, dump = tmp_path / "h.txt", tmp_path / "i.gz"
+        r = subprocess.run([cli, "-l", "list.txt", "-a", os.path.join(d, "reads.fa"), "-k", "31", "-h", "12", "-t", "3",
+                            "-o", str(out), "-d", str(dump), "--devices", devices], cwd=tmp_path,
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "Reference indexed: 70" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
+        assert out.read_text() == open(os.path.join(d, "hits_s200.txt")).read()
+        got = orc.parse_dump(str(dump))
+        assert np.array_equal(got.rows, z["rows"]) and np.array_equal(got.genome_size, z["genome_size"])
+        assert np.array_equal(got.sketch_size, z["sketch_size"])
+        idx, val = H.bloom_nonzero(got.bloom)
+        assert np.array_equal(idx, z["bloom_idx"]) and np.array_equal(val, z["bloom_val"])
+        oute = tmp_path / "e.txt"
+        r = subprocess.run([cli, "-l", "list.txt", "-a", os.path.join(d, "reads.fa"), "-k", "31", "-h", "12", "-e",
+                            "-o", str(oute), "--devices", devices], cwd=tmp_path, capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        assert Counter(l for l in oute.read_text().split("\n") if l) == want_exact
+
+
 def test_messages(cli, tmp_path):
     r = subprocess.run([cli], capture_output=True, text=True)
     assert r.returncode == 0 and "-l" in r.stdout                       # no arguments: help, exit(0)

@@ -325,6 +325,20 @@ def test_exact_edge_cases(mk):
     ix.close()
 
 
+def test_case_d_seventy_genomes_equal_reference(mk):
+    """Golden case D: 70 genomes (two build chunks, three 32-genome groups), full 10-hit lists
+    picked among 14 candidates per family -- dump and hit lines of the reference binary."""
+    d, genomes = H.case_d()
+    ix = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    ix.insert_sequences(genomes[:3])                 # uneven calls: chunks start inside a group
+    ix.insert_sequences(genomes[3:])
+    assert_index_equals_dump(ix, H.load_dump_npz(os.path.join(d, "dump.npz")))
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    for s in (200, 0):
+        assert gpu_hit_lines(ix, reads, s) == open(os.path.join(d, "hits_s%d.txt" % s)).read()
+    ix.close()
+
+
 # ---- other geometries ---------------------------------------------------------------------
 
 def test_case_b_k21_h10_b34(mk):
