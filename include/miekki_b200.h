@@ -144,6 +144,9 @@ int mk_index_import_end(mk_ctx *ctx, const uint64_t *genome_size, const uint8_t 
  * first mk_bloom_window() bytes of the 2^b/8-byte table; bytes past it are never touched
  * for this k.  merge: dst byte = (dst != 0) ? dst : src  ("lowest rank wins"). */
 uint64_t mk_bloom_window(const mk_ctx *ctx);
+/* Bytes [mk_bloom_reach(k, b), window) can never be probed by a k-mer of size k: an upper bound
+ * of the canonical k-mer (see api.cu).  Pure arithmetic, needs no device. */
+uint64_t mk_bloom_reach(uint32_t k, uint32_t bloom_log2);
 int mk_bloom_get(mk_ctx *ctx, uint8_t *dst, uint64_t n);
 int mk_bloom_merge(mk_ctx *ctx, const uint8_t *src, uint64_t n);
 int mk_bloom_set(mk_ctx *ctx, const uint8_t *src, uint64_t n);   /* replace the first n bytes */

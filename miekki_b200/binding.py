@@ -68,6 +68,7 @@ SIGNATURES = {
     "mk_index_stats": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "mk_index_export": (_i, [_vp, _vp, _vp, _vp, _u64, _vp]),
     "mk_index_import": (_i, [_vp, _u32, _vp, _u64, _vp, _vp, _u64, _vp]),
+    "mk_bloom_reach": (_u64, [_u32, _u32]),
     "mk_bloom_window": (_u64, [_vp]),
     "mk_bloom_get": (_i, [_vp, _vp, _u64]),
     "mk_bloom_merge": (_i, [_vp, _vp, _u64]),

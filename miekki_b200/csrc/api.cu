@@ -1054,14 +1054,7 @@ int mk_create(uint32_t k, uint32_t h, uint32_t bits_per_min, uint32_t bits_manti
     uint64_t window = ((top >> bloom_log2) >> 3) + 1;
     window = std::min<uint64_t>(window, (1ull << bloom_log2) / 8);
     ctx->window = (window + 15) / 16 * 16;
-    // A canonical k-mer min(S, RC) is < M = 4^k - 4^(ceil(k/2)-1): a digit 3 of S comes from a
-    // 'T', whose reverse-strand digit is 0, so S >= 4^k - 4^j forces RC <= 4^k - 4^(k-j), and both
-    // can hold only for j >= k/2.  Table bytes past ((M - 1 + 1023) >> (b + 3)) are therefore
-    // never probed; the build's "page is saturated" test ignores them.
-    {
-        const uint64_t M = (1ull << (2 * k)) - (1ull << (2 * ((k + 1) / 2 - 1)));
-        ctx->bloom_reach = std::min<uint64_t>(ctx->window, (((M - 1 + 1023) >> bloom_log2) >> 3) + 1);
-    }
+    ctx->bloom_reach = std::min<uint64_t>(ctx->window, mk_bloom_reach(k, bloom_log2));
     {   // keep freed per-call buffers in the stream-ordered pool instead of returning them
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1468,6 +1461,18 @@ int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_st
 }
 
 uint64_t mk_bloom_window(const mk_ctx* c) { return c ? c->window : 0; }
+
+// A canonical k-mer min(S, RC) is < M = 4^k - 4^(ceil(k/2)-1): a digit 3 of S comes from a 'T'
+// (or 't' in the prefix encoder), whose reverse-strand digit is 0, so S >= 4^k - 4^j forces the
+// low k-j digits of RC to 0, i.e. RC <= 4^k - 4^(k-j), and both can hold only for j >= k/2.
+// Table bytes from ((M - 1 + 1023) >> (b + 3)) + 1 on are therefore never probed; the build's
+// "page is saturated" test ignores them.  Pure arithmetic (no device needed):
+// tests/test_abi_cpu.py checks the bound against every k-mer the oracle can produce for small k.
+uint64_t mk_bloom_reach(uint32_t k, uint32_t bloom_log2) {
+    if (k < 1 || k > 31 || bloom_log2 > 60) return 0;
+    const uint64_t M = (1ull << (2 * k)) - (1ull << (2 * ((k + 1) / 2 - 1)));
+    return (((M - 1 + 1023) >> bloom_log2) >> 3) + 1;
+}
 
 int mk_bloom_get(mk_ctx* c, uint8_t* dst, uint64_t n) {
     if (!c || !dst) return MK_ERR_ARG;
