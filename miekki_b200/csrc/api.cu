@@ -85,7 +85,7 @@ struct mk_ctx {
     uint8_t* bloom = nullptr;
     uint32_t* owner = nullptr;
     uint64_t window = 0;          // bytes, multiple of 16
-    uint64_t bloom_reach = 0;     // bytes [bloom_reach, window) can never be probed (see mk_create)
+    uint64_t bloom_reach = 0;     // bytes [bloom_reach, window) can never be probed (mk_bloom_reach)
 
     DevBuf planeF, planeR, keys, fp, meta, list, list_len, list2, list_len2, counts, counts2, heap, heap_len, heap2,
         heap_len2, misc, pages;

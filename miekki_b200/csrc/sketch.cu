@@ -541,7 +541,7 @@ resolve_slow_kernel(unsigned long long* __restrict__ keys_anc, const uint32_t* _
 
 // Which 4 KB pages of the Bloom table hold no zero byte?  One warp per page -> full8[page];
 // then pair bit j = full8[j] && full8[j + 1] (a k-mer's probes may cross into the next page).
-// Only bytes below `reach` can ever be probed (api.cu: bloom_reach), so bytes from there on do
+// Only bytes below `reach` can ever be probed (api.cu: mk_bloom_reach), so bytes from there on do
 // not count, and a page that starts at or past `reach` is vacuously full.
 __global__ void __launch_bounds__(256)
 bloom_pages_kernel(const uint8_t* __restrict__ bloom, uint64_t reach, uint32_t n_pages,
