@@ -462,19 +462,40 @@ void query_file(Index& ix, const string& path) {
         return;
     }
     mkcli::LineReader in(path);
-    ReadBatch b;
-    vector<mk_hit> hits;
-    vector<uint32_t> nhits;
-    const size_t cap = 1 << 16;
-    while (next_reads(in, ix.k, cap, b, false)) {
-        cout << "-" << flush;                                    // :345
-        run_query(ix, b, 10, 10, 0.5 * ix.threshold, hits, nhits);   // :437
-        vector<string> lines(b.size());
+    // Three stages overlap: while batch i is on the GPU, batch i+1 is parsed from the file and
+    // the lines of batch i-1 are formatted and written (in order: one writer at a time).
+    static const size_t cap = [] {
+        const char* e = getenv("MIEKKI_QUERY_BATCH_READS");      // tests shrink it to force many batches
+        return e ? max<size_t>(1, strtoull(e, nullptr, 10)) : (size_t)1 << 16;
+    }();
+    struct Scored {
+        ReadBatch b;
+        vector<mk_hit> hits;
+        vector<uint32_t> nhits;
+    };
+    auto emit = [&ix](Scored* s) {
+        vector<string> lines(s->b.size());
         #pragma omp parallel for num_threads(ix.threads) schedule(static)
-        for (size_t i = 0; i < b.size(); ++i)
-            lines[i] = b.heads[i] + ":" + hit_text(&hits[i * 10], nhits[i]) + "\n";   // :440-444
-        for (const string& s : lines) *ix.out << s;
+        for (size_t i = 0; i < s->b.size(); ++i)
+            lines[i] = s->b.heads[i] + ":" + hit_text(&s->hits[i * 10], s->nhits[i]) + "\n";   // :440-444
+        for (const string& l : lines) *ix.out << l;
+        delete s;
+    };
+    future<void> writer;
+    Scored* cur = new Scored();
+    bool have = next_reads(in, ix.k, cap, cur->b, false);
+    while (have) {
+        Scored* nxt = new Scored();
+        future<bool> parsed = async(launch::async, [&in, &ix, nxt] { return next_reads(in, ix.k, cap, nxt->b, false); });
+        cout << "-" << flush;                                    // :345
+        run_query(ix, cur->b, 10, 10, 0.5 * ix.threshold, cur->hits, cur->nhits);   // :437
+        if (writer.valid()) writer.get();
+        writer = async(launch::async, emit, cur);
+        have = parsed.get();
+        cur = nxt;
     }
+    delete cur;
+    if (writer.valid()) writer.get();
     *ix.out << flush;
 }
 

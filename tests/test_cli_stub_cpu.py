@@ -130,6 +130,18 @@ def test_case_d_seventy_genomes_over_shards(cli, tmp_path):
         assert Counter(l for l in oute.read_text().split("\n") if l) == want_exact
 
 
+@pytest.mark.parametrize("batch", [1, 7])
+def test_query_pipeline_keeps_the_order_of_the_file(cli, tmp_path, batch):
+    """query_file overlaps parsing, scoring and writing of consecutive read batches; with 1 or 7
+    reads per batch (MIEKKI_QUERY_BATCH_READS) the 56 lines must still come out in file order."""
+    out = tmp_path / "hits.txt"
+    stdout = run(cli, ["-l", "list.txt", "-a", "reads.fa", "-k", 31, "-h", 12, "-s", 0, "-o", out],
+                 {"MIEKKI_QUERY_BATCH_READS": str(batch)})
+    assert out.read_text() == open(os.path.join(D, "hits_s0.txt")).read()
+    n_reads = open(os.path.join(D, "hits_s0.txt")).read().count("\n")
+    assert stdout.count("-") >= (n_reads + batch - 1) // batch          # one tick per batch (:345)
+
+
 def test_messages(cli, tmp_path):
     r = subprocess.run([cli], capture_output=True, text=True)
     assert r.returncode == 0 and "-l" in r.stdout                       # no arguments: help, exit(0)
