@@ -17,7 +17,7 @@ namespace mkcli {
 // Sequential reader with std::getline semantics on the decompressed bytes.
 class LineReader {
 public:
-    explicit LineReader(const std::string& path) : in_(1 << 20), out_(1 << 20) {
+    explicit LineReader(const std::string& path, int threads = 1) : in_(1 << 20), out_(1 << 20) {
         f_ = fopen(path.c_str(), "rb");
         if (!f_) throw std::runtime_error("cannot open " + path);
         memset(&zs_, 0, sizeof(zs_));
@@ -26,6 +26,14 @@ public:
         const unsigned char* p = in_.data();
         compressed_ = in_len_ >= 2 && ((p[0] == 0x1F && p[1] == 0x8B) ||
                                        (p[0] == 0x78 && (p[1] == 0x01 || p[1] == 0x9C || p[1] == 0xDA)));
+        // our own dumps: gzip members that carry their sizes (ParallelGzWriter) are inflated
+        // `threads` at a time
+        indexed_ = threads > 1 && in_len_ >= 24 && member_sizes(p, nullptr, nullptr);
+        if (indexed_) {
+            threads_ = threads;
+            fseek(f_, 0, SEEK_SET);
+            return;
+        }
         if (compressed_) {
             if (inflateInit2(&zs_, 15 + 32) != Z_OK) throw std::runtime_error("inflateInit2 failed");
             zs_.next_in = in_.data();
@@ -33,7 +41,7 @@ public:
         }
     }
     ~LineReader() {
-        if (compressed_) inflateEnd(&zs_);
+        if (compressed_ && !indexed_) inflateEnd(&zs_);
         if (f_) fclose(f_);
     }
     LineReader(const LineReader&) = delete;
@@ -86,11 +94,79 @@ public:
     }
 
 private:
-    const unsigned char* cur() const { return compressed_ ? out_.data() : in_.data(); }
+    const unsigned char* cur() const {
+        return indexed_ ? wave_[wave_pos_].data() : compressed_ ? out_.data() : in_.data();
+    }
+    // header of a member written by ParallelGzWriter -> its total and payload sizes
+    static bool member_sizes(const unsigned char* h, uint32_t* total, uint32_t* usize) {
+        if (!(h[0] == 0x1F && h[1] == 0x8B && h[2] == 8 && h[3] == 4 && h[10] == 12 && h[11] == 0 && h[12] == 'M' &&
+              h[13] == 'K' && h[14] == 8 && h[15] == 0))
+            return false;
+        if (total) memcpy(total, h + 16, 4);
+        if (usize) memcpy(usize, h + 20, 4);
+        return true;
+    }
+    // indexed mode: read the next `threads_` members from the file, inflate them in parallel
+    bool next_wave() {
+        std::vector<std::vector<unsigned char>> raw;
+        std::vector<uint32_t> usz;
+        for (int i = 0; i < threads_; ++i) {
+            unsigned char h[24];
+            const size_t got = fread(h, 1, 24, f_);
+            if (got == 0) break;
+            uint32_t total = 0, usize = 0;
+            if (got != 24 || !member_sizes(h, &total, &usize) || total < 32)
+                throw std::runtime_error("index dump: gzip member without the size record");
+            raw.emplace_back(total);
+            memcpy(raw.back().data(), h, 24);
+            if (fread(raw.back().data() + 24, 1, total - 24, f_) != total - 24)
+                throw std::runtime_error("index dump: truncated gzip member");
+            usz.push_back(usize);
+        }
+        wave_.assign(raw.size(), {});
+        wave_pos_ = 0;
+        if (raw.empty()) return false;
+        int bad = 0;
+        #pragma omp parallel for num_threads(threads_) schedule(dynamic, 1)
+        for (size_t i = 0; i < raw.size(); ++i) {
+            wave_[i].resize(usz[i]);
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            bool ok = inflateInit2(&zs, -15) == Z_OK;
+            if (ok) {
+                zs.next_in = raw[i].data() + 24;
+                zs.avail_in = (uInt)(raw[i].size() - 24 - 8);
+                zs.next_out = wave_[i].data();
+                zs.avail_out = (uInt)usz[i];
+                ok = inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.avail_out == 0;
+                inflateEnd(&zs);
+            }
+            uint32_t crc = 0;
+            memcpy(&crc, raw[i].data() + raw[i].size() - 8, 4);
+            ok = ok && crc == (uint32_t)crc32(crc32(0L, Z_NULL, 0), wave_[i].data(), (uInt)usz[i]);
+            if (!ok) {
+                #pragma omp atomic write
+                bad = 1;
+            }
+        }
+        if (bad) throw std::runtime_error("index dump: corrupt gzip member");
+        return true;
+    }
     void fill_in() {
         in_len_ = fread(in_.data(), 1, in_.size(), f_);
     }
     bool refill() {
+        if (indexed_) {
+            // members may be empty (an empty payload is still one member): skip them
+            for (;;) {
+                if (wave_started_ && wave_pos_ + 1 < wave_.size()) ++wave_pos_;
+                else if (!next_wave()) return false;
+                wave_started_ = true;
+                pos_ = 0;
+                len_ = wave_[wave_pos_].size();
+                if (len_ > 0) return true;
+            }
+        }
         if (!compressed_) {
             if (first_plain_) {          // the constructor already read the first block
                 first_plain_ = false;
@@ -137,6 +213,10 @@ private:
     std::vector<unsigned char> in_, out_;
     size_t in_len_ = 0, pos_ = 0, len_ = 0;
     bool compressed_ = false, eof_ = false, z_done_ = false, first_plain_ = true;
+    bool indexed_ = false, wave_started_ = false;
+    int threads_ = 1;
+    std::vector<std::vector<unsigned char>> wave_;
+    size_t wave_pos_ = 0;
 };
 
 // Parallel gzip-1 writer for the index dump (zstr::ofstream writes gzip level 1,
@@ -146,6 +226,7 @@ private:
 // member end (zstr.hpp:193-197), so the dump stays loadable by the reference's -i.
 class ParallelGzWriter {
 public:
+    static constexpr size_t member_header_bytes() { return 24; }
     ParallelGzWriter(const std::string& path, int threads) : threads_(threads < 1 ? 1 : threads) {
         f_ = fopen(path.c_str(), "wb");
         if (!f_) throw std::runtime_error("cannot open " + path);
@@ -176,21 +257,36 @@ public:
 
 private:
     static constexpr size_t CHUNK = 32u << 20;
+    // One gzip member written by hand around a raw deflate stream, so that its header can say
+    // how long the member is (the way BGZF does): FEXTRA subfield 'M','K' = {u32 member bytes,
+    // u32 payload bytes}.  Any gzip reader skips the field; IndexedGzSource hops from member to
+    // member with it and inflates them in parallel.
     static void deflate_member(const unsigned char* src, size_t n, std::vector<unsigned char>& out) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
-        if (deflateInit2(&zs, 1, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+        if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK)
             throw std::runtime_error("deflateInit2 failed");
-        out.resize(deflateBound(&zs, (uLong)n) + 64);
+        const size_t head = member_header_bytes();
+        out.resize(head + deflateBound(&zs, (uLong)n) + 64 + 8);
         zs.next_in = const_cast<unsigned char*>(src);
         zs.avail_in = (uInt)n;
-        zs.next_out = out.data();
-        zs.avail_out = (uInt)out.size();
+        zs.next_out = out.data() + head;
+        zs.avail_out = (uInt)(out.size() - head - 8);
         const int r = deflate(&zs, Z_FINISH);
-        const size_t produced = out.size() - zs.avail_out;
+        const size_t produced = (out.size() - head - 8) - zs.avail_out;
         deflateEnd(&zs);
         if (r != Z_STREAM_END) throw std::runtime_error("deflate failed");
-        out.resize(produced);
+        const uint32_t total = (uint32_t)(head + produced + 8), usize = (uint32_t)n;
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)n);
+        unsigned char* h = out.data();
+        const unsigned char fixed[12] = {0x1F, 0x8B, 8, 4 /* FEXTRA */, 0, 0, 0, 0, 0, 3 /* unix */, 12, 0 /* XLEN */};
+        memcpy(h, fixed, 12);
+        h[12] = 'M'; h[13] = 'K'; h[14] = 8; h[15] = 0;
+        memcpy(h + 16, &total, 4);
+        memcpy(h + 20, &usize, 4);
+        memcpy(h + head + produced, &crc, 4);
+        memcpy(h + head + produced + 4, &usize, 4);
+        out.resize(total);
     }
     void flush_pending() {
         if (pending_.empty()) return;

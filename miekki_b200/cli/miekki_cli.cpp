@@ -322,7 +322,7 @@ bool load_disk(Index& ix, const string& path) {
         cout << "File problem" << endl;                          // :683-686
         return false;
     }
-    mkcli::LineReader in(path);
+    mkcli::LineReader in(path, ix.threads);     // our own dumps inflate `threads` members at a time
     unsigned char head[39];
     if (in.read(head, 39) != 39) {
         cerr << "miekki: truncated index dump" << endl;

@@ -22,7 +22,7 @@ int main(int argc, char** argv) {
     } else if (cmd == "records") {              // Miekki.cpp:801-822, k = argv[3]
         for (const std::string& r : mkcli::read_genome_records(argv[2], (uint32_t)std::stoul(argv[3])))
             std::cout << r << "\n";
-    } else if (cmd == "gzwrite") {              // ParallelGzWriter: argv[2] = out, argv[3] = payload bytes
+    } else if (cmd == "gzwrite" || cmd == "gzwrite-readonly") {   // ParallelGzWriter: argv[2] = file, argv[3] = payload bytes
         const size_t n = std::stoull(argv[3]);
         std::string payload(n, '\0');
         uint64_t x = 88172645463325252ull;
@@ -30,14 +30,16 @@ int main(int argc, char** argv) {
             x ^= x << 13; x ^= x >> 7; x ^= x << 17;
             payload[i] = (i / 4096) % 3 == 0 ? 0 : (char)(x & 0xFF);     // zero runs and noise
         }
-        mkcli::ParallelGzWriter w(argv[2], 4);
-        w.write("HEAD", 4);
-        w.write(payload.data(), n / 3);
-        w.write(payload.data() + n / 3, n - n / 3);
-        w.write("TAIL", 4);
-        w.close();
-        // read it back with our own reader
-        mkcli::LineReader in(argv[2]);
+        if (cmd == "gzwrite") {
+            mkcli::ParallelGzWriter w(argv[2], 4);
+            w.write("HEAD", 4);
+            w.write(payload.data(), n / 3);
+            w.write(payload.data() + n / 3, n - n / 3);
+            w.write("TAIL", 4);
+            w.close();
+        }
+        // read it back with our own reader: sequential inflate, or (argv[4] threads) member-parallel
+        mkcli::LineReader in(argv[2], argc > 4 ? std::stoi(argv[4]) : 1);
         std::string back(n + 8, '\0');
         const size_t got = in.read(&back[0], n + 8);
         char extra;

@@ -64,11 +64,26 @@ def test_genome_concat_and_records_follow_the_reference(exe, tmp_path):
     assert [l for l in run(exe, "records", g4, 31).split(b"\n") if l] == want and len(want) == 2
 
 
+@pytest.mark.parametrize("threads", [1, 4])
 @pytest.mark.parametrize("n", [0, 5, 100_000, 70_000_000])
-def test_parallel_gzip_writer_round_trips(exe, tmp_path, n):
+def test_parallel_gzip_writer_round_trips(exe, tmp_path, n, threads):
+    """Members carry their sizes in a gzip FEXTRA field (like BGZF): any gzip reader skips it,
+    ours inflates `threads` members at a time (threads = 1: plain sequential inflate)."""
     p = tmp_path / "d.gz"
-    assert run(exe, "gzwrite", p, n).strip() == b"roundtrip-ok"
+    assert run(exe, "gzwrite", p, n, threads).strip() == b"roundtrip-ok"
     data = gzip.open(p, "rb").read()                 # concatenated members are one gzip file
     assert len(data) == n + 8 and data[:4] == b"HEAD" and data[-4:] == b"TAIL"
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[12:16] == b"MK\x08\x00"       # FEXTRA size record
     if n > 64 << 20:
-        assert open(p, "rb").read().count(b"\x1f\x8b\x08") >= 3     # several members
+        assert raw.count(b"\x1f\x8b\x08\x04") >= 3                 # several members
+
+
+def test_corrupt_member_is_reported(exe, tmp_path):
+    p = tmp_path / "d.gz"
+    run(exe, "gzwrite", p, 100_000, 4)
+    raw = bytearray(open(p, "rb").read())
+    raw[len(raw) // 2] ^= 0x5A
+    p.write_bytes(bytes(raw))
+    r = subprocess.run([exe, "gzwrite-readonly", str(p), "100000", "4"], capture_output=True)
+    assert r.returncode != 0 or b"roundtrip-ok" not in r.stdout

@@ -72,6 +72,12 @@ def test_dump_in_slabs_load_and_names(cli, tmp_path, devices):
                        "--devices", devices], env)       # -k / -s are ignored with -i (quirk G6)
     assert "Load sucessful" in stdout
     assert out.read_text() == open(os.path.join(D, "hits_s200.txt")).read()
+    # the reference binary reads the same file (its zlib skips the members' size records)
+    ref = orc.RefBinary()
+    if ref.available:
+        outr = tmp_path / "ref_hits.txt"
+        ref.run(["-i", str(dump), "-a", os.path.join(D, "reads.fa"), "-t", "1", "-o", str(outr)], cwd=D)
+        assert outr.read_text() == open(os.path.join(D, "hits_s200.txt")).read()
     # exact mode from a loaded index works thanks to the side-car (the reference crashes: quirk G4)
     oute = tmp_path / "exact.txt"
     run(cli, ["-i", dump, "-a", os.path.join(D, "reads.fa"), "-e", "-o", oute, "--devices", devices])
