@@ -243,6 +243,23 @@ public:
         flush_pending();
         compress_and_write(src, n);
     }
+    // n zero bytes (the never-touched tail of the Bloom table: 15/16 of the reference's 1 GiB at
+    // the default -k / -b).  Whole chunks reuse one member deflated once.
+    void write_zeros(size_t n) {
+        flush_pending();
+        if (n >= CHUNK && zero_member_.empty()) {
+            const std::vector<unsigned char> z(CHUNK, 0);
+            deflate_member(z.data(), CHUNK, zero_member_);
+        }
+        for (; n >= CHUNK; n -= CHUNK) {
+            fwrite(zero_member_.data(), 1, zero_member_.size(), f_);
+            wrote_any_ = true;
+        }
+        if (n) {
+            const std::vector<unsigned char> z(n, 0);
+            compress_and_write(z.data(), n);
+        }
+    }
     void close() {
         if (!f_) return;
         flush_pending();
@@ -312,7 +329,7 @@ private:
     FILE* f_ = nullptr;
     int threads_;
     bool wrote_any_ = false;
-    std::vector<unsigned char> pending_;
+    std::vector<unsigned char> pending_, zero_member_;
 };
 
 // Miekki.cpp:559-567 (index_file_of_file): every line that does not start with '>' is

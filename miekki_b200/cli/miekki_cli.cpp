@@ -298,7 +298,11 @@ void dump_disk(Index& ix, const string& path) {
             w.write(buf[cur].data(), buf[cur].size());
         }
     }
-    vector<uint8_t> bloom(bloom_bits / 8);
+    // Only the first mk_bloom_window bytes of the table can be non-zero for this k; the rest of
+    // the reference's 2^b / 8 bytes is written as zeros without ever being materialised.
+    const uint64_t bloom_bytes = bloom_bits / 8;
+    const uint64_t window = min<uint64_t>(bloom_bytes, mk_bloom_window(ix.shard[0]));
+    vector<uint8_t> bloom(window);
     vector<uint64_t> gs(n);
     vector<uint32_t> ss(n);
     for (size_t r = 0; r < ix.shard.size(); ++r)
@@ -307,6 +311,7 @@ void dump_disk(Index& ix, const string& path) {
             die(ix.shard[r], "mk_index_export");
     w.write(gs.data(), gs.size() * 8);
     w.write(bloom.data(), bloom.size());
+    w.write_zeros(bloom_bytes - window);
     w.write(ss.data(), ss.size() * 4);
     w.close();
     // file_names is not part of the dump (quirk G4: the reference's `-i ... -e` crashes).  A
@@ -367,11 +372,22 @@ bool load_disk(Index& ix, const string& path) {
                     die(ix.shard[r], "mk_index_import_rows");
         }
     }
-    vector<uint8_t> bloom(bloom_bits / 8);
+    // of the table's 2^b / 8 bytes only the first mk_bloom_window can be non-zero for this k: the
+    // rest is read past, not kept
+    const uint64_t bloom_bytes = bloom_bits / 8;
+    vector<uint8_t> bloom((size_t)min<uint64_t>(bloom_bytes, mk_bloom_window(ix.shard[0])));
     vector<uint64_t> gs(n);
     vector<uint32_t> ss(n);
     ok = ok && in.read(gs.data(), gs.size() * 8) == gs.size() * 8;
-    if (bloom_bits != 0) ok = ok && in.read(bloom.data(), bloom.size()) == bloom.size();
+    ok = ok && in.read(bloom.data(), bloom.size()) == bloom.size();
+    {
+        vector<uint8_t> skip(16u << 20);
+        for (uint64_t left = bloom_bytes - bloom.size(); ok && left > 0;) {
+            const size_t m = (size_t)min<uint64_t>(left, skip.size());
+            ok = in.read(skip.data(), m) == m;
+            left -= m;
+        }
+    }
     ok = ok && in.read(ss.data(), ss.size() * 4) == ss.size() * 4;
     if (!ok) {
         cerr << "miekki: truncated index dump" << endl;

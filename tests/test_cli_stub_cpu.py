@@ -148,6 +148,35 @@ def test_query_pipeline_keeps_the_order_of_the_file(cli, tmp_path, batch):
     assert stdout.count("-") >= (n_reads + batch - 1) // batch          # one tick per batch (:345)
 
 
+@pytest.mark.parametrize("devices", ["0", "0,0"])
+def test_loads_reference_style_dump(cli, tmp_path, devices):
+    """A dump written the way the reference writes it: one gzip member, no size records, the
+    full 1 GiB Bloom table (read past beyond the window), a garbage jaccard_estimation byte."""
+    import gzip
+    z = H.load_dump_npz(os.path.join(D, "dump.npz"))
+    bloom = np.zeros((1 << 33) // 8, np.uint8)
+    bloom[z["bloom_idx"]] = z["bloom_val"]
+    p = tmp_path / "ref.gz"
+    with gzip.open(p, "wb", compresslevel=1) as f:
+        f.write(np.array([31, 12, 8, 5, 14, 33], "<u4").tobytes())
+        f.write(np.array([1 << 33], "<u8").tobytes())
+        f.write(bytes([7, 0]))
+        f.write(np.array([200], "<u4").tobytes() + bytes([1]))
+        f.write(z["rows"].tobytes() + z["genome_size"].astype("<u8").tobytes())
+        f.write(bloom.tobytes())
+        f.write(z["sketch_size"].astype("<u4").tobytes())
+    del bloom
+    out = tmp_path / "hits.txt"
+    run(cli, ["-i", p, "-a", os.path.join(D, "reads.fa"), "-o", out, "--devices", devices])
+    assert out.read_text() == open(os.path.join(D, "hits_s200.txt")).read()
+    # a truncated file is reported, not loaded
+    raw = open(p, "rb").read()
+    (tmp_path / "cut.gz").write_bytes(raw[: len(raw) // 2])
+    r = subprocess.run([cli, "-i", str(tmp_path / "cut.gz"), "-a", os.path.join(D, "reads.fa"), "-o", str(out)],
+                       cwd=D, capture_output=True, text=True)
+    assert r.returncode != 0
+
+
 def test_messages(cli, tmp_path):
     r = subprocess.run([cli], capture_output=True, text=True)
     assert r.returncode == 0 and "-l" in r.stdout                       # no arguments: help, exit(0)
