@@ -576,12 +576,15 @@ void query_file_exact(Index& ix, const string& path) {
         return;
     }
     mkcli::LineReader in(path);
-    ReadBatch b;
+    ReadBatch b, nxt;
     vector<mk_hit> hits;
     vector<uint32_t> nhits;
     map<uint32_t, vector<Candidate>> per_genome;
     size_t held = 0;
-    while (next_reads(in, ix.k, 1 << 14, b, true)) {
+    bool have = next_reads(in, ix.k, 1 << 14, b, true);
+    while (have) {
+        // the next batch is parsed while this one is scored (and its genomes intersected)
+        future<bool> parsed = async(launch::async, [&in, &ix, &nxt] { return next_reads(in, ix.k, 1 << 14, nxt, true); });
         run_query(ix, b, 5, 10, (double)ix.threshold, hits, nhits);   // :741
         for (size_t i = 0; i < b.size(); ++i)
             for (uint32_t j = 0; j < nhits[i]; ++j) {
@@ -593,6 +596,9 @@ void query_file_exact(Index& ix, const string& path) {
             ground_truth_all(ix, per_genome);
             held = 0;
         }
+        have = parsed.get();
+        swap(b.heads, nxt.heads);
+        swap(b.seqs, nxt.seqs);
     }
     ground_truth_all(ix, per_genome);
     *ix.out << flush;
@@ -609,10 +615,15 @@ void query_file_of_file(Index& ix, const string& list) {
     }
     const vector<string> names = read_list(list);
     const size_t wave = max<size_t>(16, 2 * (size_t)ix.threads);
-    for (size_t w0 = 0; w0 < names.size(); w0 += wave) {
+    struct Wave {
+        vector<string> seqs;
+        vector<char> ok;
+    };
+    auto parse = [&](size_t w0) {
+        Wave w;
         const size_t m = min(wave, names.size() - w0);
-        vector<string> seqs(m);
-        vector<char> ok(m, 0);
+        w.seqs.resize(m);
+        w.ok.assign(m, 0);
         #pragma omp parallel for num_threads(ix.threads) schedule(dynamic, 1)
         for (size_t i = 0; i < m; ++i) {
             const string& fn = names[w0 + i];
@@ -621,14 +632,23 @@ void query_file_of_file(Index& ix, const string& list) {
                 cout << "File problem" << endl;                  // :488
                 continue;
             }
-            seqs[i] = mkcli::read_genome_concat(fn);             // :491-497
-            ok[i] = seqs[i].size() >= ix.k;                      // :498
+            w.seqs[i] = mkcli::read_genome_concat(fn);           // :491-497
+            w.ok[i] = w.seqs[i].size() >= ix.k;                  // :498
         }
+        return w;
+    };
+    // wave i+1 is read and parsed while wave i is scored
+    future<Wave> next;
+    if (!names.empty()) next = async(launch::async, parse, (size_t)0);
+    for (size_t w0 = 0; w0 < names.size(); w0 += wave) {
+        Wave cur = next.get();
+        if (w0 + wave < names.size()) next = async(launch::async, parse, w0 + wave);
+        const size_t m = cur.seqs.size();
         ReadBatch b;
         for (size_t i = 0; i < m; ++i) {
-            if (ok[i]) {
+            if (cur.ok[i]) {
                 b.heads.push_back(names[w0 + i]);
-                b.seqs.push_back(std::move(seqs[i]));
+                b.seqs.push_back(std::move(cur.seqs[i]));
             }
             cout << "-" << flush;                                // :608
         }
