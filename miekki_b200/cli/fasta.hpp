@@ -231,7 +231,9 @@ public:
         f_ = fopen(path.c_str(), "wb");
         if (!f_) throw std::runtime_error("cannot open " + path);
     }
-    ~ParallelGzWriter() { close(); }
+    ~ParallelGzWriter() {
+        try { close(); } catch (...) {}
+    }
     // small pieces (header fields) are gathered and leave with the next large block
     void write(const void* p, size_t n) {
         const unsigned char* src = (const unsigned char*)p;
@@ -252,7 +254,7 @@ public:
             deflate_member(z.data(), CHUNK, zero_member_);
         }
         for (; n >= CHUNK; n -= CHUNK) {
-            fwrite(zero_member_.data(), 1, zero_member_.size(), f_);
+            put(zero_member_.data(), zero_member_.size());
             wrote_any_ = true;
         }
         if (n) {
@@ -260,20 +262,32 @@ public:
             compress_and_write(z.data(), n);
         }
     }
+    // Throws when any byte could not be written (full disk, I/O error): a dump must never be
+    // silently short.
     void close() {
         if (!f_) return;
-        flush_pending();
-        if (!wrote_any_) {                      // an empty payload is still a valid gzip file
-            std::vector<unsigned char> out;
-            deflate_member(nullptr, 0, out);
-            fwrite(out.data(), 1, out.size(), f_);
+        FILE* f = f_;
+        try {
+            flush_pending();
+            if (!wrote_any_) {                  // an empty payload is still a valid gzip file
+                std::vector<unsigned char> out;
+                deflate_member(nullptr, 0, out);
+                put(out.data(), out.size());
+            }
+        } catch (...) {
+            f_ = nullptr;
+            fclose(f);
+            throw;
         }
-        fclose(f_);
         f_ = nullptr;
+        if (fclose(f) != 0) throw std::runtime_error("index dump: close failed (disk full?)");
     }
 
 private:
     static constexpr size_t CHUNK = 32u << 20;
+    void put(const void* p, size_t n) {
+        if (n && fwrite(p, 1, n, f_) != n) throw std::runtime_error("index dump: short write (disk full?)");
+    }
     // One gzip member written by hand around a raw deflate stream, so that its header can say
     // how long the member is (the way BGZF does): FEXTRA subfield 'M','K' = {u32 member bytes,
     // u32 payload bytes}.  Any gzip reader skips the field; IndexedGzSource hops from member to
@@ -317,12 +331,19 @@ private:
         for (size_t c0 = 0; c0 < nchunks; c0 += (size_t)threads_) {
             const size_t m = std::min<size_t>((size_t)threads_, nchunks - c0);
             std::vector<std::vector<unsigned char>> outs(m);
+            int bad = 0;                        // an exception must not leave the parallel region
             #pragma omp parallel for num_threads(threads_) schedule(dynamic, 1)
             for (size_t i = 0; i < m; ++i) {
                 const size_t off = (c0 + i) * CHUNK;
-                deflate_member(src + off, std::min(CHUNK, n - off), outs[i]);
+                try {
+                    deflate_member(src + off, std::min(CHUNK, n - off), outs[i]);
+                } catch (...) {
+                    #pragma omp atomic write
+                    bad = 1;
+                }
             }
-            for (size_t i = 0; i < m; ++i) fwrite(outs[i].data(), 1, outs[i].size(), f_);
+            if (bad) throw std::runtime_error("index dump: deflate failed");
+            for (size_t i = 0; i < m; ++i) put(outs[i].data(), outs[i].size());
         }
         wrote_any_ = wrote_any_ || n > 0;
     }

@@ -58,14 +58,54 @@ bool exists_test(const string& name) {
     return stat(name.c_str(), &buffer) == 0;
 }
 
-// utils.cpp:145-157 intToString (thousands separators) -- banner only
+// Decimal with a comma between groups of three digits, as the reference's banners print sizes
+// (main.cpp:186, Miekki.cpp:585).
 string int_to_string(uint64_t n) {
-    if (n < 1000) return to_string(n);
-    string end(to_string(n % 1000));
-    if (end.size() == 3) return int_to_string(n / 1000) + "," + end;
-    if (end.size() == 2) return int_to_string(n / 1000) + ",0" + end;
-    return int_to_string(n / 1000) + ",00" + end;
+    string digits = to_string(n), out;
+    const size_t lead = digits.size() % 3;
+    for (size_t i = 0; i < digits.size(); ++i) {
+        if (i && i % 3 == lead) out += ',';
+        out += digits[i];
+    }
+    return out;
 }
+
+// Readers throw on unreadable / corrupt input (fasta.hpp).  An exception must not cross an OpenMP
+// region, so loop bodies run through this: the first message is kept and reported by the caller.
+struct LoopError {
+    string first;
+    template <class F>
+    void run(F&& body) {
+        try {
+            body();
+        } catch (const exception& e) {
+            #pragma omp critical(loop_error)
+            if (first.empty()) first = e.what();
+        }
+    }
+    void rethrow() const {
+        if (!first.empty()) throw runtime_error(first);
+    }
+};
+
+// 64-bit FNV-1a, chained
+uint64_t fnv1a(const void* p, size_t n, uint64_t h = 0xCBF29CE484222325ull) {
+    const unsigned char* s = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) h = (h ^ s[i]) * 0x100000001B3ull;
+    return h;
+}
+// What binds a `<dump>.names` side-car to its dump: the header fields and both statistics arrays.
+string names_token(uint32_t k, uint32_t h, uint32_t b, uint32_t threshold, const vector<uint32_t>& ss,
+                   const vector<uint64_t>& gs) {
+    const uint32_t head[5] = {k, h, b, threshold, (uint32_t)ss.size()};
+    uint64_t t = fnv1a(head, sizeof(head));
+    t = fnv1a(ss.data(), ss.size() * 4, t);
+    t = fnv1a(gs.data(), gs.size() * 8, t);
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%016llx", (unsigned long long)t);
+    return buf;
+}
+const char* const kNamesMagic = "#miekki-names v1 ";
 
 // One table drives both the usage text and the option parser.  Letters, arities and defaults
 // are the reference's (getopt string "i:l:a:h:t:f:k:s:b:o:ed:A:", main.cpp:130-137); note that -h
@@ -188,6 +228,7 @@ void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo,
         const size_t m = min(wave, hi - w0);
         w.seqs.resize(m);
         w.ok.assign(m, 0);
+        LoopError err;
         #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
         for (size_t i = 0; i < m; ++i) {
             const string& fn = names[w0 + i];
@@ -196,9 +237,12 @@ void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo,
                 cout << "Missed file: " << fn << endl;           // :557
                 continue;
             }
-            w.seqs[i] = mkcli::read_genome_concat(fn);
-            w.ok[i] = w.seqs[i].size() >= ix.k;                  // :569
+            err.run([&] {
+                w.seqs[i] = mkcli::read_genome_concat(fn);
+                w.ok[i] = w.seqs[i].size() >= ix.k;              // :569
+            });
         }
+        err.rethrow();
         return w;
     };
     future<Wave> next;
@@ -239,9 +283,13 @@ void index_file_of_file(Index& ix, const string& list) {
         // contiguous slices of the list per GPU, built concurrently; nested OpenMP teams parse
         omp_set_max_active_levels(2);
         const int per = max(1, ix.threads / (int)R);
+        LoopError err;
         #pragma omp parallel for num_threads((int)R) schedule(static, 1)
         for (size_t r = 0; r < R; ++r)
-            build_shard(ix, ix.shard[r], names, r * names.size() / R, (r + 1) * names.size() / R, per, kept[r]);
+            err.run([&] {
+                build_shard(ix, ix.shard[r], names, r * names.size() / R, (r + 1) * names.size() / R, per, kept[r]);
+            });
+        err.rethrow();
     }
     for (auto& v : kept) ix.file_names.insert(ix.file_names.end(), v.begin(), v.end());
     ix.seal_shards();
@@ -313,12 +361,19 @@ void dump_disk(Index& ix, const string& path) {
     w.write(bloom.data(), bloom.size());
     w.write_zeros(bloom_bytes - window);
     w.write(ss.data(), ss.size() * 4);
-    w.close();
+    w.close();                                  // throws on a short write: no silent truncation
     // file_names is not part of the dump (quirk G4: the reference's `-i ... -e` crashes).  A
-    // side-car `<dump>.names` keeps them, one path per id; the dump itself stays byte-compatible.
-    if (!ix.file_names.empty()) {
-        ofstream names((path + ".names").c_str());
+    // side-car `<dump>.names` keeps them, one path per id, under a line that binds it to this
+    // dump; the dump itself stays byte-compatible.  Without names a stale side-car is removed.
+    const string side = path + ".names";
+    if (ix.file_names.size() == n && n) {
+        ofstream names(side.c_str());
+        names << kNamesMagic << names_token(ix.k, ix.h, ix.b, ix.threshold, ss, gs) << "\n";
         for (const string& s : ix.file_names) names << s << "\n";
+        names.close();
+        if (!names) throw runtime_error("cannot write " + side);
+    } else {
+        remove(side.c_str());
     }
 }
 
@@ -399,8 +454,18 @@ bool load_disk(Index& ix, const string& path) {
     ix.seal_shards();      // every shard already holds the whole Bloom table: the fold is a no-op
     ix.compressed_flag = false;                                   // :705
     if (exists_test(path + ".names")) {      // side-car written by our -d: makes `-i ... -e` work
-        vector<string> names = read_list(path + ".names");
-        if (names.size() == n) ix.file_names = names;
+        mkcli::LineReader side(path + ".names");
+        string first;
+        side.getline(first);
+        const string want = string(kNamesMagic) + names_token(ix.k, ix.h, ix.b, ix.threshold, ss, gs);
+        vector<string> names;
+        string name;
+        while (!side.eof()) {
+            side.getline(name);
+            if (!name.empty()) names.push_back(name);
+        }
+        if (first == want && names.size() == n) ix.file_names = names;
+        else cerr << "miekki: " << path << ".names does not belong to this dump: ignored" << endl;
     }
     return true;
 }
@@ -557,10 +622,14 @@ void ground_truth_all(Index& ix, map<uint32_t, vector<Candidate>>& per_genome) {
     for (auto& kv : per_genome) work.push_back({kv.first, &kv.second});
     vector<string> text(work.size());
     const int R = (int)ix.shard.size();
+    LoopError err;
     #pragma omp parallel for num_threads(R) schedule(dynamic, 1)
     for (size_t i = 0; i < work.size(); ++i)
-        text[i] = ground_truth(ix, ix.shard[(size_t)omp_get_thread_num() % ix.shard.size()],
-                               ix.file_names[work[i].first], *work[i].second);
+        err.run([&] {
+            text[i] = ground_truth(ix, ix.shard[(size_t)omp_get_thread_num() % ix.shard.size()],
+                                   ix.file_names[work[i].first], *work[i].second);
+        });
+    err.rethrow();
     for (const string& s : text) *ix.out << s;
     per_genome.clear();
 }
@@ -624,6 +693,7 @@ void query_file_of_file(Index& ix, const string& list) {
         const size_t m = min(wave, names.size() - w0);
         w.seqs.resize(m);
         w.ok.assign(m, 0);
+        LoopError err;
         #pragma omp parallel for num_threads(ix.threads) schedule(dynamic, 1)
         for (size_t i = 0; i < m; ++i) {
             const string& fn = names[w0 + i];
@@ -632,9 +702,12 @@ void query_file_of_file(Index& ix, const string& list) {
                 cout << "File problem" << endl;                  // :488
                 continue;
             }
-            w.seqs[i] = mkcli::read_genome_concat(fn);           // :491-497
-            w.ok[i] = w.seqs[i].size() >= ix.k;                  // :498
+            err.run([&] {
+                w.seqs[i] = mkcli::read_genome_concat(fn);       // :491-497
+                w.ok[i] = w.seqs[i].size() >= ix.k;              // :498
+            });
         }
+        err.rethrow();
         return w;
     };
     // wave i+1 is read and parsed while wave i is scored
@@ -714,7 +787,20 @@ void query_file_of_file_exact(Index& ix, const string& list) {
 
 }  // namespace
 
+static int run(int argc, char** argv);
+
+// A corrupt or truncated input, an unwritable dump: one line on stderr and exit code 1, never
+// std::terminate and never "The end" after a failed step.
 int main(int argc, char** argv) {
+    try {
+        return run(argc, argv);
+    } catch (const exception& e) {
+        cerr << "miekki: " << e.what() << endl;
+        return 1;
+    }
+}
+
+static int run(int argc, char** argv) {
     if (argc < 2) {
         help();
         exit(0);

@@ -780,8 +780,14 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     bool busy[2] = {false, false}, lists_busy[2] = {false, false};
     int rc = MK_OK;
     uint32_t tile_no = 0;
-    cudaEventRecord(slice_start, c->stream);
-    cudaEventRecord(lists_free[0], c->stream);
+    // event / stream-wait calls of the pipeline: the first failure ends the query with its text
+    auto ck = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == MK_OK)
+            rc = fail(c, MK_ERR_CUDA, std::string("query pipeline: ") + what + ": " + cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    ck(cudaEventRecord(slice_start, c->stream), "cudaEventRecord");
+    ck(cudaEventRecord(lists_free[0], c->stream), "cudaEventRecord");
     for (uint32_t first = 0; first < n && rc == MK_OK;) {
         uint32_t cnt = 0;
         uint64_t entries = 0;
@@ -813,23 +819,23 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
         auto sketch_tile = [&](size_t ti, int set) -> int {          // lists of reads [cut[ti], cut[ti+1])
             const uint32_t q0 = cut[ti];
             const uint32_t nq = cut[ti + 1] - q0;
-            if (lists_busy[set]) cudaStreamWaitEvent(c->sk_stream, lists_free[set], 0);   // last scan that read it
+            if (lists_busy[set]) ck(cudaStreamWaitEvent(c->sk_stream, lists_free[set], 0), "cudaStreamWaitEvent");   // last scan that read it
             c->bl_stream = c->sk_stream;
             c->bl_set = set;
             int r = build_lists(c, b, first + q0, nq, &L[set]);
             if (r == MK_OK) r = account_lists(c, L[set], nq, nullptr, c->sk_stream);
             c->bl_stream = nullptr;
             c->bl_set = 0;
-            cudaEventRecord(sketched[set], c->sk_stream);
-            return r;
+            ck(cudaEventRecord(sketched[set], c->sk_stream), "cudaEventRecord");
+            return r != MK_OK ? r : rc;
         };
         if (has_long) {
-            cudaStreamWaitEvent(c->stream, lists_free[0], 0);
-            rc = build_lists(c, b, first, cnt, &L[0]);
+            ck(cudaStreamWaitEvent(c->stream, lists_free[0], 0), "cudaStreamWaitEvent");
+            if (rc == MK_OK) rc = build_lists(c, b, first, cnt, &L[0]);
             if (rc == MK_OK) rc = account_lists(c, L[0], cnt, nullptr);
         } else {
-            cudaStreamWaitEvent(c->sk_stream, slice_start, 0);   // heap init etc. precede everything
-            rc = sketch_tile(0, 0);
+            ck(cudaStreamWaitEvent(c->sk_stream, slice_start, 0), "cudaStreamWaitEvent");   // heap init etc. precede everything
+            if (rc == MK_OK) rc = sketch_tile(0, 0);
         }
         if (rc != MK_OK) break;
         for (size_t ti = 0; ti + 1 < cut.size() && rc == MK_OK; ++ti, ++tile_no) {
@@ -841,37 +847,41 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
                 rc = sketch_tile(ti + 1, set ^ 1);
                 if (rc != MK_OK) break;
             }
-            if (!has_long) cudaStreamWaitEvent(c->stream, sketched[set], 0);
+            if (!has_long) ck(cudaStreamWaitEvent(c->stream, sketched[set], 0), "cudaStreamWaitEvent");
+            if (busy[s]) ck(cudaStreamWaitEvent(c->stream, done[s], 0), "cudaStreamWaitEvent");   // count tile s is free again
+            if (rc != MK_OK) break;
             if (c->n > 0) {
-                if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);     // count tile s is free again
                 Lists view = L[set];
                 const uint32_t rel = has_long ? q0 : 0;          // tile lists start at 0, slice lists at q0
                 rc = scan_reads(c, view, rel, nq, plan, tile[s]);
                 if (rc != MK_OK) break;
-                cudaEventRecord(scanned[s], c->stream);
-                cudaStreamWaitEvent(c->aux_stream, scanned[s], 0);
+            }
+            // an empty shard still passes the heap on and, as the last link, sorts it (:396)
+            if (c->n > 0 || finalize) {
+                ck(cudaEventRecord(scanned[s], c->stream), "cudaEventRecord");
+                ck(cudaStreamWaitEvent(c->aux_stream, scanned[s], 0), "cudaStreamWaitEvent");
                 {
                     PhaseTimer t(c, PH_TOPK, c->aux_stream);
                     launch_topk(tile[s], nq, c->n, c->first_id, c->d_sketch_size, c->d_genome_size, c->d_ratio, K,
                                 min_score, min_int, d_heap + (size_t)(first + q0) * K, d_hlen + first + q0, finalize,
                                 c->aux_stream);
                 }
-                cudaEventRecord(done[s], c->aux_stream);
+                ck(cudaEventRecord(done[s], c->aux_stream), "cudaEventRecord");
                 busy[s] = true;
                 c->stats.kernel_launches += 1;
             }
-            cudaEventRecord(lists_free[set], c->stream);         // this list set may be refilled
+            ck(cudaEventRecord(lists_free[set], c->stream), "cudaEventRecord");   // this list set may be refilled
             lists_busy[set] = true;
         }
         first += cnt;
     }
     for (int s = 0; s < 2; ++s)
-        if (busy[s]) cudaStreamWaitEvent(c->stream, done[s], 0);
+        if (busy[s]) ck(cudaStreamWaitEvent(c->stream, done[s], 0), "cudaStreamWaitEvent");
     {
         cudaError_t le = cudaGetLastError();
-        if (cudaStreamSynchronize(c->aux_stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
-            le != cudaSuccess)
-            rc = rc != MK_OK ? rc : fail(c, MK_ERR_CUDA, std::string("query pipeline: ") + cudaGetErrorString(le));
+        ck(cudaStreamSynchronize(c->aux_stream), "cudaStreamSynchronize(aux)");
+        ck(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+        ck(le, "kernel launch");
     }
     cudaStreamSynchronize(c->sk_stream);
     for (int s = 0; s < 2; ++s) {

@@ -11,6 +11,11 @@ struct SketchParams {
     uint64_t bloom_window;      // bytes of the Bloom table kept on the device
 };
 
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  The attribute is
+// per device and per function; the size already granted is remembered per (device, function)
+// under a mutex, so launches from several host threads / on several GPUs are safe.
+bool smem_optin(const void* func, size_t bytes);
+
 // ---- sketch.cu ------------------------------------------------------------------
 constexpr int KEY_TAG_BITS = 24;    // tagged sketch keys, see launch_sketch_dense
 // Dense path (genomes, long reads): sequences -> 2-bit planes -> per-bucket min key.

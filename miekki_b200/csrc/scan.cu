@@ -559,13 +559,9 @@ static int launch_scan_j(const ScanPlan& plan, const uint8_t* rows, uint64_t str
                          uint32_t n_genomes, const uint32_t* list, const uint64_t* list_off,
                          const uint32_t* list_len, uint32_t n_reads, uint32_t* counts,
                          uint32_t* work_counter, cudaStream_t st) {
-    static size_t configured = 0;
-    if (plan.smem > configured) {
-        if (cudaFuncSetAttribute(scan_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)plan.smem) != cudaSuccess)
-            return -1;
-        configured = plan.smem;
-    }
+    // The opt-in is a per-device attribute of the function: a process that drives several GPUs
+    // (`miekki --gpus N`, one host thread per shard) needs it on each of them.
+    if (!smem_optin(reinterpret_cast<const void*>(scan_kernel<J>), plan.smem)) return -1;
     const uint32_t tg = plan.tile_w / 32;
     const uint32_t n_groups = (n_genomes + 31) / 32;
     const uint32_t n_pad = n_groups * 32;

@@ -12,6 +12,9 @@
 //     to it (order-independent restatement of Miekki.cpp:295-299).
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -952,6 +955,23 @@ account_rows_kernel(const uint32_t* __restrict__ list_len, uint32_t n, uint32_t 
 
 // ---- launchers ---------------------------------------------------------------------
 
+bool smem_optin(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (getenv("MIEKKI_TEST_FAIL_SMEM_OPTIN")) return false;    // tests: the caller must report it, not launch
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = granted[{dev, func}];
+    if (bytes <= have) return true;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    have = bytes;
+    return true;
+}
+
 void launch_account_rows(const uint32_t* list_len, uint32_t n, uint32_t n_genomes, unsigned long long* stat,
                          cudaStream_t st) {
     if (!n) return;
@@ -1106,13 +1126,7 @@ int launch_sketch_reads(const uint8_t* chars, const uint64_t* coff, const uint64
     const size_t smem = sketch_reads_smem(max_len, p.k, &slots);
     if (slots > SPARSE_MAX_SLOTS) return -1;     // caller routes such reads to the dense path
     const uint32_t words = (uint32_t)((max_len + 15) / 16 + 2);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(sketch_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
-            return -2;
-        configured = smem;
-    }
+    if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sketch_reads_kernel), smem)) return -2;
     const unsigned grid = n_ids < 148u * 32u ? n_ids : 148u * 32u;
     // a long read owns most of an SM's shared memory: give it enough warps to hide latency
     const unsigned threads = slots >= 8192 ? 512u : slots >= 4096 ? 256u : 128u;

@@ -700,5 +700,56 @@ def test_errors(mk):
     with pytest.raises(mk.MiekkiError):
         ix.insert_sequences([b"ACGT"])      # shorter than k
     assert ix.n == 0
-    assert ix.query([b"ACGTACGTACGTACGTACGTACGTACGTACGTACGT"]) == [] or True
+    hits = ix.query([b"ACGTACGTACGTACGTACGTACGTACGTACGTACGT"])     # empty index: one empty hit list per read
+    assert len(hits) == 1 and len(hits[0]) == 0
     ix.close()
+
+
+def test_smem_optin_failure_is_reported(mk, monkeypatch):
+    """The ring scan needs > 48 KB of dynamic shared memory, granted per device by
+    cudaFuncSetAttribute (kernels.h: smem_optin).  When that fails the call must return an error
+    with a message -- not launch, not fall back; afterwards the same context works again."""
+    rng = np.random.default_rng(6)
+    k, h, N = 31, 8, 1500                                   # > 1,024 genomes: ring kernel
+    B = 1 << h
+    rows = rng.integers(0, 256, (B, N), dtype=np.uint8)
+    ss = rng.integers(1, B + 1, N).astype(np.uint32)
+    gs = rng.integers(0, 5_000_000, N).astype(np.uint64)
+    o = orc.Oracle(k=k, h=h, cap=N)
+    bloom = np.ones(len(o.bloom), np.uint8)
+    o.load(rows, gs, bloom, ss)
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.import_(rows, gs, bloom, ss)
+    read = rand_seq(rng, 900)
+    monkeypatch.setenv("MIEKKI_TEST_FAIL_SMEM_OPTIN", "1")
+    with pytest.raises(mk.MiekkiError, match="scan launch configuration failed"):
+        ix.query_counts([read])
+    monkeypatch.delenv("MIEKKI_TEST_FAIL_SMEM_OPTIN")
+    counts, surv = ix.query_counts([read])
+    oc, oa = o.counts(read)
+    assert surv[0] == oa and np.array_equal(counts[0], oc)
+    ix.close()
+
+
+def test_empty_last_shard_still_sorts_the_heap(mk, case_a):
+    """mk_query_chain with finalize on a shard that holds no genome: the chained heap must still
+    go through sort_heap (Miekki.cpp:396), as mk_topk_slot does."""
+    d, ix, genomes = case_a
+    a = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    a.insert_sequences(genomes)
+    empty = mk.Miekki(k=31, h=12, b=33, threshold=200)
+    empty.set_shard(len(genomes))
+    empty.bloom_set(a.bloom_get())
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    seqs = [x for _, x in reads]
+    for s in (200, 0):
+        heap = np.zeros((len(seqs), 10), mk.HIT_DTYPE)
+        lens = np.zeros(len(seqs), np.uint32)
+        ba, be = a.upload(seqs), empty.upload(seqs)
+        a.query_chain(ba, heap, lens, 10, 10, 0.5 * s, finalize=False)
+        empty.query_chain(be, heap, lens, 10, 10, 0.5 * s, finalize=True)
+        got = "".join(orc.format_hit_line(hd, heap[i, :lens[i]]) for i, (hd, _) in enumerate(reads))
+        assert got == open(os.path.join(d, "hits_s%d.txt" % s)).read()
+        ba.free(); be.free()
+    a.close()
+    empty.close()
