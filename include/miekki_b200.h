@@ -140,6 +140,14 @@ int mk_index_import_rows(mk_ctx *ctx, uint64_t row0, uint64_t nrows, const uint8
 int mk_index_import_end(mk_ctx *ctx, const uint64_t *genome_size, const uint8_t *bloom,
                         uint64_t bloom_bytes, const uint32_t *sketch_size);
 
+/* Miekki::merge_indexes, Miekki.cpp:901-910: appends the genomes of `other` after ours (ids
+ * mk_index_size(ctx) ...), with their statistics, and folds the two Bloom tables "ours wins where
+ * set" -- the reference leaves that as a TODO (:907).  The result equals one in-order build of
+ * both genome lists.  Both indexes must share k, h, fingerprint width and bloom_log2; they may
+ * live on different GPUs.  `other` is left unchanged and still owned by the caller (the reference
+ * deletes it, :908). */
+int mk_index_merge(mk_ctx *ctx, mk_ctx *other);
+
 /* Bloom bytes only (multi-GPU merge): the window the device keeps is the
  * first mk_bloom_window() bytes of the 2^b/8-byte table; bytes past it are never touched
  * for this k.  merge: dst byte = (dst != 0) ? dst : src  ("lowest rank wins"). */

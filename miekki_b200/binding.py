@@ -68,6 +68,7 @@ SIGNATURES = {
     "mk_index_stats": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "mk_index_export": (_i, [_vp, _vp, _vp, _vp, _u64, _vp]),
     "mk_index_import": (_i, [_vp, _u32, _vp, _u64, _vp, _vp, _u64, _vp]),
+    "mk_index_merge": (_i, [_vp, _vp]),
     "mk_bloom_reach": (_u64, [_u32, _u32]),
     "mk_bloom_window": (_u64, [_vp]),
     "mk_bloom_get": (_i, [_vp, _vp, _u64]),
@@ -277,6 +278,10 @@ class Miekki:
         bl = np.ascontiguousarray(bloom, np.uint8)
         self._ck(lib().mk_index_import(self._ctx, n, _ptr(rows), rows.strides[0], _ptr(gs), _ptr(bl),
                                        len(bl), _ptr(ss)))
+
+    def merge(self, other: "Miekki"):
+        """merge_indexes (Miekki.cpp:901): `other`'s genomes follow ours; Bloom tables folded."""
+        self._ck(lib().mk_index_merge(self._ctx, other._ctx))
 
     def export_rows(self, row0: int, nrows: int, out: np.ndarray | None = None, col0: int = 0) -> np.ndarray:
         """Rows [row0, row0+nrows) of the dump payload.  With `out` (uint8 [nrows, width]) this

@@ -116,7 +116,8 @@ struct OptionDoc {
     const char* text;
 };
 const OptionDoc kOptions[] = {
-    {"Input", "-i <dump>", "load an index written by -d (its k, h, b, s override the flags)"},
+    {"Input", "-i <dump>", "load an index written by -d (its k, h, b, s override the flags); repeat -i to merge "
+                           "several dumps, ids in the order given (then -d writes the merged index)"},
     {"Input", "-l <list>", "build an index from a file of genome FASTA paths (plain or gz), one per line"},
     {"Input", "-a <fasta>", "query every 2-line record (header, sequence) of a FASTA file"},
     {"Input", "-A <list>", "query whole files: each listed FASTA is one query"},
@@ -470,6 +471,38 @@ bool load_disk(Index& ix, const string& path) {
     return true;
 }
 
+// ---- merge: Miekki::merge_indexes, Miekki.cpp:901-910 ----------------------------------------
+// `-i a.gz -i b.gz ...`: the genomes of each further dump follow those already loaded, ids in
+// the order of the command line; the Bloom tables are folded (the reference's TODO at :907).
+// The result is the index one in-order build of all the genome lists would have given.
+bool merge_disk(Index& ix, const string& path) {
+    Index other;
+    other.threads = ix.threads;
+    other.device0 = ix.device0;
+    other.gpus = ix.gpus;
+    other.devices = ix.devices;
+    if (!load_disk(other, path)) return false;
+    if (other.k != ix.k || other.h != ix.h || other.b != ix.b || other.nbm != ix.nbm) {
+        cerr << "miekki: " << path << " was built with other -k / -h / -f / -b values: cannot merge" << endl;
+        return false;
+    }
+    const uint32_t n0 = ix.size(), n1 = other.size();
+    if (ix.shard.size() == 1 && other.shard.size() == 1) {
+        if (mk_index_merge(ix.shard[0], other.shard[0]) != MK_OK) die(ix.shard[0], "mk_index_merge");
+        mk_destroy(other.shard[0]);
+    } else {
+        // sharded over GPUs: the new columns stay where they were loaded, as further shards with
+        // the following ids; seal_shards folds the Bloom tables in shard (= id) order
+        ix.shard.insert(ix.shard.end(), other.shard.begin(), other.shard.end());
+    }
+    if (ix.file_names.size() == n0 && other.file_names.size() == n1)
+        ix.file_names.insert(ix.file_names.end(), other.file_names.begin(), other.file_names.end());
+    else
+        ix.file_names.clear();
+    ix.seal_shards();
+    return true;
+}
+
 // ---- query: Miekki::query_file, Miekki.cpp:426-483 -------------------------------------------
 struct ReadBatch {
     vector<string> heads, seqs;
@@ -806,6 +839,7 @@ static int run(int argc, char** argv) {
         exit(0);
     }
     string index_file, list_file, query_fa, query_list, output_file("out.txt"), index_dump;
+    vector<string> index_files;                  // every -i, in order (the first is loaded, the rest merged)
     uint64_t H = 17, core_number = 8, kmer_size = 31, bloom_size = 33, fingerprint_size = 3;
     double threshold = 200;
     bool exact_mode = false;
@@ -824,6 +858,7 @@ static int run(int argc, char** argv) {
     while ((c = getopt_long(argc, argv, "i:l:a:h:t:f:k:s:b:o:ed:A:", longopts, nullptr)) != -1) {
         if (auto t = text_flags.find(c); t != text_flags.end()) {
             *t->second = optarg;
+            if (c == 'i') index_files.push_back(optarg);
         } else if (auto n = count_flags.find(c); n != count_flags.end()) {
             *n->second = (uint64_t)stoi(optarg);
         } else if (c == 's') {
@@ -850,7 +885,9 @@ static int run(int argc, char** argv) {
     ix.gpus = devices.empty() ? gpus : (int)devices.size();
     ix.devices = devices;
     if (!index_file.empty()) {
-        if (!load_disk(ix, index_file)) return 1;
+        if (!load_disk(ix, index_files[0])) return 1;
+        for (size_t i = 1; i < index_files.size(); ++i)
+            if (!merge_disk(ix, index_files[i])) return 1;
         ix.out = new ofstream(output_file.c_str());
         cout << "I output results in " << output_file << endl;
         cout << "Load sucessful" << endl;                        // main.cpp:193 (sic)

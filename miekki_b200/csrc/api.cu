@@ -1470,6 +1470,53 @@ int mk_index_import(mk_ctx* c, uint32_t n, const uint8_t* rows, uint64_t rows_st
     return import_end(c, genome_size, bloom, bloom_bytes, sketch_size);
 }
 
+// Miekki::merge_indexes, Miekki.cpp:901-910: the columns of `other` are appended to ours (the
+// reference leaves the Bloom merge as a TODO, :907, and never updates its statistics; here both
+// are done).  The result is the index a single in-order build of "our genomes, then theirs" gives:
+// fingerprints and statistics do not depend on the Bloom table, and a table byte belongs to the
+// smallest (genome id, bucket, probe) that maps to it (sketch.cu: bloom_commit_kernel), i.e. to
+// us whenever we have set it -- the same fold as across GPU shards.
+int mk_index_merge(mk_ctx* c, mk_ctx* other) {
+    if (!c || !other) return fail(c, MK_ERR_ARG, "mk_index_merge: NULL argument");
+    if (c == other) return fail(c, MK_ERR_ARG, "mk_index_merge: an index cannot be merged into itself");
+    // both contexts stay locked; address order avoids a deadlock between crossing merges
+    std::unique_lock<std::mutex> l1(c < other ? c->mu : other->mu), l2(c < other ? other->mu : c->mu);
+    if (c->k != other->k || c->h != other->h || c->b != other->b || c->nbm != other->nbm || c->nbmant != other->nbmant)
+        return fail(c, MK_ERR_ARG, "mk_index_merge: the two indexes were built with different -k / -h / -f / -b");
+    if (c->import_open || other->import_open) return fail(c, MK_ERR_STATE, "mk_index_merge: an import is in progress");
+    // everything queued on the other index must have landed before its memory is read from here
+    cudaSetDevice(other->device);
+    if (cudaStreamSynchronize(other->stream) != cudaSuccess)
+        return fail(c, MK_ERR_CUDA, "mk_index_merge: the other context's stream failed");
+    cudaSetDevice(c->device);
+    const uint32_t m = other->n;
+    if ((uint64_t)c->n + m > 0xFFFFFFFFull) return fail(c, MK_ERR_ARG, "mk_index_merge: more than 2^32 genomes");
+    if (m) {
+        TRY(ensure_capacity(c, c->n + m));
+        // rows travel in slabs (cudaMemcpyDefault: the two contexts may sit on different GPUs)
+        const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / other->stride);
+        TRY(reserve(c, c->misc, std::min<uint64_t>(slab, c->B) * other->stride));
+        for (uint64_t r0 = 0; r0 < c->B; r0 += slab) {
+            const uint64_t nr = std::min<uint64_t>(slab, c->B - r0);
+            CU(cudaMemcpyAsync(c->misc.p, other->rows + r0 * other->stride, nr * other->stride, cudaMemcpyDefault,
+                               c->stream));
+            launch_merge_planes(c->rows, c->stride, c->n, static_cast<const uint8_t*>(c->misc.p), other->stride, m,
+                                r0, nr, c->stream);
+            c->stats.kernel_launches += 1;
+        }
+        CU(cudaMemcpyAsync(c->d_sketch_size + c->n, other->d_sketch_size, (size_t)m * 4, cudaMemcpyDefault, c->stream));
+        CU(cudaMemcpyAsync(c->d_genome_size + c->n, other->d_genome_size, (size_t)m * 8, cudaMemcpyDefault, c->stream));
+        CU(cudaMemcpyAsync(c->d_ratio + c->n, other->d_ratio, (size_t)m * 4, cudaMemcpyDefault, c->stream));
+    }
+    TRY(reserve(c, c->misc, c->window));
+    CU(cudaMemcpyAsync(c->misc.p, other->bloom, c->window, cudaMemcpyDefault, c->stream));
+    launch_bloom_merge(c->bloom, static_cast<uint8_t*>(c->misc.p), c->window, c->stream);
+    c->stats.kernel_launches += 1;
+    CU(cudaGetLastError());
+    c->n += m;           // the host mirrors of the statistics are completed on demand (host_stats)
+    return sync(c);
+}
+
 uint64_t mk_bloom_window(const mk_ctx* c) { return c ? c->window : 0; }
 
 // A canonical k-mer min(S, RC) is < M = 4^k - 4^(ceil(k/2)-1): a digit 3 of S comes from a 'T'

@@ -70,6 +70,10 @@ void launch_planes_to_bytes(const uint8_t* rows, uint64_t stride, uint64_t row0,
                             uint8_t* out, cudaStream_t st);
 void launch_bytes_to_planes(const uint8_t* in, uint64_t in_stride, uint64_t row0, uint64_t nrows, uint32_t n,
                             uint8_t* rows, uint64_t stride, cudaStream_t st);
+// index merge: plane rows [row0, row0 + nrows) of another index (n_src genomes, staged at `src` with
+// pitch src_stride) become columns col0 .. col0 + n_src - 1 of `rows`
+void launch_merge_planes(uint8_t* rows, uint64_t stride, uint32_t col0, const uint8_t* src, uint64_t src_stride,
+                         uint32_t n_src, uint64_t row0, uint64_t nrows, cudaStream_t st);
 // dense read sketch -> (bucket << 8 | fp) list of buckets that are non-empty and pass Bloom
 void launch_compact_list(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,
                          SketchParams p, const uint8_t* bloom, const uint32_t* read_ids,

@@ -754,6 +754,47 @@ bytes_to_planes_kernel(const uint8_t* __restrict__ in, uint64_t in_stride, uint6
     }
 }
 
+// Index merge (Miekki::merge_indexes, Miekki.cpp:901-906: the rows of the other index are appended
+// column-wise): the n_src genomes of `src` (plane rows [row0, row0 + nrows) of the other index,
+// staged with pitch src_stride) become columns col0 .. col0 + n_src - 1 of `rows`.  One thread per
+// (row, destination group): a destination group takes its bits from two neighbouring source
+// groups, funnel-shifted by col0 % 32; the first group keeps the genomes that are already there,
+// columns past the last source genome stay all ones (255 = empty, Miekki.cpp:29).
+__global__ void __launch_bounds__(256)
+merge_planes_kernel(uint8_t* __restrict__ rows, uint64_t stride, uint32_t col0, const uint8_t* __restrict__ src,
+                    uint64_t src_stride, uint32_t n_src, uint64_t row0, uint64_t nrows) {
+    const uint32_t g0 = col0 >> 5, g1 = (col0 + n_src - 1) >> 5, sh = col0 & 31u;
+    const uint32_t dst_groups = g1 - g0 + 1, src_groups = (n_src + 31) >> 5;
+    const uint64_t total = nrows * dst_groups;
+    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / dst_groups;
+        const uint32_t j = (uint32_t)(i % dst_groups);          // source group aligned with this one
+        #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint8_t* sp = src + r * src_stride + (half ? (src_stride >> 1) : 0);
+            const uint4 hi = j < src_groups ? *reinterpret_cast<const uint4*>(sp + 16ull * j) : ones;
+            uint4* q = plane_ptr(rows, stride, row0 + r, g0 + j, half);
+            uint4 v = hi;
+            if (sh) {
+                uint4 lo;
+                if (j) {
+                    lo = *reinterpret_cast<const uint4*>(sp + 16ull * (j - 1));
+                } else {
+                    // genomes already in the first group: its bits below sh, moved to the top of
+                    // the word the funnel shift takes them from
+                    const uint4 old = *q;
+                    lo = make_uint4(old.x << (32 - sh), old.y << (32 - sh), old.z << (32 - sh), old.w << (32 - sh));
+                }
+                v = make_uint4(__funnelshift_l(lo.x, hi.x, sh), __funnelshift_l(lo.y, hi.y, sh),
+                               __funnelshift_l(lo.z, hi.z, sh), __funnelshift_l(lo.w, hi.w, sh));
+            }
+            *q = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 compact_list_kernel(const unsigned long long* __restrict__ anc, const uint8_t* __restrict__ fp,
                     SketchParams p, const uint8_t* __restrict__ bloom,
@@ -1094,6 +1135,14 @@ void launch_bytes_to_planes(const uint8_t* in, uint64_t in_stride, uint64_t row0
     const uint64_t total = nrows * ((n + 31) / 32);
     bytes_to_planes_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, st>>>(in, in_stride, row0, nrows, n, rows,
                                                                           stride);
+}
+
+void launch_merge_planes(uint8_t* rows, uint64_t stride, uint32_t col0, const uint8_t* src, uint64_t src_stride,
+                         uint32_t n_src, uint64_t row0, uint64_t nrows, cudaStream_t st) {
+    if (!nrows || !n_src) return;
+    const uint64_t total = nrows * (((col0 + n_src - 1) >> 5) - (col0 >> 5) + 1);
+    merge_planes_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, st>>>(rows, stride, col0, src, src_stride, n_src,
+                                                                       row0, nrows);
 }
 
 void launch_compact_list(const unsigned long long* anc, const uint8_t* fp, uint32_t n_seq,

@@ -183,6 +183,28 @@ int mk_index_import_end(mk_ctx *c, const uint64_t *genome_size, const uint8_t *b
     return MK_OK;
 }
 
+/* Miekki.cpp:901-906 (columns appended) + the Bloom fold of SURVEY.md 8e (ours wins where set) */
+int mk_index_merge(mk_ctx *c, mk_ctx *other) {
+    if (!c || !other || c == other) return fail(c, MK_ERR_ARG, "mk_index_merge: bad argument");
+    if (c->k != other->k || c->h != other->h || c->b != other->b)
+        return fail(c, MK_ERR_ARG, "mk_index_merge: the two indexes were built with different -k / -h / -f / -b");
+    pthread_mutex_lock(&g_mu);
+    const uint32_t n = mko_index_n(c->ix), m = mko_index_n(other->ix), ocap = mko_index_cap(other->ix);
+    ensure_cap(c, n + m);
+    const uint32_t cap = mko_index_cap(c->ix);
+    for (uint64_t r = 0; r < c->B; ++r)
+        memcpy(mko_index_rows(c->ix) + r * cap + n, mko_index_rows(other->ix) + r * ocap, m);
+    memcpy(mko_index_sketch_size(c->ix) + n, mko_index_sketch_size(other->ix), (size_t)m * 4);
+    memcpy(mko_index_genome_size(c->ix) + n, mko_index_genome_size(other->ix), (size_t)m * 8);
+    uint8_t *mine = mko_index_bloom(c->ix);
+    const uint8_t *theirs = mko_index_bloom(other->ix);
+    for (uint64_t i = 0; i < c->window; ++i)
+        if (!mine[i]) mine[i] = theirs[i];
+    mko_index_set_n(c->ix, n + m);
+    pthread_mutex_unlock(&g_mu);
+    return MK_OK;
+}
+
 uint64_t mk_bloom_window(const mk_ctx *c) { return c->window; }
 int mk_bloom_get(mk_ctx *c, uint8_t *dst, uint64_t n) {
     memcpy(dst, mko_index_bloom(c->ix), n);

@@ -177,6 +177,27 @@ def test_loads_reference_style_dump(cli, tmp_path, devices):
     assert r.returncode != 0
 
 
+@pytest.mark.parametrize("devices", ["0", "0,0"])
+def test_merge_of_two_dumps_equals_one_build(cli, tmp_path, devices):
+    H.merge_scenario(cli, tmp_path, devices)
+
+
+def test_unreadable_input_is_an_error_not_a_crash(cli, tmp_path):
+    """A genome file that is not what its gzip header promises: `miekki: ...` on stderr and exit
+    code 1 (the reader's exception may not escape an OpenMP region or a std::async task)."""
+    import gzip
+    good = gzip.compress(b">g\n" + b"ACGT" * 5000 + b"\n")
+    (tmp_path / "bad.fa.gz").write_bytes(good[:200] + bytes(300))
+    (tmp_path / "list.txt").write_text(str(tmp_path / "bad.fa.gz") + "\n")
+    r = subprocess.run([cli, "-l", str(tmp_path / "list.txt"), "-k", "31", "-h", "10", "-o", str(tmp_path / "o.txt")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "miekki:" in r.stderr and "The end" not in r.stdout
+    # a dump that cannot be written (its directory does not exist) fails the run as well
+    r = subprocess.run([cli, "-l", "list.txt", "-k", "31", "-h", "10", "-d", str(tmp_path / "nodir" / "x.gz"),
+                        "-o", str(tmp_path / "o.txt")], cwd=D, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "miekki:" in r.stderr and "The end" not in r.stdout
+
+
 def test_messages(cli, tmp_path):
     r = subprocess.run([cli], capture_output=True, text=True)
     assert r.returncode == 0 and "-l" in r.stdout                       # no arguments: help, exit(0)

@@ -123,6 +123,13 @@ def test_cli_sharded_outputs_are_identical(tmp_path, devices):
     assert outa.read_text() == open(os.path.join(d, "hits_A.txt")).read()
 
 
+@pytest.mark.parametrize("devices", ["0", "0,0"])
+def test_cli_merge_of_two_dumps_equals_one_build(tmp_path, devices):
+    """Row f4: mk_index_merge (one shard) / shard concatenation (several) behind `-i a -i b`."""
+    assert os.path.exists(CLI), "build the CLI first: make"
+    H.merge_scenario(CLI, tmp_path, devices)
+
+
 def test_cli_loads_reference_style_dump(tmp_path):
     """A dump written the way the reference writes it (gzip, full 1 GiB Bloom table) loads."""
     import gzip

@@ -753,3 +753,55 @@ def test_empty_last_shard_still_sorts_the_heap(mk, case_a):
         ba.free(); be.free()
     a.close()
     empty.close()
+
+
+@pytest.mark.parametrize("n_a,n_b", [(1, 1), (31, 2), (32, 40), (33, 100), (70, 31), (6, 8), (0, 5), (5, 0)])
+def test_index_merge_appends_columns_and_folds_bloom(mk, n_a, n_b):
+    """mk_index_merge (Miekki::merge_indexes, Miekki.cpp:901-910) on random fingerprint matrices:
+    the merged rows are [A | B] for every alignment of B inside the 32-genome plane groups,
+    statistics are concatenated, a Bloom byte is A's where A set it, else B's; B is unchanged;
+    and the merged index scores reads like the oracle loaded with the same payload."""
+    rng = np.random.default_rng(100 * n_a + n_b)
+    k, h = 31, 9
+    B = 1 << h
+    o = orc.Oracle(k=k, h=h, cap=max(1, n_a + n_b))
+    W = len(o.bloom)
+
+    def part(n):
+        rows = rng.integers(0, 256, (B, n), dtype=np.uint8)
+        ss = rng.integers(1, B + 1, n).astype(np.uint32)
+        gs = rng.integers(0, 5_000_000, n).astype(np.uint64)
+        bloom = np.where(rng.random(W) < 0.5, 1 << rng.integers(0, 8, W), 0).astype(np.uint8)
+        return rows, gs, bloom, ss
+
+    pa, pb = part(n_a), part(n_b)
+    a, b = mk.Miekki(k=k, h=h, threshold=0), mk.Miekki(k=k, h=h, threshold=0)
+    a.import_(*pa)
+    b.import_(*pb)
+    a.merge(b)
+    assert a.n == n_a + n_b and b.n == n_b
+    e = a.export()
+    rows = np.hstack([pa[0], pb[0]])
+    gs, ss = np.concatenate([pa[1], pb[1]]), np.concatenate([pa[3], pb[3]])
+    bloom = np.where(pa[2] != 0, pa[2], pb[2])
+    assert np.array_equal(e["rows"], rows)
+    assert np.array_equal(e["genome_size"], gs) and np.array_equal(e["sketch_size"], ss)
+    assert np.array_equal(e["bloom"][:W], bloom)
+    eb = b.export()
+    assert np.array_equal(eb["rows"], pb[0]) and np.array_equal(eb["bloom"][:W], pb[2])
+    o.load(rows, gs, bloom, ss)
+    reads = [rand_seq(rng, n) for n in (400, 1500)]
+    counts, surv = a.query_counts(reads)
+    hits = a.query(reads, 10, 1, 0.0)
+    for i, s in enumerate(reads):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa and np.array_equal(counts[i], oc)
+        oh = o.filter(oc, 10, 1, 0.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+    with pytest.raises(mk.MiekkiError):
+        a.merge(a)
+    other_h = mk.Miekki(k=k, h=h + 1, threshold=0)
+    with pytest.raises(mk.MiekkiError):
+        a.merge(other_h)
+    for x in (a, b, other_h):
+        x.close()
