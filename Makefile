@@ -13,7 +13,14 @@ CU := $(SRC)/api.cu $(SRC)/sketch.cu $(SRC)/scan.cu $(SRC)/topk.cu $(SRC)/exact.
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
 HDRS := $(SRC)/common.cuh $(SRC)/kernels.h include/miekki_b200.h
 
-all: $(LIB) $(CLI)
+TOOLS := benchmarks/make_dump
+
+all: $(LIB) $(CLI) $(TOOLS)
+
+# bench tooling (see the header of the source): index of a synthetic configuration as a dump file
+benchmarks/make_dump: benchmarks/make_dump.cpp include/miekki_b200.h $(LIB)
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ benchmarks/make_dump.cpp \
+	    -Lmiekki_b200 -lmiekki_b200 -Wl,-rpath,'$$ORIGIN/../miekki_b200'
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -31,6 +38,6 @@ oracle:
 	@if [ -d /root/reference ]; then $(MAKE) -C oracle ref; fi
 
 clean:
-	rm -rf build $(LIB) $(CLI)
+	rm -rf build $(LIB) $(CLI) $(TOOLS)
 
 .PHONY: all oracle clean

@@ -14,13 +14,23 @@ the bucket-major matrix -> threshold + bounded-heap top-k) over all reads.
             producer of the lists) / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline  the unmodified reference binary (oracle/_ref/Miekki, all host threads) on a
             bounded sample of the same reads against the same index
+  parity_checked  (untimed) the hit lists the timed path produced for sampled reads, compared
+            with the oracle's filter chained over every rank's counts (tests/ hold the full suite)
 
 N > 1 (torchrun, one rank per GPU): genome-sharded, weak scaling -- every rank holds its own
 10,000-genome shard (N x 10,000 genomes in total), every rank scans all reads against its
 shard, the bounded heap is chained through the ranks in ascending id order (NCCL send/recv
 of 24 MB), `value` = sum over ranks of the read kbp each scored per second.
 
-`--impl reference` times the reference's own CPU implementation on the same config.
+Extra blocks on the same line, measured in the same run (none of them inside the timed region
+of `value`): `c3_strong` (BASELINE config 3: 100,000 genomes at -h 17 in total, split over the
+ranks, 10 kbp reads with 5 % substitutions: strong scaling), `build` (config 4: Gbp/s of the
+sketch kernels, of the device-resident build and of host memory -> index), `exact` (config 5 in
+small: true k-mer intersections of the hits), `query_vs_genomes` (metric vs #genomes indexed).
+
+`--impl reference` times the reference's own CPU implementation on the same config; that
+process never loads libmiekki_b200.so (the index it queries is prepared by a separate helper
+process, benchmarks/make_dump).
 """
 from __future__ import annotations
 
@@ -43,6 +53,7 @@ if ROOT not in sys.path:
 SEED = 0x5EED_B200
 METRIC = "query_throughput_kbp_per_s"
 UNIT = "kbp/s"
+K_RESULTS = 10
 
 
 def parse_args():
@@ -62,8 +73,21 @@ def parse_args():
     ap.add_argument("--threshold", type=int, default=200)
     ap.add_argument("--cpu-reads", type=int, default=2_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-reads", type=int, default=64, help="reads whose hit lists are checked (untimed)")
     ap.add_argument("--build-e2e-genomes", type=int, default=64,
                     help="genomes pushed through the host->index path to report build Gbp/s e2e")
+    # extra blocks (BASELINE configs 3, 4, 5 and the metric's "vs #genomes indexed")
+    ap.add_argument("--no-extras", action="store_true", help="headline only")
+    ap.add_argument("--c3-genomes", type=int, default=100_000, help="genomes of config 3 in TOTAL (split over the ranks)")
+    ap.add_argument("--c3-reads", type=int, default=20_000)
+    ap.add_argument("--c3-read-len", type=int, default=10_000)
+    ap.add_argument("--c3-sub-rate", type=float, default=0.05)
+    ap.add_argument("--c3-hbits", type=int, default=17)
+    ap.add_argument("--c3-steps", type=int, default=2)
+    ap.add_argument("--exact-reads", type=int, default=2_000)
+    ap.add_argument("--exact-genomes", type=int, default=48, help="genomes intersected in the exact-mode block")
+    ap.add_argument("--sweep-genomes", default="100,1000,3000")
+    ap.add_argument("--sweep-reads", type=int, default=20_000)
     return ap.parse_args()
 
 
@@ -73,6 +97,19 @@ def workload_name(a):
             if a.sub_rate == 0 else
             "%d x %.1f Mbp genomes per GPU, -k %d -h %d, %d reads of %d bp with %.0f%% substitutions"
             % (a.genomes, a.genome_len / 1e6, a.k, a.hbits, a.reads, a.read_len, 100 * a.sub_rate))
+
+
+def config_of(a, world):
+    """The `config` object of the JSON line: identical for both arms."""
+    return {
+        "workload": workload_name(a), "genomes_per_gpu": a.genomes,
+        "genomes_indexed_total": a.genomes * world, "reads_per_step": a.reads,
+        "index_bytes_per_gpu": int((1 << a.hbits) * a.genomes),
+        "l2": "index >> L2 and rows are hit in hash order; no flush between steps",
+        "value_definition": "sum over ranks of read kbp scored against that rank's shard per second "
+                            "(weak scaling: job read throughput = value / n_gpus on an n_gpus x larger index)",
+        "sharding": "genomes (matrix columns), contiguous ascending ids per rank",
+    }
 
 
 def measured_peak():
@@ -85,14 +122,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """DRAM bytes per scan launch from the committed ncu capture, if any."""
+def ncu_traffic(kernel_config):
+    """DRAM bytes per algorithmic byte from a committed ncu capture of THIS configuration
+    (profiles/scan_traffic.json holds one entry per captured configuration), else None: a ratio
+    captured on another shape says nothing about this one (L2 serves part of the rows at -h 17)."""
     p = os.path.join(ROOT, "profiles", "scan_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            pass
+    try:
+        entries = json.load(open(p))
+    except Exception:
+        return None
+    if isinstance(entries, dict):
+        entries = [entries]
+    for e in entries:
+        if all(e.get("config", {}).get(k) == v for k, v in kernel_config.items()):
+            return e
     return None
 
 
@@ -149,20 +192,20 @@ class ClockSampler:
 
 # ---- synthetic reads (host) -------------------------------------------------------------
 
-def make_reads(a, n_genomes_total):
+def make_reads(n_reads, read_len, sub_rate, n_genomes_total, genome_len, long_reads=False):
     """Reads cut from the counter-based genomes; returns (uint8 [n, stride] pinned-friendly
-    array with 16-byte aligned rows, offsets u64[n+1])."""
+    array with 16-byte aligned rows, offsets u64[n], lens u64[n])."""
     from miekki_b200 import synth
-    stride = (a.read_len + 15) // 16 * 16
-    data = np.zeros((a.reads, stride), np.uint8)
+    stride = (read_len + 15) // 16 * 16
+    data = np.zeros((n_reads, stride), np.uint8)
     blk = 10_000
-    for b0 in range(0, a.reads, blk):
-        m = min(blk, a.reads - b0)
-        r, _, _ = synth.cb_reads(SEED, n_genomes_total, a.genome_len, m, a.read_len, a.sub_rate,
-                                 block=b0 // blk)
-        data[b0:b0 + m, :a.read_len] = r
-    offsets = (np.arange(a.reads, dtype=np.uint64) * np.uint64(stride))
-    lens = np.full(a.reads, a.read_len, np.uint64)
+    for b0 in range(0, n_reads, blk):
+        m = min(blk, n_reads - b0)
+        gen = synth.cb_reads_block if long_reads else synth.cb_reads
+        r, _, _ = gen(SEED, n_genomes_total, genome_len, m, read_len, sub_rate, block=b0 // blk)
+        data[b0:b0 + m, :read_len] = r
+    offsets = (np.arange(n_reads, dtype=np.uint64) * np.uint64(stride))
+    lens = np.full(n_reads, read_len, np.uint64)
     return data, offsets, lens
 
 
@@ -198,47 +241,164 @@ def scratch_dir(need_bytes):
     return None
 
 
-def reference_query(a, ix, reads_data, n_sample, steps, warmup, threads):
-    """Times oracle/_ref/Miekki (unmodified reference, -t threads) querying the first n_sample
-    reads against the SAME index, loaded through its own -i loader from a dump of the index
-    (load not timed: the binary reports query time separately, main.cpp:232-234)."""
+def write_sample_fasta(path, reads_data, read_len, n_sample):
+    with open(path, "wb") as f:
+        for i in range(n_sample):
+            f.write(b">r%d\n" % i + reads_data[i, :read_len].tobytes() + b"\n")
+
+
+def time_reference_binary(ref, dump, fa, workdir, threads, steps, warmup):
+    """`steps` timed runs of the unmodified binary (-i dump -a sample), `warmup` untimed ones
+    before; the time of a run is the binary's own second `elapsed time:` line = query_file
+    (main.cpp:232-234), so the index load is outside."""
+    times = []
+    for s in range(warmup + steps):
+        out = ref.run(["-i", dump, "-a", fa, "-o", os.path.join(workdir, "ref_out.txt"), "-t", threads],
+                      cwd=workdir, timeout=3600)
+        el = ref.elapsed(out)
+        if len(el) < 2:
+            return None
+        if s >= warmup:
+            times.append(el[1])
+    return times
+
+
+def reference_arm(a):
+    """--impl reference: oracle/_ref/Miekki (the unmodified reference, all host threads) on a
+    bounded sample of the config's reads against the config's full index.  This process maps
+    neither libmiekki_b200.so nor CUDA: the index file is written by benchmarks/make_dump, a
+    separate process (GPU build, bit-identical to a reference -t 1 build -- tests/test_gpu_*)."""
     from oracle import oracle as orc
+    nproc = os.cpu_count() or 1
+
+    def unavailable(why):
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+        return 0
+
     ref = orc.RefBinary()
     if not ref.available:
-        return None, "oracle/_ref/Miekki missing (run make -C oracle ref where /root/reference exists)"
-    n = ix.n
-    need = (1 << a.hbits) * n + (1 << 33) // 8 + 64 * n
+        return unavailable("oracle/_ref/Miekki missing (run make -C oracle ref where /root/reference exists)")
+    helper = os.path.join(ROOT, "benchmarks", "make_dump")
+    if not os.path.exists(helper):
+        return unavailable("benchmarks/make_dump missing (run make)")
+    need = (1 << a.hbits) * a.genomes + (1 << 33) // 8 + 64 * a.genomes
     d = scratch_dir(need)
     if d is None:
-        return None, "no scratch space for a %.1f GB dump" % (need / 1e9)
+        return unavailable("no scratch space for a %.1f GB dump" % (need / 1e9))
     try:
-        e = ix.export()
         dump = os.path.join(d, "index.dump")
-        write_dump(dump, a.k, a.hbits, 33, a.threshold, e["rows"], e["genome_size"], e["bloom"],
-                   e["sketch_size"])
-        del e
+        t0 = time.perf_counter()
+        r = subprocess.run([helper, str(a.k), str(a.hbits), "33", str(a.threshold), str(a.genomes),
+                            str(a.genome_len), str(SEED), "0", dump], capture_output=True, text=True, timeout=1800)
+        if r.returncode != 0:
+            return unavailable("make_dump failed: " + (r.stderr.strip().split("\n") or ["?"])[-1][:200])
+        prep_s = time.perf_counter() - t0
+        n_sample = min(a.cpu_reads, a.reads)
+        reads_np, _, _ = make_reads(min(a.reads, (n_sample + 9_999) // 10_000 * 10_000), a.read_len, a.sub_rate,
+                                    a.genomes, a.genome_len)
         fa = os.path.join(d, "sample.fa")
-        with open(fa, "wb") as f:
-            for i in range(n_sample):
-                f.write(b">r%d\n" % i + reads_data[i, :a.read_len].tobytes() + b"\n")
-        times = []
-        for s in range(warmup + steps):
-            out = ref.run(["-i", dump, "-a", fa, "-o", os.path.join(d, "ref_out.txt"), "-t", threads],
-                          cwd=d, timeout=3600)
-            el = ref.elapsed(out)
-            if len(el) < 2:
-                return None, "reference output had no timing lines"
-            if s >= warmup:
-                times.append(el[1])
-        return times, None
+        write_sample_fasta(fa, reads_np, a.read_len, n_sample)
+        times = time_reference_binary(ref, dump, fa, d, nproc, a.steps, a.warmup)
+        if times is None:
+            return unavailable("reference output had no timing lines")
     finally:
         shutil.rmtree(d, ignore_errors=True)
+    sample_kbp = n_sample * a.read_len / 1e3
+    v = sample_kbp * len(times) / sum(times)
+    sample = ("each step = the first %d of the config's %d reads (bounded sample: one full step takes minutes on "
+              "these cores), against the config's full %d-genome index; timed = the binary's own query time "
+              "(2nd `elapsed time:`), index load excluded; index file prepared by benchmarks/make_dump in a "
+              "separate process (%.0f s, untimed); this process loads no GPU code"
+              % (n_sample, a.reads, a.genomes, prep_s))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": config_of(a, 1),
+        "sample_reads_per_step": n_sample,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if a.gpus > 1:
+        line["note"] = ("the reference has no multi-GPU path: this is the same 1 x %d-genome CPU run at every N; "
+                        "the GPU arm's value at N > 1 is summed over N shards (an N x larger index), so a ratio "
+                        "of the two values is only meaningful at N = 1" % a.genomes)
+    print(json.dumps(line))
+    return 0
+
+
+# ---- parity of the timed path's output (untimed) ---------------------------------------------
+
+def check_hit_lists(ix, sample_seqs, sample_idx, got_hits, got_len, first_id, min_score, min_int,
+                    world, rank, dist, torch):
+    """Hit lists of the sampled reads as the timed path produced them (on the LAST rank:
+    got_hits [n, K] HIT_DTYPE, got_len [n]) against the oracle's filter (Miekki.cpp:376-397 with
+    libstdc++'s heap) chained in rank order over every rank's shared-fingerprint counts.
+    -> dict for the JSON line (identical on all ranks)."""
+    from oracle import oracle as orc
+    import miekki_b200
+    K = K_RESULTS
+    counts, _ = ix.query_counts(sample_seqs)                      # [m, n_local]
+    ss, gs = ix.stats_arrays()
+    m, n_local = counts.shape
+    firsts, widths = [first_id], [n_local]
+    if world > 1:
+        meta = torch.tensor([first_id, n_local], dtype=torch.int64, device="cuda")
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        firsts, widths = [int(x[0]) for x in metas], [int(x[1]) for x in metas]
+        wmax = max(widths)
+
+        def gather(x, dtype, cols):                               # shards may differ in width: pad
+            pad = np.zeros((x.shape[0], wmax), dtype)
+            pad[:, :cols] = x
+            t = torch.from_numpy(pad.view(np.uint8).reshape(-1)).cuda()
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return [o.cpu().numpy().view(dtype).reshape(x.shape[0], wmax)[:, :widths[r]] for r, o in enumerate(out)]
+        all_counts = gather(counts, np.uint32, n_local)
+        all_ss = [x[0] for x in gather(ss[None, :], np.uint32, n_local)]
+        all_gs = [x[0] for x in gather(gs[None, :], np.uint64, n_local)]
+    else:
+        all_counts, all_ss, all_gs = [counts], [ss], [gs]
+    ok, bad, floats_identical = True, [], True
+    if rank == world - 1:
+        for j, i in enumerate(sample_idx):
+            heap = np.zeros(K, miekki_b200.HIT_DTYPE)
+            n = 0
+            for r in range(world):
+                n = orc.filter_chain(np.ascontiguousarray(all_counts[r][j]), firsts[r], all_ss[r], all_gs[r], K,
+                                     min_score, min_int, heap, n, r == world - 1)
+            g = got_hits[i, :got_len[i]]
+            same = (n == got_len[i] and np.array_equal(g["genome"], heap["genome"][:n])
+                    and np.array_equal(g["matches"], heap["matches"][:n])
+                    and np.allclose(g["jaccard"], heap["jaccard"][:n], rtol=1e-6, atol=0)
+                    and np.allclose(g["intersection"], heap["intersection"][:n], rtol=1e-6, atol=0))
+            if same:
+                floats_identical = floats_identical and g.tobytes() == heap[:n].tobytes()
+            else:
+                ok = False
+                bad.append(int(i))
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0, 1 if floats_identical else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok, floats_identical = bool(flag[0].item()), bool(flag[1].item())
+    return {"reads": len(sample_idx), "ok": ok, "floats_bit_identical": floats_identical,
+            "against": "oracle filter (libstdc++ heap) chained in rank order over every rank's counts",
+            "mismatching_reads": bad[:8]}
 
 
 # ---- main ---------------------------------------------------------------------------------
 
 def main():
     a = parse_args()
+    if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0                               # rank 0 alone runs the CPU reference
+        return reference_arm(a)
+
     import torch
     import torch.distributed as dist
 
@@ -246,18 +406,28 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if a.impl == "reference" and rank != 0:
-        return 0                                   # rank 0 alone runs the CPU reference
-
     if not torch.cuda.is_available():
         print(json.dumps({"impl": a.impl, "error": "no CUDA device: this bench needs a B200"}))
         return 1
     torch.cuda.set_device(local)
-    if world > 1 and a.impl == "ours":
+    if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import miekki_b200
+    from miekki_b200 import sharded, synth
     nproc = os.cpu_count() or 1
+    K = K_RESULTS
+
+    # config-3 reads are cut on the host while the GPU builds and runs config 2
+    c3 = {"reads": None}
+    c3_on = not a.no_extras and a.c3_genomes >= world and a.c3_reads > 0
+
+    def gen_c3():
+        c3["reads"] = make_reads(a.c3_reads, a.c3_read_len, a.c3_sub_rate, a.c3_genomes, a.genome_len,
+                                 long_reads=True)
+    c3_thread = threading.Thread(target=gen_c3, daemon=True)
+    if c3_on:
+        c3_thread.start()
 
     # ---- setup (untimed): the index, like weights, is state ------------------------------
     ix = miekki_b200.Miekki(k=a.k, h=a.hbits, b=33, threshold=a.threshold, device=local)
@@ -265,162 +435,291 @@ def main():
     stream = torch.cuda.Stream(priority=-1)
     torch.cuda.set_stream(stream)
     ix.set_stream(stream.cuda_stream)
-    ix.reserve(a.genomes)
-    first = rank * a.genomes if a.impl == "ours" else 0
-    ix.set_shard(first)
-    t0 = time.perf_counter()
-    ix.stats_reset()
-    step_g = 128
-    insert_wall = 0.0           # wall clock of the insert calls alone (the generator is bench tooling)
-    for g0 in range(0, a.genomes, step_g):
-        m = min(step_g, a.genomes - g0)
-        b = ix.synth(SEED, first + g0, m, a.genome_len)
-        t1 = time.perf_counter()
-        ix.insert_batch(b)
-        insert_wall += time.perf_counter() - t1
-        b.free()
-    st_build = ix.stats()
-    build_wall = time.perf_counter() - t0
-    build_kernel_gbps = st_build["bases_sketched"] / max(st_build["sketch_ms"], 1e-9) / 1e6
 
-    total_genomes = a.genomes * (world if a.impl == "ours" else 1)
-    if world > 1 and a.impl == "ours":
-        # global Bloom filter: byte-wise "lowest rank wins" 
-        from miekki_b200 import sharded
-        w = ix.bloom_window()
+    def build_shard(index, first, count, genome_len):
+        """count synthetic genomes (ids first ..) generated on the device and inserted;
+        -> (stats of the build, wall seconds of the insert calls alone)."""
+        index.reserve(count)
+        index.set_shard(first)
+        index.stats_reset()
+        insert_wall = 0.0
+        for g0 in range(0, count, 128):
+            m = min(128, count - g0)
+            b = index.synth(SEED, first + g0, m, genome_len)
+            t1 = time.perf_counter()
+            index.insert_batch(b)
+            insert_wall += time.perf_counter() - t1
+            b.free()
+        return index.stats(), insert_wall
+
+    def merge_bloom_all(index):
+        """global Bloom filter: byte-wise "lowest rank wins" """
+        if world == 1:
+            return
+        w = index.bloom_window()
         mine = torch.empty(w, dtype=torch.uint8, device="cuda")
-        ix.bloom_get_ptr(mine.data_ptr(), w)
+        index.bloom_get_ptr(mine.data_ptr(), w)
         merged = sharded.merge_bloom(mine).contiguous()
-        ix.bloom_set_ptr(merged.data_ptr(), w)
-        del merged, mine
-        # whole-job build rate: all shards were built concurrently, the slowest rank sets the time
-        tb = torch.tensor([st_build["sketch_ms"], insert_wall * 1e3], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        build_all = {"kernel_gbp_per_s": world * st_build["bases_sketched"] / max(float(tb[0]), 1e-9) / 1e6,
-                     "device_resident_wall_gbp_per_s": world * st_build["bases_sketched"] / float(tb[1]) / 1e6}
-    else:
-        build_all = {"kernel_gbp_per_s": build_kernel_gbps,
-                     "device_resident_wall_gbp_per_s": st_build["bases_sketched"] / insert_wall / 1e9}
+        index.bloom_set_ptr(merged.data_ptr(), w)
 
-    reads_np, offsets, rlens = make_reads(a, total_genomes)
+    def build_rates(st, insert_wall):
+        """kernel and device-resident build Gbp/s, this rank and whole job (slowest rank sets the time)"""
+        mine = {"kernel_gbp_per_s": st["bases_sketched"] / max(st["sketch_ms"], 1e-9) / 1e6,
+                "device_resident_wall_gbp_per_s": st["bases_sketched"] / max(insert_wall, 1e-9) / 1e9}
+        if world == 1:
+            return mine, dict(mine)
+        tb = torch.tensor([st["sketch_ms"], insert_wall * 1e3, float(st["bases_sketched"])], dtype=torch.float64,
+                          device="cuda")
+        mx = tb.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tb.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        return mine, {"kernel_gbp_per_s": float(sm[2]) / max(float(mx[0]), 1e-9) / 1e6,
+                      "device_resident_wall_gbp_per_s": float(sm[2]) / max(float(mx[1]), 1e-9) / 1e6}
+
+    t0 = time.perf_counter()
+    first = rank * a.genomes
+    st_build, insert_wall = build_shard(ix, first, a.genomes, a.genome_len)
+    build_wall = time.perf_counter() - t0
+    merge_bloom_all(ix)
+    build_mine, build_all = build_rates(st_build, insert_wall)
+    total_genomes = a.genomes * world
+
+    reads_np, offsets, rlens = make_reads(a.reads, a.read_len, a.sub_rate, total_genomes, a.genome_len)
     read_kbp = a.reads * a.read_len / 1e3
-
-    if a.impl == "reference":
-        times, why = reference_query(a, ix, reads_np, min(a.cpu_reads, a.reads), a.steps,
-                                     min(a.warmup, 1), nproc)
-        if times is None:
-            print(json.dumps({"impl": "reference", "unavailable": why}))
-            return 0
-        sample_kbp = min(a.cpu_reads, a.reads) * a.read_len / 1e3
-        v = sample_kbp * len(times) / sum(times)
-        line = {
-            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": workload_name(a), "genomes_indexed": a.genomes,
-                       "reads_per_step": min(a.cpu_reads, a.reads)},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "reference",
-                             "sample": "first %d of the %d reads per step, against the full %d-genome index "
-                                       "(built on the GPU, bit-identical to a reference build, loaded by the "
-                                       "reference's own -i loader; load not timed)"
-                                       % (min(a.cpu_reads, a.reads), a.reads, a.genomes)},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line))
-        return 0
-
-    # ---- our arm -------------------------------------------------------------------------
-    K = 10
-    min_int = 0.5 * a.threshold
-    pinned = torch.from_numpy(reads_np).pin_memory()
-    hits_host = torch.empty((a.reads, K * 24), dtype=torch.uint8).pin_memory()
-    nh_host = torch.empty(a.reads, dtype=torch.int32).pin_memory()
-    d_heap = torch.zeros((a.reads, K * 24), dtype=torch.uint8, device="cuda")
-    d_len = torch.zeros(a.reads, dtype=torch.int32, device="cuda")
-    resident = ix.upload_flat_ptr(pinned.data_ptr(), offsets, rlens)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from miekki_b200 import sharded
+    class Workload:
+        """One index + one read set: resident and end-to-end passes, timing, parity check."""
 
-    def run_resident(steps):
-        """`steps` passes over the reads already in HBM; hit lists stay in HBM."""
-        if world == 1:
-            for _ in range(steps):
-                ix.query_batch(resident, K, 10, min_int, fetch=False)
-        else:
-            # scan of step i+1 is in flight while step i's heap is chained through the ranks
-            sharded.pipelined_query(ix, (resident for _ in range(steps)), d_heap, d_len, K, 10, min_int)
+        def __init__(self, index, reads_np, offsets, rlens, min_int):
+            self.ix, self.min_int = index, float(min_int)
+            self.n = len(rlens)
+            self.offsets, self.rlens = offsets, rlens
+            self.reads_np = reads_np
+            self.pinned = torch.from_numpy(reads_np).pin_memory()
+            self.hits_host = torch.empty((self.n, K * 24), dtype=torch.uint8).pin_memory()
+            self.nh_host = torch.empty(self.n, dtype=torch.int32).pin_memory()
+            self.d_heap = torch.zeros((self.n, K * 24), dtype=torch.uint8, device="cuda")
+            self.d_len = torch.zeros(self.n, dtype=torch.int32, device="cuda")
+            self.resident = index.upload_flat_ptr(self.pinned.data_ptr(), offsets, rlens)
 
-    def run_e2e(steps):
-        """Same through host buffers: every step uploads its reads from pinned host memory and
-        brings the hit lists back to the host."""
-        if world == 1:
-            import ctypes as C
-            lib = miekki_b200.lib()
-            for _ in range(steps):
-                b = ix.upload_flat_ptr(pinned.data_ptr(), offsets, rlens)      # H2D of this step's reads
-                ix._ck(lib.mk_query_batch(ix._ctx, b._h, K, 10, float(min_int),
-                                          C.c_void_p(hits_host.data_ptr()), C.c_void_p(nh_host.data_ptr())))
-                b.free()
-            return
-        live = {}
+        def run_resident(self, steps):
+            """`steps` passes over the reads already in HBM; hit lists stay in HBM."""
+            if world == 1:
+                for _ in range(steps):
+                    self.ix.query_batch(self.resident, K, 10, self.min_int, fetch=False)
+            else:
+                # scan of step i+1 is in flight while step i's heap is chained through the ranks
+                sharded.pipelined_query(self.ix, (self.resident for _ in range(steps)), self.d_heap, self.d_len,
+                                        K, 10, self.min_int)
 
-        def uploads():
-            for i in range(steps):
-                live[i] = ix.upload_flat_ptr(pinned.data_ptr(), offsets, rlens)
-                yield live[i]
+        def run_e2e(self, steps):
+            """Same through host buffers: every step uploads its reads from pinned host memory and
+            brings the hit lists back to the host."""
+            if world == 1:
+                import ctypes as C
+                lib = miekki_b200.lib()
+                for _ in range(steps):
+                    b = self.ix.upload_flat_ptr(self.pinned.data_ptr(), self.offsets, self.rlens)   # H2D
+                    self.ix._ck(lib.mk_query_batch(self.ix._ctx, b._h, K, 10, self.min_int,
+                                                   C.c_void_p(self.hits_host.data_ptr()),
+                                                   C.c_void_p(self.nh_host.data_ptr())))
+                    b.free()
+                return
+            live = {}
 
-        def fetched(i):                                  # last rank: D2H of batch i's hit lists
-            hits_host.copy_(d_heap, non_blocking=True)
-            nh_host.copy_(d_len, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            def uploads():
+                for i in range(steps):
+                    live[i] = self.ix.upload_flat_ptr(self.pinned.data_ptr(), self.offsets, self.rlens)
+                    yield live[i]
 
-        sharded.pipelined_query(ix, uploads(), d_heap, d_len, K, 10, min_int, on_result=fetched,
-                                after_chain=lambda i: live.pop(i).free())   # its scan has run by then
+            def fetched(i):                              # last rank: D2H of batch i's hit lists
+                self.hits_host.copy_(self.d_heap, non_blocking=True)
+                self.nh_host.copy_(self.d_len, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
-    def timed(run, steps, warmup):
-        run(warmup)
-        barrier()
-        ix.stats_reset()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(stream)
-        run(steps)
-        torch.cuda.synchronize()                         # side / aux streams of the last step
-        ev1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        dev_ms = ev0.elapsed_time(ev1)
-        st = ix.stats()
-        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), st
+            sharded.pipelined_query(self.ix, uploads(), self.d_heap, self.d_len, K, 10, self.min_int,
+                                    on_result=fetched, after_chain=lambda i: live.pop(i).free())
 
+        def timed(self, run, steps, warmup):
+            run(warmup)
+            barrier()
+            self.ix.stats_reset()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            run(steps)
+            torch.cuda.synchronize()                     # side / aux streams of the last step
+            ev1.record(stream)
+            barrier()
+            wall = time.perf_counter() - t0
+            dev_ms = ev0.elapsed_time(ev1)
+            st = self.ix.stats()
+            t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0]), float(t[1]), st
+
+        def parity(self, n_sample, first_id):
+            """the hit lists of the LAST end-to-end step (hits_host / nh_host on the last rank)"""
+            n_sample = max(1, min(n_sample, self.n))
+            idx = np.unique(np.linspace(0, self.n - 1, n_sample).astype(np.int64))
+            L = int(self.rlens[0])
+            seqs = [self.reads_np[i, :L].tobytes() for i in idx]
+            got = self.hits_host.numpy().view(miekki_b200.HIT_DTYPE).reshape(self.n, K)
+            return check_hit_lists(self.ix, seqs, idx, got, self.nh_host.numpy().view(np.uint32), first_id, 10,
+                                   self.min_int, world, rank, dist, torch)
+
+        def close(self):
+            self.resident.free()
+
+    # ---- headline: config 2 ---------------------------------------------------------------
+    w2 = Workload(ix, reads_np, offsets, rlens, 0.5 * a.threshold)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_ms, st = timed(run_resident, a.steps, a.warmup)
+    dev_ms, wall_ms, st = w2.timed(w2.run_resident, a.steps, a.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_dev_ms, e2e_wall_ms, st_e2e = timed(run_e2e, a.steps, max(3, a.warmup))
+    e2e_dev_ms, e2e_wall_ms, st_e2e = w2.timed(w2.run_e2e, a.steps, max(3, a.warmup))
+    parity = w2.parity(a.parity_reads, first)
 
     # the index exceeds L2 (10.5 GB vs 126 MB) and rows are touched in hash order: no flush needed
     value = world * read_kbp * a.steps / (dev_ms / 1e3)
     e2e_value = world * read_kbp * a.steps / (e2e_wall_ms / 1e3)
     peak, peak_src = measured_peak()
     scan_gbs = st["scan_row_bytes"] / max(st["scan_ms"], 1e-9) / 1e6
-    traffic = ncu_traffic()
+    traffic = ncu_traffic({"h": a.hbits, "genomes": a.genomes, "read_len": a.read_len})
+    alg_per_launch = int(st["scan_row_bytes"] // max(1, st["scan_launches"]))
+
+    extras = {}
+
+    # ---- config 3: 100,000 genomes at -h 17 in total, 10 kbp reads with 5 % substitutions ----
+    if c3_on:
+        gfirst, gcount = sharded.shard_range(a.c3_genomes, rank, world)
+        ix3 = miekki_b200.Miekki(k=a.k, h=a.c3_hbits, b=33, threshold=a.threshold, device=local)
+        ix3.set_stream(stream.cuda_stream)
+        t0 = time.perf_counter()
+        st3b, wall3b = build_shard(ix3, gfirst, gcount, a.genome_len)
+        merge_bloom_all(ix3)
+        c3_build_s = time.perf_counter() - t0
+        _, c3_build_all = build_rates(st3b, wall3b)
+        c3_thread.join()
+        r3, o3, l3 = c3["reads"]
+        # -s 0: at -h 17 every 5 Mbp sketch is saturated, genome_size = 0 (quirk G2) and the default
+        # -s leaves every list empty (SURVEY.md 8d); -s 0 keeps the all-ties heap order in play
+        w3 = Workload(ix3, r3, o3, l3, 0.0)
+        d3_ms, _, st3 = w3.timed(w3.run_resident, a.c3_steps, 1)
+        _, e3_wall_ms, _ = w3.timed(w3.run_e2e, 1, 1)
+        par3 = w3.parity(16, gfirst)
+        c3_kbp = a.c3_reads * a.c3_read_len / 1e3
+        extras["c3_strong"] = {
+            "workload": "C3: %d x %.1f Mbp genomes in total at -h %d split over %d GPU(s) (%d on this rank), %d reads "
+                        "of %d bp with %.0f%% substitutions, -s 0" % (a.c3_genomes, a.genome_len / 1e6, a.c3_hbits,
+                                                                      world, gcount, a.c3_reads, a.c3_read_len,
+                                                                      100 * a.c3_sub_rate),
+            "scaling": "strong", "steps": a.c3_steps, "ms_per_step": d3_ms / a.c3_steps,
+            "job_kbp_per_s": c3_kbp * a.c3_steps / (d3_ms / 1e3),
+            "e2e_job_kbp_per_s": c3_kbp / (e3_wall_ms / 1e3),
+            "scan_gbs_algorithmic_this_rank": st3["scan_row_bytes"] / max(st3["scan_ms"], 1e-9) / 1e6,
+            "scan_frac_of_peak": st3["scan_row_bytes"] / max(st3["scan_ms"], 1e-9) / 1e6 / peak,
+            "phases_ms_per_step": {"read_sketch": st3["read_sketch_ms"] / a.c3_steps,
+                                   "scan": st3["scan_ms"] / a.c3_steps, "topk": st3["topk_ms"] / a.c3_steps},
+            "surviving_buckets_per_read": st3["scan_rows"] / max(1, a.c3_steps * a.c3_reads),
+            "build_s": c3_build_s, "build_all_ranks": c3_build_all,
+            "parity_checked": par3,
+        }
+        w3.close()
+        ix3.close()
+        del w3, ix3
+        torch.cuda.empty_cache()
+
+    # ---- config 5 in small: exact mode on the hits of a read sample (rank 0's shard) ----------
+    if not a.no_extras and a.exact_reads > 0 and rank == 0:
+        from oracle import oracle as orc
+        ne = min(a.exact_reads, a.reads)
+        seqs = [reads_np[i, :a.read_len].tobytes() for i in range(ne)]
+        t0 = time.perf_counter()
+        hits = ix.query(seqs, 5, 10, float(a.threshold))             # Miekki.cpp:741
+        per_genome = {}
+        for i, hh in enumerate(hits):
+            for g in hh["genome"]:
+                per_genome.setdefault(int(g), []).append(i)
+        genomes = sorted(g for g in per_genome if first <= g < first + a.genomes)[:a.exact_genomes]
+        ix.stats_reset()
+        pairs, t_exact, checked, exact_ok, kmers = 0, 0.0, 0, True, 0
+        for g in genomes:
+            rec = ix.synth(SEED, g, 1, a.genome_len)                 # the genome file's one record, in HBM
+            rb = ix.upload([seqs[i] for i in per_genome[g]])
+            t1 = time.perf_counter()
+            nB, inter, uni = ix.exact_batch(rec, rb)
+            t_exact += time.perf_counter() - t1
+            pairs += len(per_genome[g])
+            kmers += a.genome_len - a.k + 1
+            if checked < 2:                                          # the oracle redoes two genomes on the CPU
+                host = rec.download(0, a.genome_len)
+                oB, opairs = orc.exact([host], [seqs[i] for i in per_genome[g]], a.k)
+                exact_ok = exact_ok and oB == nB and [(int(x), int(y)) for x, y in zip(inter, uni)] == opairs
+                checked += 1
+            rec.free()
+            rb.free()
+        st_x = ix.stats()
+        extras["exact"] = {
+            "workload": "C5 in small: hits (top 5, -s %d) of the first %d reads, true k-mer intersection against %d of "
+                        "their genomes (5 Mbp each, resident in HBM)" % (a.threshold, ne, len(genomes)),
+            "pairs": pairs, "genomes": len(genomes),
+            "device_ms_per_genome": st_x["exact_ms"] / max(1, len(genomes)),
+            "call_ms_per_genome": 1e3 * t_exact / max(1, len(genomes)),
+            "pairs_per_s": pairs / max(t_exact, 1e-9),
+            "genome_kmers_per_s_device": kmers / max(st_x["exact_ms"], 1e-9) * 1e3,
+            "roofline": {"bound": "hbm", "kernel": "exact_insert_kernel",
+                         "algorithmic_bytes_per_genome": 8 * (a.genome_len - a.k + 1),
+                         "achieved": 8 * kmers / max(st_x["exact_ms"], 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": 8 * kmers / max(st_x["exact_ms"], 1e-9) / 1e6 / peak,
+                         "note": "8 B per genome k-mer (the key a sort or a set must move at least once) over the "
+                                 "device time of the whole exact phase; the kernel is a random-access insert, "
+                                 "bound by L2 atomics, not by streaming bandwidth"},
+            "parity_checked": {"genomes": checked, "ok": exact_ok, "against": "oracle (CPU sets) on the same pairs"},
+        }
+
+    # ---- metric vs #genomes indexed (rank 0, single GPU shapes) --------------------------------
+    if not a.no_extras and a.sweep_genomes and rank == 0:
+        sweep = []
+        for n_g in [int(x) for x in a.sweep_genomes.split(",") if x]:
+            ixs = miekki_b200.Miekki(k=a.k, h=a.hbits, b=33, threshold=a.threshold, device=local)
+            ixs.set_stream(stream.cuda_stream)
+            build_shard(ixs, 0, n_g, a.genome_len)
+            rs, os_, ls = make_reads(a.sweep_reads, a.read_len, 0.0, n_g, a.genome_len)
+            pin = torch.from_numpy(rs).pin_memory()
+            res = ixs.upload_flat_ptr(pin.data_ptr(), os_, ls)
+            for _ in range(2):
+                ixs.query_batch(res, K, 10, 0.5 * a.threshold, fetch=False)
+            torch.cuda.synchronize()
+            ixs.stats_reset()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(3):
+                ixs.query_batch(res, K, 10, 0.5 * a.threshold, fetch=False)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            sts = ixs.stats()
+            ms = ev0.elapsed_time(ev1) / 3
+            sweep.append({"genomes": n_g, "reads": a.sweep_reads, "ms_per_step": ms,
+                          "kbp_per_s": a.sweep_reads * a.read_len / 1e3 / (ms / 1e3),
+                          "scan_gbs_algorithmic": sts["scan_row_bytes"] / max(sts["scan_ms"], 1e-9) / 1e6})
+            res.free()
+            ixs.close()
+        sweep.append({"genomes": a.genomes, "reads": a.reads, "ms_per_step": dev_ms / a.steps,
+                      "kbp_per_s": value / world, "scan_gbs_algorithmic": scan_gbs})
+        extras["query_vs_genomes"] = sweep
 
     # ---- build throughput through the host path (extra, not the headline) ----------------
     build_e2e = None
     if a.build_e2e_genomes > 0 and rank == 0:
-        from miekki_b200 import synth
         m = a.build_e2e_genomes
         bx = miekki_b200.Miekki(k=a.k, h=a.hbits, b=33, threshold=a.threshold, device=local)
         bx.reserve(2 * m)
@@ -435,30 +734,46 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        times, why = reference_query(a, ix, reads_np, min(a.cpu_reads, a.reads), 1, 0, nproc)
+        from oracle import oracle as orc
+        ref = orc.RefBinary()
+        n_sample = min(a.cpu_reads, a.reads)
+        why, times = None, None
+        if not ref.available:
+            why = "oracle/_ref/Miekki missing (run make -C oracle ref where /root/reference exists)"
+        else:
+            need = (1 << a.hbits) * ix.n + (1 << 33) // 8 + 64 * ix.n
+            d = scratch_dir(need)
+            if d is None:
+                why = "no scratch space for a %.1f GB dump" % (need / 1e9)
+            else:
+                try:
+                    e = ix.export()
+                    dump = os.path.join(d, "index.dump")
+                    write_dump(dump, a.k, a.hbits, 33, a.threshold, e["rows"], e["genome_size"], e["bloom"],
+                               e["sketch_size"])
+                    del e
+                    fa = os.path.join(d, "sample.fa")
+                    write_sample_fasta(fa, reads_np, a.read_len, n_sample)
+                    times = time_reference_binary(ref, dump, fa, d, nproc, 1, 0)
+                    if times is None:
+                        why = "reference output had no timing lines"
+                finally:
+                    shutil.rmtree(d, ignore_errors=True)
         if times is None:
             cpu = {"value": None, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": "unavailable: " + why}
         else:
-            cpu = {"value": min(a.cpu_reads, a.reads) * a.read_len / 1e3 / times[0], "unit": UNIT,
+            cpu = {"value": n_sample * a.read_len / 1e3 / times[0], "unit": UNIT,
                    "cores": nproc, "kind": "reference",
                    "sample": "first %d of the %d reads, against the full %d-genome index (dumped from the GPU "
                              "build, loaded by the reference's -i loader; load not timed); query seconds = %.2f"
-                             % (min(a.cpu_reads, a.reads), a.reads, a.genomes, times[0])}
+                             % (n_sample, a.reads, a.genomes, times[0])}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {
-                "workload": workload_name(a), "genomes_per_gpu": a.genomes,
-                "genomes_indexed_total": total_genomes, "reads_per_step": a.reads,
-                "index_bytes_per_gpu": int((1 << a.hbits) * a.genomes),
-                "l2": "index >> L2 and rows are hit in hash order; no flush between steps",
-                "value_definition": "sum over ranks of read kbp scored against that rank's shard per second "
-                                    "(weak scaling: job read throughput = value / n_gpus on an n_gpus x larger index)",
-                "sharding": "genomes (matrix columns), contiguous ascending ids per rank",
-            },
+            "config": config_of(a, world),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] // a.steps),
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] // a.steps + (a.reads * (K * 24 + 4) if world > 1 else 0)),
@@ -466,26 +781,41 @@ def main():
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": scan_gbs, "peak": peak,
                          "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(st["scan_row_bytes"] // max(1, st["scan_launches"])),
+                         "algorithmic_bytes_per_launch": alg_per_launch,
                          "launch_ms": st["scan_ms"] / max(1, st["scan_launches"]),
-                         # ncu's DRAM bytes per algorithmic byte (one capture), scaled to this launch size
-                         "traffic": (int(traffic["dram_bytes_per_algorithmic_byte"] *
-                                         (st["scan_row_bytes"] // max(1, st["scan_launches"])))
+                         # DRAM bytes are not measured in this run (that needs ncu): the figure is the
+                         # committed capture of the same configuration scaled to this launch size, or null
+                         "traffic": (int(traffic["dram_bytes_per_algorithmic_byte"] * alg_per_launch)
                                      if traffic else None),
-                         "traffic_source": (traffic or {}).get("source")},
+                         "traffic_source": ((traffic or {}).get("source", "") +
+                                            " -- ncu capture of this configuration, scaled by the algorithmic "
+                                            "bytes of this run's launches; not measured in this run")
+                                           if traffic else "no ncu capture of this configuration is committed"},
+            "parity_checked": parity,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "phases_ms_per_step": {"read_sketch": st["read_sketch_ms"] / a.steps, "scan": st["scan_ms"] / a.steps,
                                    "topk": st["topk_ms"] / a.steps},
             "surviving_buckets_per_read": st["scan_rows"] / max(1, a.steps * a.reads),
-            "build": {"kernel_gbp_per_s": build_kernel_gbps, "setup_wall_s": build_wall,
-                      "e2e_host_to_index_gbp_per_s": build_e2e, "genomes": a.genomes,
-                      "all_ranks": build_all},
+            "build": {"workload": "C4 point: %d x %.1f Mbp genomes per GPU, -k %d -h %d (config 3 adds -h %d)"
+                                  % (a.genomes, a.genome_len / 1e6, a.k, a.hbits, a.c3_hbits),
+                      "kernel_gbp_per_s": build_mine["kernel_gbp_per_s"],
+                      "device_resident_wall_gbp_per_s": build_mine["device_resident_wall_gbp_per_s"],
+                      "setup_wall_s": build_wall,
+                      "e2e_host_to_index_gbp_per_s": build_e2e,
+                      "e2e_host_to_index_note": "%d inserts of %d distinct host genomes (pageable memory -> pinned "
+                                                "staging -> H2D -> sketch), second call timed"
+                                                % (a.build_e2e_genomes, min(a.build_e2e_genomes, 8)),
+                      "genomes": a.genomes, "all_ranks": build_all,
+                      "ncu": "profiles/ holds the per-kernel ncu details (issue slots, L2 %) of the build kernels"},
         }
+        line.update(extras)
         print(json.dumps(line))
+    ok = parity["ok"] and all(extras.get(k, {}).get("parity_checked", {}).get("ok", True) for k in extras
+                              if isinstance(extras.get(k), dict))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 0 if ok else 1
 
 
 if __name__ == "__main__":

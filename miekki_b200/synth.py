@@ -94,3 +94,27 @@ def cb_reads(seed: int, n_genomes: int, genome_len: int, n_reads: int, read_len:
     for r in range(n_reads):
         out[r] = substitute(cb_bases(seed, int(gs[r]), int(ps[r]), read_len), sub_rate, rng)
     return out, gs, ps
+
+
+def cb_reads_block(seed: int, n_genomes: int, genome_len: int, n_reads: int, read_len: int,
+                   sub_rate: float = 0.0, block: int = 0, chunk: int = 1000):
+    """Vectorised form of ``cb_reads`` for the long-read configurations (its own random stream:
+    ``default_rng(3_000_000 + block)``, a chunk of reads per numpy call instead of one read).
+    -> (uint8 [n_reads, read_len], source genome ids, offsets)."""
+    rng = np.random.default_rng(3_000_000 + block)
+    gs = rng.integers(n_genomes, size=n_reads)
+    ps = rng.integers(genome_len - read_len, size=n_reads)
+    out = np.empty((n_reads, read_len), np.uint8)
+    span = np.arange(read_len, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for r0 in range(0, n_reads, chunk):
+            m = min(chunk, n_reads - r0)
+            base = (np.uint64(seed & _M) + (gs[r0:r0 + m].astype(np.uint64) << np.uint64(40))
+                    + ps[r0:r0 + m].astype(np.uint64))
+            codes = (_splitmix64(base[:, None] + span[None, :]) >> np.uint64(62)).astype(np.uint8)
+            if sub_rate > 0:
+                hit = rng.random((m, read_len), dtype=np.float32) < sub_rate
+                shift = rng.integers(1, 4, (m, read_len), dtype=np.uint8)
+                codes = np.where(hit, (codes + shift) & 3, codes)
+            out[r0:r0 + m] = ACGT[codes]
+    return out, gs, ps
