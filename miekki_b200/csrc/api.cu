@@ -713,7 +713,8 @@ int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists*
 // reads per scan launch: bounded by the count tile buffer
 uint32_t scan_batch_reads(const mk_ctx* c, uint32_t n_reads) {
     const uint64_t n_pad = (c->n + 31) / 32 * 32;
-    const uint64_t budget = 1ull << 30;
+    uint64_t budget = 1ull << 30;
+    if (const char* e = getenv("MIEKKI_COUNT_TILE_BYTES")) budget = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests: many tiles
     uint64_t q = budget / (n_pad * 4);
     q = std::max<uint64_t>(1, std::min<uint64_t>(q, n_reads));
     return (uint32_t)q;

@@ -382,7 +382,7 @@ def test_random_index_and_long_reads_vs_oracle(mk, monkeypatch, narrow):
     _random_index_and_long_reads(mk)
 
 
-def _random_index_and_long_reads(mk):
+def _random_index_and_long_reads(mk, short_only=False):
     """40 genomes (more than one dense chunk), reads of 60 bp .. 40 kbp: the long ones take the
     dense read path, the short ones the shared-memory path."""
     rng = np.random.default_rng(11)
@@ -405,7 +405,8 @@ def _random_index_and_long_reads(mk):
     assert np.array_equal(e["genome_size"], o.genome_size)
     assert np.array_equal(e["bloom"][: len(o.bloom)], o.bloom[: len(e["bloom"])])
     reads = []
-    for n in (60, 200, 1000, 5000, 12000, 12350, 20000, 40000, 31, 32, 10):
+    for n in ((60, 200, 1000, 5000, 12000, 3000, 800, 31, 32, 10, 7000, 1500, 100) if short_only else
+              (60, 200, 1000, 5000, 12000, 12350, 20000, 40000, 31, 32, 10)):
         g = genomes[int(rng.integers(len(genomes)))]
         p = int(rng.integers(0, len(g) - n)) if len(g) > n else 0
         reads.append(g[p:p + n])
@@ -423,6 +424,19 @@ def _random_index_and_long_reads(mk):
         assert np.array_equal(hits[i]["matches"], oh["matches"])
         np.testing.assert_allclose(hits[i]["intersection"], oh["intersection"], rtol=REL_TOL)
     ix.close()
+
+
+@pytest.mark.parametrize("tile_bytes", ["1", "700", "2000"])
+def test_query_in_many_count_tiles_with_long_reads(mk, monkeypatch, tile_bytes):
+    """The query pipeline scans a batch in tiles of reads bounded by the count-tile buffer (1 GiB:
+    ~10,000 reads at 12,500 genomes) while the top-k of the previous tile runs beside it.
+    MIEKKI_COUNT_TILE_BYTES shrinks the buffer so that this small case crosses many tiles, both
+    for a batch with long reads (dense sketch, lists built at once) and without (sketched tile by
+    tile, one ahead of the scan)."""
+    monkeypatch.setenv("MIEKKI_COUNT_TILE_BYTES", tile_bytes)
+    _random_index_and_long_reads(mk)
+    monkeypatch.setenv("MIEKKI_SCAN_NARROW_GROUPS", "0")
+    _random_index_and_long_reads(mk, short_only=True)
 
 
 @pytest.mark.parametrize("narrow", ["32", "0"])
