@@ -27,8 +27,8 @@ pytestmark = pytest.mark.gpu
 SEED = 0x5EED_B200
 L = 5_000_000
 N3 = int(os.environ.get("MIEKKI_C3_GENOMES", "12500"))
-NG5 = int(os.environ.get("MIEKKI_C5_GENOMES", "50"))
-NR5 = int(os.environ.get("MIEKKI_C5_READS", "500"))
+NG5 = int(os.environ.get("MIEKKI_C5_GENOMES", "24"))
+NR5 = int(os.environ.get("MIEKKI_C5_READS", "300"))
 CLI = os.path.join(H.ROOT, "miekki_b200", "cli", "miekki")
 REF = orc.RefBinary()
 
