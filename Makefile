@@ -9,9 +9,9 @@ SRC := miekki_b200/csrc
 OBJ := build/obj
 LIB := miekki_b200/libmiekki_b200.so
 CLI := miekki_b200/cli/miekki
-CU := $(SRC)/api.cu $(SRC)/sketch.cu $(SRC)/scan.cu $(SRC)/topk.cu $(SRC)/exact.cu
+CU := $(SRC)/api.cu $(SRC)/sketch.cu $(SRC)/scan.cu $(SRC)/scan_tiled.cu $(SRC)/topk.cu $(SRC)/exact.cu
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
-HDRS := $(SRC)/common.cuh $(SRC)/kernels.h include/miekki_b200.h
+HDRS := $(SRC)/common.cuh $(SRC)/scan_common.cuh $(SRC)/kernels.h include/miekki_b200.h
 
 TOOLS := benchmarks/make_dump
 

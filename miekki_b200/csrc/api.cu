@@ -88,7 +88,7 @@ struct mk_ctx {
     uint64_t bloom_reach = 0;     // bytes [bloom_reach, window) can never be probed (mk_bloom_reach)
 
     DevBuf planeF, planeR, keys, fp, meta, list, list_len, list2, list_len2, counts, counts2, heap, heap_len, heap2,
-        heap_len2, misc, pages;
+        heap_len2, misc, pages, slist, slist2;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint32_t* d_work = nullptr;
@@ -585,7 +585,34 @@ struct Lists {
     uint32_t* list;
     uint64_t* list_off;     // device, n+1
     uint32_t* list_len;     // device, n
+    // tiled scan (scan_tiled.cu): the same lists sorted by bucket, each ending in sentinels
+    uint32_t* slist = nullptr;
+    uint64_t* soff = nullptr;   // device, n
 };
+
+// Which scan kernel serves a batch of reads?  The tiled kernel streams every row of the index once
+// per tile of reads instead of one row per (read, bucket) pair: worth it when the reads of a tile
+// together cover the bucket space a few times over (long reads at small -h), legal when the list
+// sort fits shared memory (-h <= 17) and no list exceeds the tiled counters.  MIEKKI_SCAN_TILED=0 /
+// 1 forces the choice where legal (tests, A/B measurements).
+constexpr uint64_t TILED_MAX_ENTRIES = 16380;
+bool want_tiled(const mk_ctx* c, const uint64_t* lens, uint32_t n) {
+    if (c->n == 0 || c->h > (uint32_t)TILED_MAX_H || c->h < 5 || n == 0) return false;
+    const char* e = getenv("MIEKKI_SCAN_TILED");
+    if (e && atoi(e) == 0) return false;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t ent = std::min<uint64_t>(lens[i] > c->k ? lens[i] - c->k : 0, c->B);
+        if (ent > TILED_MAX_ENTRIES) return false;
+        total += ent;
+    }
+    if (e && atoi(e) == 1) return true;
+    TiledPlan plan{};
+    if (tiled_plan(c->n, (int)c->h, c->sm_count, c->smem_optin, &plan) != 0) return false;
+    // expected (read, row) pairs per staged row: 0.9 = share of k-mers that end up as list entries
+    const double cover = 0.9 * (double)plan.tile_reads * ((double)total / n) / (double)c->B;
+    return cover >= 2.0 && c->n >= 768 && n >= 4 * plan.tile_reads;
+}
 constexpr uint64_t SPARSE_MAX_KMERS = 12288;   // 16384-slot table at load <= 0.75
 
 // small pinned staging areas for per-call metadata (two, alternating): uploads from them never
@@ -706,6 +733,33 @@ int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists*
     out->list = list;
     out->list_off = d_off;
     out->list_len = d_len;
+    out->slist = nullptr;
+    out->soff = nullptr;
+    if (want_tiled(c, b_len, n)) {
+        // sorted copies of the lists for the tiled scan: [64 sentinels | list 0 | list 1 | ...]
+        DevBuf& sbuf = c->bl_set ? c->slist2 : c->slist;
+        void* pin2 = nullptr;
+        TRY(pinned_meta(c, (size_t)n * 8 + 64, &pin2));
+        uint64_t* soff = static_cast<uint64_t*>(pin2);
+        uint64_t at = 64;
+        for (uint32_t i = 0; i < n; ++i) {
+            soff[i] = at;
+            at += sorted_list_capacity(std::min<uint64_t>(b_len[i] > c->k ? b_len[i] - c->k : 0, c->B));
+        }
+        if (at < (1ull << 32)) {
+            TRY(reserve(c, sbuf, at * 4 + (size_t)n * 8 + 64));
+            uint32_t* d_slist = static_cast<uint32_t*>(sbuf.p);
+            uint64_t* d_soff = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(sbuf.p) + ((at * 4 + 15) & ~(size_t)15));
+            CU(cudaMemcpyAsync(d_soff, soff, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaEventRecord(c->meta_ev[c->meta_flip], st));
+            c->stats.h2d_bytes += (size_t)n * 8;
+            launch_sort_lists(list, d_off, d_len, n, (int)c->h, d_slist, d_soff, st);
+            c->stats.kernel_launches += 2;
+            CU(cudaGetLastError());
+            out->slist = d_slist;
+            out->soff = d_soff;
+        }
+    }
     for (uint32_t i = 0; i < n; ++i) c->stats.bases_queried += b_len[i];
     return MK_OK;
 }
@@ -725,8 +779,18 @@ int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPl
                uint32_t* counts = nullptr) {
     PhaseTimer t(c, PH_SCAN);
     CU(cudaMemsetAsync(c->d_work, 0, 4, c->stream));
-    int r = launch_scan(plan, c->rows, c->stride, c->n, L.list, L.list_off + q0, L.list_len + q0, nq,
-                        counts ? counts : static_cast<uint32_t*>(c->counts.p), c->d_work, c->stream);
+    uint32_t* out = counts ? counts : static_cast<uint32_t*>(c->counts.p);
+    int r;
+    if (L.slist) {
+        TiledPlan tp{};
+        r = tiled_plan(c->n, (int)c->h, c->sm_count, c->smem_optin, &tp);
+        if (r == 0)
+            r = launch_scan_tiled(tp, c->rows, c->stride, c->n, (int)c->h, L.slist, L.soff + q0, nq, out, c->d_work,
+                                  c->stream);
+    } else {
+        r = launch_scan(plan, c->rows, c->stride, c->n, L.list, L.list_off + q0, L.list_len + q0, nq, out, c->d_work,
+                        c->stream);
+    }
     if (r != 0) return fail(c, MK_ERR_CUDA, "scan launch configuration failed");
     c->stats.kernel_launches += 1;
     c->stats.scan_launches += 1;
@@ -1108,7 +1172,8 @@ void mk_destroy(mk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     for (DevBuf* b : {&c->planeF, &c->planeR, &c->keys, &c->fp, &c->meta, &c->list, &c->list_len, &c->counts,
-                      &c->list2, &c->list_len2, &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc, &c->pages})
+                      &c->list2, &c->list_len2, &c->counts2, &c->heap, &c->heap_len, &c->heap2, &c->heap_len2, &c->misc, &c->pages,
+                      &c->slist, &c->slist2})
         if (b->p) cudaFree(b->p);
     for (void* p : {(void*)c->rows, (void*)c->d_sketch_size, (void*)c->d_genome_size, (void*)c->d_ratio, (void*)c->bloom,
                     (void*)c->owner, (void*)c->d_work, (void*)c->d_stat})

@@ -116,6 +116,31 @@ int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint
                 const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len,
                 uint32_t n_reads, uint32_t* counts, uint32_t* work_counter, cudaStream_t st);
 
+// ---- scan_tiled.cu ----------------------------------------------------------------
+// The scan for read batches that cover the bucket space densely (long reads at small -h): a CTA
+// owns a tile of reads x 1,024 genomes and streams every row of its genome tile through shared
+// memory once (TMA tensor copies), each staged row serving all reads of the tile that hit it.
+constexpr int TILED_MAX_H = 17;      // the list sort keeps one byte per bucket in shared memory
+struct TiledPlan {
+    int J, warps;           // reads per consumer warp, consumer warps
+    uint32_t tile_reads;    // J * warps
+    uint32_t n_gt;          // genome tiles (<= 32 groups of 32 genomes each, balanced)
+    uint32_t S;             // rows per ring stage (power of two)
+    int stages;
+    size_t smem;
+    int grid;
+};
+int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes, TiledPlan* out);
+// entries a sorted list of `entries` entries occupies with its sentinels
+uint32_t sorted_list_capacity(uint64_t entries);
+// list (bucket << 8 | fp, any order) -> slist + soff[q]: ascending buckets, then sentinels.  soff[q] >= 64:
+// the first 64 entries of slist are a block of sentinels.
+void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
+                       uint32_t* slist, const uint64_t* soff, cudaStream_t st);
+int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
+                      const uint32_t* slist, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
+                      uint32_t* work_counter, cudaStream_t st);
+
 // ---- topk.cu --------------------------------------------------------------------
 struct HitDev { uint32_t genome, matches; double jaccard, intersection; };
 // heap: n_reads x nresults HitDev, len: n_reads.  chained across shards (first_id offsets).

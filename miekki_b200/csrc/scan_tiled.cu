@@ -1,0 +1,413 @@
+// scan_tiled.cu -- the fingerprint scan for read batches that cover the bucket space densely
+// (long reads at small -h: BASELINE config 3, 10 kbp reads at -h 17), sm_100a.
+//
+// Same result as scan.cu (Miekki::query_sequences, Miekki.cpp:355-369):
+//     count[q][g] = #{ (bucket, fp) of read q : rows[bucket][g] == fp }.
+//
+// scan.cu fetches one index row per (read, bucket) pair: N bytes of DRAM per pair, no reuse
+// (ncu, round 1: DRAM bytes = 1.0004 x algorithmic, issue slots 27 % busy).  At -h 17 a 10 kbp
+// read touches 7 % of the 2^17 rows, so a few dozen reads together touch nearly all of them,
+// several times over: the reference itself fetches a row once per 201-read batch
+// (Miekki.cpp:362).  Here a CTA owns a tile of RT = NWARPS x J reads x 1,024 genomes and streams
+// ALL rows of its genome tile through shared memory once, in bucket order; every staged row is
+// used by each read of the tile that has that bucket (about 3 of 44 at config 3).  Rows arrive by
+// TMA: one 3-D tensor copy (cp.async.bulk.tensor, SASS UTMALDG) lands S rows x {planes 0-3,
+// planes 4-7} x 512 B in a stage of the mbarrier ring.  CTAs take work items in genome-tile-major
+// order, so the CTAs running at any time stream the same 134 MB slice of the index, which the
+// 126 MB L2 serves: DRAM sees the index about once per launch instead of once per read.
+//
+// Consumers: a warp owns J reads, its lanes the 32 groups (of 32 genomes) of the genome tile.
+// The reads' lists are sorted by bucket (sort_lists_kernel) and end in sentinels; a warp walks
+// them in lock step with the stages: entry (bucket, fp) -> row slot bucket - row0 of the stage ->
+// two 16-byte loads per lane (conflict free: lane l reads bytes 16 l ..), the XOR masks of fp
+// from a 256-entry table in shared memory (broadcast loads), eight 3-input logic ops, and the
+// 1-bit results go into the same carry-save vertical counters as scan.cu, four rows per fold.
+// A fold may straddle stages: the per-read position inside the block of four is kept across
+// stages (the switch into the loop below).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "scan_common.cuh"
+
+namespace mk {
+
+namespace {
+
+using namespace scan_detail;
+
+constexpr uint32_t T_FIRST = 1, T_LAST = 2, T_END = 8;
+constexpr uint32_t ROW_BYTES = 1024;          // a staged row: planes 0-3 of 32 groups, then planes 4-7
+constexpr uint32_t SENTINEL = 0xFFFFFFFFu;    // ends every sorted list: no bucket reaches 2^24
+constexpr uint32_t MASK_TAB_BYTES = 256 * 32;
+
+struct __align__(16) TileMeta {
+    uint32_t flags, rt, gt, row0;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// Lists of at most TILED_MAX_ENTRIES entries: 14 counter planes (counts < 16,384) instead of 16
+// keep the per-read state at 34 registers, so that a warp can own four reads.
+constexpr int T_TOP = 14;
+
+// one read of a warp: its counters, the block of four rows being gathered, its list cursor
+struct ReadState {
+    CountersT<T_TOP> cnt;
+    uint32_t x0, x1, x2, x3;      // equality planes of the rows gathered so far (r of them)
+    uint32_t chunk, pre;          // 32 list entries (one per lane) in use / already fetched for later
+    uint32_t ptr;                 // list offset of the next entry; its low 5 bits index `chunk`
+    uint32_t rn;                  // r << 16 | nblk
+};
+
+// next entry of the read if its bucket lies below the end of the stage
+__device__ __forceinline__ bool take(ReadState& s, uint32_t& e, uint32_t stage_end_e,
+                                     const uint32_t* __restrict__ lane_list) {
+    e = __shfl_sync(0xffffffffu, s.chunk, (int)s.ptr);            // source lane = ptr mod 32
+    if (e >= stage_end_e) return false;
+    if ((++s.ptr & 31u) == 0) {
+        s.chunk = s.pre;
+        s.pre = __ldg(lane_list + s.ptr + 32);                    // lists start on chunk boundaries
+    }
+    return true;
+}
+
+// "fingerprint == fp" for the lane's 32 genomes of the staged row (see scan.cu for the layout)
+__device__ __forceinline__ uint32_t match(uint32_t e, uint32_t row_base, uint32_t mask_tab) {
+    const uint32_t ra = row_base + ((e & 0xFFFFFF00u) << 2);      // + bucket * ROW_BYTES
+    const uint32_t ma = mask_tab + ((e & 0xFFu) << 5);
+    const uint4 a = lds128(ra), b = lds128(ra + 512u);
+    const uint4 m0 = lds128(ma), m1 = lds128(ma + 16u);
+    uint32_t x = a.x ^ m0.x;
+    x = (a.y ^ m0.y) & x;
+    x = (a.z ^ m0.z) & x;
+    x = (a.w ^ m0.w) & x;
+    x = (b.x ^ m1.x) & x;
+    x = (b.y ^ m1.y) & x;
+    x = (b.z ^ m1.z) & x;
+    x = (b.w ^ m1.w) & x;
+    return x;
+}
+
+// all entries of the read that fall into this stage; resumes inside the block of four
+__device__ __forceinline__ void run_stage(ReadState& s, uint32_t stage_end_e, uint32_t row_base, uint32_t mask_tab,
+                                          const uint32_t* __restrict__ lane_list) {
+    uint32_t e;
+    const uint32_t nblk = s.rn & 0xFFFFu;
+    switch (s.rn >> 16) {
+        for (;;) {
+            case 0:
+                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu); return; }
+                s.x0 = match(e, row_base, mask_tab);
+                // fall through
+            case 1:
+                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu) | (1u << 16); return; }
+                s.x1 = match(e, row_base, mask_tab);
+                // fall through
+            case 2:
+                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu) | (2u << 16); return; }
+                s.x2 = match(e, row_base, mask_tab);
+                // fall through
+            default:
+                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu) | (3u << 16); return; }
+                s.x3 = match(e, row_base, mask_tab);
+                s.cnt.add4(s.x0, s.x1, s.x2, s.x3, s.rn & 0xFFFFu);
+                ++s.rn;                                           // nblk: never carries into r (see T_TOP)
+        }
+    }
+    (void)nblk;
+}
+
+template <int J, int NWARPS>
+__global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
+scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ slist,
+                  const uint64_t* __restrict__ soff, uint32_t n_reads, uint32_t n_groups, uint32_t n_pad,
+                  uint32_t n_gt, uint32_t n_rt, uint32_t n_rows, uint32_t S, int stages, uint32_t* __restrict__ counts,
+                  uint32_t* __restrict__ work_counter) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t stage_bytes = S * ROW_BYTES;
+    uint8_t* ring = smem;
+    uint32_t* mask_tab = reinterpret_cast<uint32_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(mask_tab) + MASK_TAB_BYTES);
+    uint64_t* empty = full + stages;
+    TileMeta* meta = reinterpret_cast<TileMeta*>(empty + stages);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // mask_tab[fp][p] = (fp bit p) ? 0 : ~0
+    for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x)
+        mask_tab[i] = ((i >> 3) >> (i & 7)) & 1u ? 0u : 0xFFFFFFFFu;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr uint32_t RT = NWARPS * J;           // reads per tile
+
+    if (warp == NWARPS) {
+        // ---------------- producer: one thread, one tensor copy per stage ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t n_items = (uint64_t)n_gt * n_rt;
+            for (;;) {
+                const unsigned long long item = atomicAdd(work_counter, 1u);
+                if (item >= n_items) break;
+                // genome-tile major: CTAs that run together stream the same slice of the index
+                const uint32_t gt = (uint32_t)(item / n_rt), rt = (uint32_t)(item % n_rt);
+                const uint32_t glo = (uint32_t)(((uint64_t)gt * n_groups) / n_gt);
+                for (uint32_t row0 = 0; row0 < n_rows; row0 += S) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    TileMeta* m = meta + stage;
+                    m->flags = (row0 == 0 ? T_FIRST : 0u) | (row0 + S >= n_rows ? T_LAST : 0u);
+                    m->rt = rt;
+                    m->gt = gt;
+                    m->row0 = row0;
+                    mbar_arrive_expect_tx(full + stage, stage_bytes);
+                    tma_load_3d(ring + (size_t)stage * stage_bytes, &tmap, glo * 4u, 0u, row0, full + stage);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+            mbar_wait(empty + stage, phase ^ 1);
+            meta[stage].flags = T_END;
+            mbar_arrive(full + stage);
+        }
+    } else {
+        // ---------------- consumers: warp = J reads, lane = one group of 32 genomes ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        ReadState rs[J];
+        const uint32_t ring_addr = smem_u32(ring), mt_addr = smem_u32(mask_tab);
+        const uint32_t* lane_list = slist + lane;
+        for (;;) {
+            mbar_wait(full + stage, phase);
+            const TileMeta* m = meta + stage;
+            const uint32_t flags = m->flags;
+            if (flags & T_END) break;
+            const uint32_t row0 = m->row0, rt = m->rt, gt = m->gt;
+            if (flags & T_FIRST) {
+                #pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t q = rt * RT + warp * J + j;
+                    // reads past the end walk the sentinel block at the head of the buffer
+                    const uint32_t p0 = q < n_reads ? (uint32_t)soff[q] : 0u;
+                    rs[j].cnt.reset();
+                    rs[j].chunk = __ldg(lane_list + p0);
+                    rs[j].pre = __ldg(lane_list + p0 + 32);
+                    rs[j].ptr = p0;
+                    rs[j].rn = 0;
+                    rs[j].x0 = rs[j].x1 = rs[j].x2 = rs[j].x3 = 0;
+                }
+            }
+            const uint32_t stage_end_e = (row0 + S) << 8;
+            // address of the lane's 16 bytes of row `bucket` = row_base + bucket * ROW_BYTES
+            const uint32_t row_base = ring_addr + (uint32_t)stage * stage_bytes + lane * 16u - row0 * ROW_BYTES;
+            #pragma unroll
+            for (int j = 0; j < J; ++j) run_stage(rs[j], stage_end_e, row_base, mt_addr, lane_list);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);       // stage may be refilled
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+            if (flags & T_LAST) {
+                const uint32_t glo = (uint32_t)(((uint64_t)gt * n_groups) / n_gt);
+                const uint32_t ghi = (uint32_t)(((uint64_t)(gt + 1) * n_groups) / n_gt);
+                #pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t q = rt * RT + warp * J + j;
+                    // the rows still waiting in the block of four (absent ones count as no match)
+                    const uint32_t r = rs[j].rn >> 16;
+                    uint32_t nblk = rs[j].rn & 0xFFFFu;
+                    if (r) {
+                        rs[j].cnt.add4(rs[j].x0, r > 1 ? rs[j].x1 : 0u, r > 2 ? rs[j].x2 : 0u, 0u, nblk);
+                        ++nblk;
+                    }
+                    if (q < n_reads && glo + lane < ghi) {
+                        uint32_t P[32];
+                        rs[j].cnt.planes(nblk, P);
+                        transpose32(P);                       // P[i] = count of genome 32 (glo + lane) + i
+                        uint4* o = reinterpret_cast<uint4*>(counts + (uint64_t)q * n_pad + 32ull * (glo + lane));
+                        #pragma unroll
+                        for (int v = 0; v < 8; ++v) o[v] = make_uint4(P[4 * v], P[4 * v + 1], P[4 * v + 2], P[4 * v + 3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- lists sorted by bucket ------------------------------------------------------------------
+// One CTA per read: the entries are scattered into a dense byte table in shared memory (one byte
+// per bucket, 255 = absent: a fingerprint of 255 never enters a list) and read back in bucket
+// order; a run of sentinels follows.  Needs 2^h bytes of shared memory: -h <= 17.
+__global__ void __launch_bounds__(256)
+sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
+                  const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t n_buckets,
+                  uint32_t* __restrict__ slist, const uint64_t* __restrict__ soff) {
+    extern __shared__ __align__(16) uint8_t dense[];
+    __shared__ uint32_t warp_tot[8];
+    const uint32_t padded = (n_buckets + 15) & ~15u;
+    const uint32_t n_words = padded / 4;
+    // a warp owns a contiguous run of table words, walked 32 words (one per lane) at a time
+    const uint32_t seg = ((n_words + 7) / 8 + 31) & ~31u;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w0 = warp * seg, w1 = min(n_words, w0 + seg);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(dense);
+    auto present = [](uint32_t v) {            // bytes of the word that hold a fingerprint
+        uint32_t n = 0;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) n += ((v >> (8 * k)) & 0xFFu) != 0xFFu;
+        return n;
+    };
+    for (uint32_t q = blockIdx.x; q < n_reads; q += gridDim.x) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < padded / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(dense)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        __syncthreads();
+        const uint32_t L = list_len[q];
+        const uint32_t* src = list + list_off[q];
+        for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+            const uint32_t e = src[i];
+            dense[e >> 8] = (uint8_t)e;
+        }
+        __syncthreads();
+        uint32_t mine = 0;
+        for (uint32_t w = w0 + lane; w < w1; w += 32) mine += present(words[w]);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) warp_tot[warp] = mine;
+        __syncthreads();
+        uint32_t running = 0;
+        for (uint32_t w = 0; w < warp; ++w) running += warp_tot[w];
+        uint32_t* dst = slist + soff[q];
+        for (uint32_t wb = w0; wb < w1; wb += 32) {                  // uniform trip count over the warp
+            const uint32_t w = wb + lane;
+            const uint32_t v = w < w1 ? words[w] : 0xFFFFFFFFu;
+            const uint32_t cnt = present(v);
+            uint32_t incl = cnt;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            uint32_t at = running + incl - cnt;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t f = (v >> (8 * k)) & 0xFFu;
+                if (f != 0xFFu) dst[at++] = ((4 * w + k) << 8) | f;
+            }
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        // sentinels: up to the next multiple of 32 and two whole chunks more (the scan prefetches)
+        const uint32_t end = ((L + 31) & ~31u) + 64;
+        for (uint32_t i = L + threadIdx.x; i < end; i += blockDim.x) dst[i] = SENTINEL;
+    }
+}
+
+__global__ void fill_sentinels_kernel(uint32_t* p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = SENTINEL;
+}
+
+PFN_cuTensorMapEncodeTiled encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }();
+    return fn;
+}
+
+template <int J, int NWARPS>
+int launch_tiled_t(const TiledPlan& plan, const CUtensorMap& map, const uint32_t* slist, const uint64_t* soff,
+                   uint32_t n_reads, uint32_t n_genomes, uint32_t n_rows, uint32_t* counts, uint32_t* work_counter,
+                   cudaStream_t st) {
+    if (!smem_optin(reinterpret_cast<const void*>(scan_tiled_kernel<J, NWARPS>), plan.smem)) return -1;
+    const uint32_t n_groups = (n_genomes + 31) / 32;
+    const uint32_t n_rt = (n_reads + plan.tile_reads - 1) / plan.tile_reads;
+    const uint64_t items = (uint64_t)n_rt * plan.n_gt;
+    int grid = plan.grid;
+    if ((uint64_t)grid > items) grid = (int)items;
+    scan_tiled_kernel<J, NWARPS><<<grid, (NWARPS + 1) * 32, plan.smem, st>>>(
+        map, slist, soff, n_reads, n_groups, n_groups * 32, plan.n_gt, n_rt, n_rows, plan.S, plan.stages, counts,
+        work_counter);
+    return 0;
+}
+
+}  // namespace
+
+uint32_t sorted_list_capacity(uint64_t entries) { return (uint32_t)(((entries + 31) & ~31ull) + 64); }
+
+int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes, TiledPlan* out) {
+    if (n_genomes == 0 || h > TILED_MAX_H || h < 0) return -1;
+    // J reads per warp x NWARPS consumer warps: 34 registers of state per read (ReadState), 168
+    // registers per thread at 384 threads
+    out->J = 4;
+    out->warps = 11;
+    out->tile_reads = (uint32_t)(out->J * out->warps);
+    const uint32_t n_rows = 1u << h;
+    const uint32_t G = (n_genomes + 31) / 32;
+    out->n_gt = (G + 31) / 32;
+    uint32_t S = 32;
+    if (const char* e = getenv("MIEKKI_TILED_STAGE_ROWS")) S = (uint32_t)std::max(1, atoi(e));
+    while (S & (S - 1)) S &= S - 1;                       // power of two
+    S = std::min<uint32_t>(std::min<uint32_t>(S, 256), n_rows);
+    out->S = S;
+    const size_t fixed = MASK_TAB_BYTES + 1024 + 64 * (2 * sizeof(uint64_t) + sizeof(TileMeta));
+    int stages = (int)((smem_optin_bytes - fixed - 1024) / ((size_t)S * ROW_BYTES));
+    stages = std::min(stages, 64);
+    if (stages < 2) return -2;
+    out->stages = stages;
+    out->smem = (size_t)stages * S * ROW_BYTES + fixed;
+    out->grid = sm_count;
+    return 0;
+}
+
+void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
+                       uint32_t* slist, const uint64_t* soff, cudaStream_t st) {
+    if (!n_reads) return;
+    const uint32_t n_buckets = 1u << h;
+    const size_t smem = (n_buckets + 15) & ~(size_t)15;
+    if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sort_lists_kernel), smem)) return;
+    fill_sentinels_kernel<<<1, 64, 0, st>>>(slist, 64);            // the block reads past the end walk
+    const unsigned grid = n_reads < 148u * 8u ? n_reads : 148u * 8u;
+    sort_lists_kernel<<<grid, 256, smem, st>>>(list, list_off, list_len, n_reads, n_buckets, slist, soff);
+}
+
+int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
+                      const uint32_t* slist, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
+                      uint32_t* work_counter, cudaStream_t st) {
+    if (!n_reads) return 0;
+    PFN_cuTensorMapEncodeTiled encode = encode_fn();
+    if (!encode) return -2;
+    // the index as a 3-D tensor of 32-bit words: [row][half][word]; a box = S rows x 2 halves x 512 B
+    CUtensorMap map;
+    const uint32_t n_rows = 1u << h;
+    const cuuint64_t dims[3] = {stride / 8, 2, n_rows};
+    const cuuint64_t strides[2] = {stride / 2, stride};
+    const cuuint32_t box[3] = {128, 2, plan.S};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(rows), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -3;
+    return launch_tiled_t<4, 11>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
+}
+
+}  // namespace mk

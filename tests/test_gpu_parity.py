@@ -819,3 +819,51 @@ def test_index_merge_appends_columns_and_folds_bloom(mk, n_a, n_b):
         a.merge(other_h)
     for x in (a, b, other_h):
         x.close()
+
+
+@pytest.mark.parametrize("N,h", [(2100, 10), (40, 9), (1025, 5), (3300, 12)])
+def test_tiled_scan_equals_oracle_on_random_index(mk, monkeypatch, N, h):
+    """The tiled scan (scan_tiled.cu: TMA-staged rows shared by a tile of reads, lists sorted by
+    bucket) forced on with MIEKKI_SCAN_TILED=1, against the oracle's scoring of the same random
+    fingerprint matrix: several genome tiles with ragged last groups, more reads than one read
+    tile, lists from empty to thousands of entries, and the same answers as the ring kernel."""
+    rng = np.random.default_rng(1000 * h + N)
+    k = 31
+    B = 1 << h
+    rows = rng.integers(0, 256, (B, N), dtype=np.uint8)
+    ss = rng.integers(1, B + 1, N).astype(np.uint32)
+    gs = rng.integers(0, 5_000_000, N).astype(np.uint64)
+    o = orc.Oracle(k=k, h=h, cap=N)
+    bloom = np.ones(len(o.bloom), np.uint8)                 # every k-mer passes
+    o.load(rows, gs, bloom, ss)
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.import_(rows, gs, bloom, ss)
+    lens = [60, 31, 32, 10, 200, 1000, 5000, 9000, 16_000] + [int(x) for x in rng.integers(40, 3000, 130)]
+    reads = [rand_seq(rng, n) for n in lens]
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", "1")
+    monkeypatch.setenv("MIEKKI_SCAN_NARROW_GROUPS", "0")
+    st0 = ix.stats()
+    counts, surv = ix.query_counts(reads)
+    hits = ix.query(reads, 10, 1, 0.0)
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", "0")
+    counts_ring, surv_ring = ix.query_counts(reads)
+    assert np.array_equal(counts, counts_ring) and np.array_equal(surv, surv_ring)
+    for i, s in enumerate(reads):
+        if len(s) < k:
+            assert surv[i] == 0 and not counts[i].any() and len(hits[i]) == 0
+            continue
+        oc, oa = o.counts(s)
+        assert surv[i] == oa, (i, len(s))
+        assert np.array_equal(counts[i], oc), (i, len(s))
+        oh = o.filter(oc, 10, 1, 0.0)
+        assert np.array_equal(hits[i]["genome"], oh["genome"]) and np.array_equal(hits[i]["matches"], oh["matches"])
+    ix.close()
+
+
+def test_tiled_scan_on_case_a_hit_lines(mk, case_a, monkeypatch):
+    """Real sketches, real Bloom table, the reference binary's hit lines -- through the tiled scan."""
+    d, ix, _ = case_a
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", "1")
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    for s in (200, 0, 5000):
+        assert gpu_hit_lines(ix, reads, s, chunk=64) == open(os.path.join(d, "hits_s%d.txt" % s)).read()

@@ -33,8 +33,12 @@ CLI = os.path.join(H.ROOT, "miekki_b200", "cli", "miekki")
 REF = orc.RefBinary()
 
 
-def test_c3_shape_counts_and_all_ties_hit_lists():
+@pytest.mark.parametrize("tiled", ["0", "1"])
+def test_c3_shape_counts_and_all_ties_hit_lists(monkeypatch, tiled):
+    """tiled = 1 forces the tiled scan (scan_tiled.cu) for the reads it can take (lists of at most
+    16,380 entries), 0 the ring kernel; at this shape the tiled kernel is what a full batch runs."""
     import miekki_b200 as mk
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", tiled)
     K, Hb = 31, 17
     ix = mk.Miekki(k=K, h=Hb, threshold=200)
     ix.reserve(N3)
@@ -50,8 +54,12 @@ def test_c3_shape_counts_and_all_ties_hit_lists():
     # the sketch paths' boundary: 12,288 k-mers fit the shared-memory table, one more does not
     for n in (1000, 12_288 + K, 12_289 + K, 40_000):
         reads.append(synth.cb_bases(SEED, 3, 1234, n).tobytes())
-    counts, surv = ix.query_counts(reads)
-    hits = ix.query(reads, 10, 10, 0.0)                      # -s 0
+    # the 40 kbp read (39,969 list entries) is beyond the tiled kernel's counters: its own batch
+    counts, surv = ix.query_counts(reads[:-1])
+    hits = ix.query(reads[:-1], 10, 10, 0.0)                 # -s 0
+    c2, s2 = ix.query_counts(reads[-1:])
+    counts, surv = np.vstack([counts, c2]), np.concatenate([surv, s2])
+    hits = hits + ix.query(reads[-1:], 10, 10, 0.0)
     L_ = orc.lib()
     for i, s in enumerate(reads):
         fp, anc, _ = orc.sketch(s, K, Hb)
