@@ -586,7 +586,7 @@ struct Lists {
     uint64_t* list_off;     // device, n+1
     uint32_t* list_len;     // device, n
     // tiled scan (scan_tiled.cu): the same lists sorted by bucket, each ending in sentinels
-    uint32_t* slist = nullptr;
+    void* slist = nullptr;
     uint64_t* soff = nullptr;   // device, n
 };
 
@@ -736,20 +736,21 @@ int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists*
     out->slist = nullptr;
     out->soff = nullptr;
     if (want_tiled(c, b_len, n)) {
-        // sorted copies of the lists for the tiled scan: [64 sentinels | list 0 | list 1 | ...]
+        // sorted copies of the lists for the tiled scan: [128 sentinels | list 0 | list 1 | ...]
         DevBuf& sbuf = c->bl_set ? c->slist2 : c->slist;
         void* pin2 = nullptr;
         TRY(pinned_meta(c, (size_t)n * 8 + 64, &pin2));
         uint64_t* soff = static_cast<uint64_t*>(pin2);
-        uint64_t at = 64;
+        uint64_t at = 128;
         for (uint32_t i = 0; i < n; ++i) {
             soff[i] = at;
             at += sorted_list_capacity(std::min<uint64_t>(b_len[i] > c->k ? b_len[i] - c->k : 0, c->B));
         }
-        if (at < (1ull << 32)) {
-            TRY(reserve(c, sbuf, at * 4 + (size_t)n * 8 + 64));
-            uint32_t* d_slist = static_cast<uint32_t*>(sbuf.p);
-            uint64_t* d_soff = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(sbuf.p) + ((at * 4 + 15) & ~(size_t)15));
+        if (at < (1ull << 32)) {                   // the scan addresses entries with 32 bits
+            const size_t list_bytes = at * SORTED_ENTRY_BYTES;
+            TRY(reserve(c, sbuf, list_bytes + (size_t)n * 8 + 64));
+            void* d_slist = sbuf.p;
+            uint64_t* d_soff = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(sbuf.p) + ((list_bytes + 15) & ~(size_t)15));
             CU(cudaMemcpyAsync(d_soff, soff, (size_t)n * 8, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(c->meta_ev[c->meta_flip], st));
             c->stats.h2d_bytes += (size_t)n * 8;

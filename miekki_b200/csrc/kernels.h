@@ -133,12 +133,14 @@ struct TiledPlan {
 int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes, TiledPlan* out);
 // entries a sorted list of `entries` entries occupies with its sentinels
 uint32_t sorted_list_capacity(uint64_t entries);
-// list (bucket << 8 | fp, any order) -> slist + soff[q]: ascending buckets, then sentinels.  soff[q] >= 64:
-// the first 64 entries of slist are a block of sentinels.
+// list (bucket << 8 | fp, any order) -> slist + soff[q] (8-byte entries {bucket * 1024, fp * 32}):
+// ascending buckets, then sentinels.  soff[q] >= 128 and a multiple of 64: the first 128 entries of
+// slist are a block of sentinels.
+constexpr size_t SORTED_ENTRY_BYTES = 8;
 void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
-                       uint32_t* slist, const uint64_t* soff, cudaStream_t st);
+                       void* slist, const uint64_t* soff, cudaStream_t st);
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
-                      const uint32_t* slist, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
+                      const void* slist, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
                       uint32_t* work_counter, cudaStream_t st);
 
 // ---- topk.cu --------------------------------------------------------------------

@@ -59,35 +59,95 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-// Lists of at most TILED_MAX_ENTRIES entries: 14 counter planes (counts < 16,384) instead of 16
-// keep the per-read state at 34 registers, so that a warp can own four reads.
+// Vertical counters of the tiled kernel.  scan.cu's counters park one carry per level (28
+// registers for 14 planes); here only the two lowest levels have a parking slot and every fourth
+// block ripples its carry through the upper planes (20 logic ops per 16 rows), which brings a
+// read's whole state to 23 registers -- two reads per warp at 80 registers per thread, 24 warps
+// per SM.  14 planes: counts below 16,384, i.e. lists of at most TILED_MAX_ENTRIES entries.
 constexpr int T_TOP = 14;
+struct TileCounters {
+    uint32_t ones, twos, c[T_TOP], p2, p3;      // c[0], c[1] unused
+    __device__ __forceinline__ void reset() {
+        ones = twos = p2 = p3 = 0;
+        #pragma unroll
+        for (int l = 0; l < T_TOP; ++l) c[l] = 0;
+    }
+    // value = ones + 2 twos + 4 (c2 + [nblk & 1] p2) + 8 (c3 + [nblk & 2] p3) + sum_{l >= 4} 2^l c[l]
+    __device__ __forceinline__ void add4(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t nblk) {
+        uint32_t ta, tb, carry;
+        csa(ta, ones, ones, e0, e1);
+        csa(tb, ones, ones, e2, e3);
+        csa(carry, twos, twos, ta, tb);                    // weight 4
+        if ((nblk & 1u) == 0) { p2 = carry; return; }
+        csa(carry, c[2], c[2], p2, carry);                 // weight 8
+        if ((nblk & 2u) == 0) { p3 = carry; return; }
+        csa(carry, c[3], c[3], p3, carry);                 // weight 16
+        #pragma unroll
+        for (int l = 4; l < T_TOP; ++l) {
+            const uint32_t t = c[l] & carry;
+            c[l] ^= carry;
+            carry = t;
+        }
+    }
+    __device__ __forceinline__ void planes(uint32_t nblk, uint32_t (&P)[32]) {
+        uint32_t carry, nc;
+        P[0] = ones;
+        P[1] = twos;
+        csa(carry, P[2], c[2], (nblk & 1u) ? p2 : 0u, 0u);
+        csa(nc, P[3], c[3], (nblk & 2u) ? p3 : 0u, carry);
+        carry = nc;
+        #pragma unroll
+        for (int l = 4; l < T_TOP; ++l) {
+            P[l] = c[l] ^ carry;
+            carry = c[l] & carry;
+        }
+        #pragma unroll
+        for (int l = T_TOP; l < 32; ++l) P[l] = 0;
+    }
+};
+
+// A sorted list entry is two words, the shared-memory offsets the scan needs: {bucket * ROW_BYTES,
+// fp * 32}.  A warp keeps a window of 64 entries of each of its reads in shared memory (two chunks
+// of 32, one entry per lane and chunk); an entry fetch is one broadcast 8-byte load.  At most one
+// entry per row and read, so a stage of S <= 32 rows never takes more than one chunk.
+constexpr uint32_t WINDOW_BYTES = 64 * 8;
 
 // one read of a warp: its counters, the block of four rows being gathered, its list cursor
 struct ReadState {
-    CountersT<T_TOP> cnt;
-    uint32_t x0, x1, x2, x3;      // equality planes of the rows gathered so far (r of them)
-    uint32_t chunk, pre;          // 32 list entries (one per lane) in use / already fetched for later
-    uint32_t ptr;                 // list offset of the next entry; its low 5 bits index `chunk`
-    uint32_t rn;                  // r << 16 | nblk
+    TileCounters cnt;
+    uint32_t x0, x1, x2;          // equality planes of the rows gathered so far (r of them)
+    uint2 pre;                    // this lane's entry of the chunk after the two in the window
+    uint32_t ptr;                 // absolute index (in slist) of the next entry; lists start at multiples of 64
+    uint32_t rn;                  // r << 24 | nblk
 };
 
+// The window holds the chunk of `ptr` and the next one.  When ptr enters the newer chunk, the
+// prefetched chunk replaces the older one and the chunk after it is requested: once per 32
+// entries, out of line.
+__device__ __noinline__ uint2 refill(uint2 pre, uint32_t ptr, uint32_t win, const uint2* __restrict__ slist,
+                                     uint32_t lane) {
+    const uint32_t cur = ptr >> 5;
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(win + ((((cur + 1) & 1u) << 5 | lane) << 3)), "r"(pre.x), "r"(pre.y)
+                 : "memory");
+    pre = __ldg(slist + (((cur + 2) << 5) + lane));
+    __syncwarp();
+    return pre;
+}
+
 // next entry of the read if its bucket lies below the end of the stage
-__device__ __forceinline__ bool take(ReadState& s, uint32_t& e, uint32_t stage_end_e,
-                                     const uint32_t* __restrict__ lane_list) {
-    e = __shfl_sync(0xffffffffu, s.chunk, (int)s.ptr);            // source lane = ptr mod 32
-    if (e >= stage_end_e) return false;
-    if ((++s.ptr & 31u) == 0) {
-        s.chunk = s.pre;
-        s.pre = __ldg(lane_list + s.ptr + 32);                    // lists start on chunk boundaries
-    }
+__device__ __forceinline__ bool take(ReadState& s, uint2& e, uint32_t stage_end, uint32_t win,
+                                     const uint2* __restrict__ slist, uint32_t lane) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(win + ((s.ptr & 63u) << 3)));
+    if (lo >= stage_end) return false;
+    e = make_uint2(lo, hi);
+    if ((++s.ptr & 31u) == 0) s.pre = refill(s.pre, s.ptr, win, slist, lane);
     return true;
 }
 
 // "fingerprint == fp" for the lane's 32 genomes of the staged row (see scan.cu for the layout)
-__device__ __forceinline__ uint32_t match(uint32_t e, uint32_t row_base, uint32_t mask_tab) {
-    const uint32_t ra = row_base + ((e & 0xFFFFFF00u) << 2);      // + bucket * ROW_BYTES
-    const uint32_t ma = mask_tab + ((e & 0xFFu) << 5);
+__device__ __forceinline__ uint32_t match(uint2 e, uint32_t row_base, uint32_t mask_tab) {
+    const uint32_t ra = row_base + e.x, ma = mask_tab + e.y;
     const uint4 a = lds128(ra), b = lds128(ra + 512u);
     const uint4 m0 = lds128(ma), m1 = lds128(ma + 16u);
     uint32_t x = a.x ^ m0.x;
@@ -102,37 +162,34 @@ __device__ __forceinline__ uint32_t match(uint32_t e, uint32_t row_base, uint32_
 }
 
 // all entries of the read that fall into this stage; resumes inside the block of four
-__device__ __forceinline__ void run_stage(ReadState& s, uint32_t stage_end_e, uint32_t row_base, uint32_t mask_tab,
-                                          const uint32_t* __restrict__ lane_list) {
-    uint32_t e;
-    const uint32_t nblk = s.rn & 0xFFFFu;
-    switch (s.rn >> 16) {
-        for (;;) {
-            case 0:
-                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu); return; }
-                s.x0 = match(e, row_base, mask_tab);
-                // fall through
-            case 1:
-                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu) | (1u << 16); return; }
-                s.x1 = match(e, row_base, mask_tab);
-                // fall through
-            case 2:
-                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu) | (2u << 16); return; }
-                s.x2 = match(e, row_base, mask_tab);
-                // fall through
-            default:
-                if (!take(s, e, stage_end_e, lane_list)) { s.rn = (s.rn & 0xFFFFu) | (3u << 16); return; }
-                s.x3 = match(e, row_base, mask_tab);
-                s.cnt.add4(s.x0, s.x1, s.x2, s.x3, s.rn & 0xFFFFu);
-                ++s.rn;                                           // nblk: never carries into r (see T_TOP)
-        }
-    }
-    (void)nblk;
+__device__ __forceinline__ void run_stage(ReadState& s, uint32_t stage_end, uint32_t row_base, uint32_t mask_tab,
+                                          uint32_t win, const uint2* __restrict__ slist, uint32_t lane) {
+    uint2 e;
+    uint32_t x3;
+    const uint32_t r = s.rn >> 24;
+    if (r == 1) goto L1;
+    if (r == 2) goto L2;
+    if (r == 3) goto L3;
+L0:
+    if (!take(s, e, stage_end, win, slist, lane)) { s.rn &= 0xFFFFFFu; return; }
+    s.x0 = match(e, row_base, mask_tab);
+L1:
+    if (!take(s, e, stage_end, win, slist, lane)) { s.rn = (s.rn & 0xFFFFFFu) | (1u << 24); return; }
+    s.x1 = match(e, row_base, mask_tab);
+L2:
+    if (!take(s, e, stage_end, win, slist, lane)) { s.rn = (s.rn & 0xFFFFFFu) | (2u << 24); return; }
+    s.x2 = match(e, row_base, mask_tab);
+L3:
+    if (!take(s, e, stage_end, win, slist, lane)) { s.rn = (s.rn & 0xFFFFFFu) | (3u << 24); return; }
+    x3 = match(e, row_base, mask_tab);
+    s.cnt.add4(s.x0, s.x1, s.x2, x3, s.rn & 0xFFFFFFu);
+    ++s.rn;                                                       // nblk: far from the r field
+    goto L0;
 }
 
 template <int J, int NWARPS>
 __global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
-scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ slist,
+scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restrict__ slist,
                   const uint64_t* __restrict__ soff, uint32_t n_reads, uint32_t n_groups, uint32_t n_pad,
                   uint32_t n_gt, uint32_t n_rt, uint32_t n_rows, uint32_t S, int stages, uint32_t* __restrict__ counts,
                   uint32_t* __restrict__ work_counter) {
@@ -140,7 +197,8 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __re
     const uint32_t stage_bytes = S * ROW_BYTES;
     uint8_t* ring = smem;
     uint32_t* mask_tab = reinterpret_cast<uint32_t*>(smem + (size_t)stages * stage_bytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(mask_tab) + MASK_TAB_BYTES);
+    uint8_t* windows = reinterpret_cast<uint8_t*>(mask_tab) + MASK_TAB_BYTES;       // NWARPS * J windows
+    uint64_t* full = reinterpret_cast<uint64_t*>(windows + (size_t)NWARPS * J * WINDOW_BYTES);
     uint64_t* empty = full + stages;
     TileMeta* meta = reinterpret_cast<TileMeta*>(empty + stages);
 
@@ -192,7 +250,7 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __re
         uint32_t phase = 0;
         ReadState rs[J];
         const uint32_t ring_addr = smem_u32(ring), mt_addr = smem_u32(mask_tab);
-        const uint32_t* lane_list = slist + lane;
+        const uint32_t win_addr = smem_u32(windows) + warp * J * WINDOW_BYTES;
         for (;;) {
             mbar_wait(full + stage, phase);
             const TileMeta* m = meta + stage;
@@ -206,18 +264,24 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __re
                     // reads past the end walk the sentinel block at the head of the buffer
                     const uint32_t p0 = q < n_reads ? (uint32_t)soff[q] : 0u;
                     rs[j].cnt.reset();
-                    rs[j].chunk = __ldg(lane_list + p0);
-                    rs[j].pre = __ldg(lane_list + p0 + 32);
                     rs[j].ptr = p0;
+                    rs[j].x0 = rs[j].x1 = rs[j].x2 = 0;
+                    // chunks 0 and 1 into the window, chunk 2 prefetched
+                    const uint2 c0 = __ldg(slist + (p0 + lane)), c1 = __ldg(slist + (p0 + 32u + lane));
+                    const uint32_t w = win_addr + (uint32_t)j * WINDOW_BYTES;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(w + (lane << 3)), "r"(c0.x), "r"(c0.y) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(w + ((32u + lane) << 3)), "r"(c1.x), "r"(c1.y) : "memory");
+                    rs[j].pre = __ldg(slist + (p0 + 64u + lane));
                     rs[j].rn = 0;
-                    rs[j].x0 = rs[j].x1 = rs[j].x2 = rs[j].x3 = 0;
                 }
+                __syncwarp();
             }
-            const uint32_t stage_end_e = (row0 + S) << 8;
             // address of the lane's 16 bytes of row `bucket` = row_base + bucket * ROW_BYTES
             const uint32_t row_base = ring_addr + (uint32_t)stage * stage_bytes + lane * 16u - row0 * ROW_BYTES;
+            const uint32_t stage_end = (row0 + S) * ROW_BYTES;
             #pragma unroll
-            for (int j = 0; j < J; ++j) run_stage(rs[j], stage_end_e, row_base, mt_addr, lane_list);
+            for (int j = 0; j < J; ++j)
+                run_stage(rs[j], stage_end, row_base, mt_addr, win_addr + (uint32_t)j * WINDOW_BYTES, slist, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);       // stage may be refilled
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -228,8 +292,8 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __re
                 for (int j = 0; j < J; ++j) {
                     const uint32_t q = rt * RT + warp * J + j;
                     // the rows still waiting in the block of four (absent ones count as no match)
-                    const uint32_t r = rs[j].rn >> 16;
-                    uint32_t nblk = rs[j].rn & 0xFFFFu;
+                    const uint32_t r = rs[j].rn >> 24;
+                    uint32_t nblk = rs[j].rn & 0xFFFFFFu;
                     if (r) {
                         rs[j].cnt.add4(rs[j].x0, r > 1 ? rs[j].x1 : 0u, r > 2 ? rs[j].x2 : 0u, 0u, nblk);
                         ++nblk;
@@ -255,7 +319,7 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __re
 __global__ void __launch_bounds__(256)
 sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
                   const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t n_buckets,
-                  uint32_t* __restrict__ slist, const uint64_t* __restrict__ soff) {
+                  uint2* __restrict__ slist, const uint64_t* __restrict__ soff) {
     extern __shared__ __align__(16) uint8_t dense[];
     __shared__ uint32_t warp_tot[8];
     const uint32_t padded = (n_buckets + 15) & ~15u;
@@ -291,7 +355,7 @@ sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict_
         __syncthreads();
         uint32_t running = 0;
         for (uint32_t w = 0; w < warp; ++w) running += warp_tot[w];
-        uint32_t* dst = slist + soff[q];
+        uint2* dst = slist + soff[q];
         for (uint32_t wb = w0; wb < w1; wb += 32) {                  // uniform trip count over the warp
             const uint32_t w = wb + lane;
             const uint32_t v = w < w1 ? words[w] : 0xFFFFFFFFu;
@@ -306,19 +370,19 @@ sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict_
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t f = (v >> (8 * k)) & 0xFFu;
-                if (f != 0xFFu) dst[at++] = ((4 * w + k) << 8) | f;
+                if (f != 0xFFu) dst[at++] = make_uint2((4 * w + k) * ROW_BYTES, f << 5);
             }
             running += __shfl_sync(0xffffffffu, incl, 31);
         }
-        // sentinels: up to the next multiple of 32 and two whole chunks more (the scan prefetches)
-        const uint32_t end = ((L + 31) & ~31u) + 64;
-        for (uint32_t i = L + threadIdx.x; i < end; i += blockDim.x) dst[i] = SENTINEL;
+        // sentinels: up to the next multiple of 64 and four whole chunks more (the scan prefetches)
+        const uint32_t end = ((L + 63) & ~63u) + 128;
+        for (uint32_t i = L + threadIdx.x; i < end; i += blockDim.x) dst[i] = make_uint2(SENTINEL, 0u);
     }
 }
 
-__global__ void fill_sentinels_kernel(uint32_t* p, uint32_t n) {
+__global__ void fill_sentinels_kernel(uint2* p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = SENTINEL;
+    if (i < n) p[i] = make_uint2(SENTINEL, 0u);
 }
 
 PFN_cuTensorMapEncodeTiled encode_fn() {
@@ -335,7 +399,7 @@ PFN_cuTensorMapEncodeTiled encode_fn() {
 }
 
 template <int J, int NWARPS>
-int launch_tiled_t(const TiledPlan& plan, const CUtensorMap& map, const uint32_t* slist, const uint64_t* soff,
+int launch_tiled_t(const TiledPlan& plan, const CUtensorMap& map, const uint2* slist, const uint64_t* soff,
                    uint32_t n_reads, uint32_t n_genomes, uint32_t n_rows, uint32_t* counts, uint32_t* work_counter,
                    cudaStream_t st) {
     if (!smem_optin(reinterpret_cast<const void*>(scan_tiled_kernel<J, NWARPS>), plan.smem)) return -1;
@@ -352,48 +416,53 @@ int launch_tiled_t(const TiledPlan& plan, const CUtensorMap& map, const uint32_t
 
 }  // namespace
 
-uint32_t sorted_list_capacity(uint64_t entries) { return (uint32_t)(((entries + 31) & ~31ull) + 64); }
+uint32_t sorted_list_capacity(uint64_t entries) { return (uint32_t)(((entries + 63) & ~63ull) + 128); }
 
 int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes, TiledPlan* out) {
     if (n_genomes == 0 || h > TILED_MAX_H || h < 0) return -1;
-    // J reads per warp x NWARPS consumer warps: 34 registers of state per read (ReadState), 168
-    // registers per thread at 384 threads
-    out->J = 4;
-    out->warps = 11;
+    // J reads per warp x NWARPS consumer warps: 23 registers of state per read (ReadState), 80
+    // registers per thread at 768 threads
+    out->J = 2;
+    out->warps = 23;
     out->tile_reads = (uint32_t)(out->J * out->warps);
     const uint32_t n_rows = 1u << h;
     const uint32_t G = (n_genomes + 31) / 32;
     out->n_gt = (G + 31) / 32;
-    uint32_t S = 32;
+    // 64 rows per stage (3 stages of 64 KB): measured at 50,000 genomes, 16 / 32 / 64 rows give
+    // 8.0 / 11.4 / 14.5 TB/s: the fixed cost per stage (barrier round trip, window upkeep) counts
+    uint32_t S = 64;
     if (const char* e = getenv("MIEKKI_TILED_STAGE_ROWS")) S = (uint32_t)std::max(1, atoi(e));
     while (S & (S - 1)) S &= S - 1;                       // power of two
     S = std::min<uint32_t>(std::min<uint32_t>(S, 256), n_rows);
     out->S = S;
-    const size_t fixed = MASK_TAB_BYTES + 1024 + 64 * (2 * sizeof(uint64_t) + sizeof(TileMeta));
-    int stages = (int)((smem_optin_bytes - fixed - 1024) / ((size_t)S * ROW_BYTES));
+    const size_t fixed = MASK_TAB_BYTES + (size_t)out->tile_reads * WINDOW_BYTES + 256;
+    const size_t per_stage = (size_t)S * ROW_BYTES + 2 * sizeof(uint64_t) + sizeof(TileMeta);
+    int stages = (int)((smem_optin_bytes - fixed) / per_stage);
     stages = std::min(stages, 64);
     if (stages < 2) return -2;
     out->stages = stages;
-    out->smem = (size_t)stages * S * ROW_BYTES + fixed;
+    out->smem = (size_t)stages * per_stage + fixed;
     out->grid = sm_count;
     return 0;
 }
 
 void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
-                       uint32_t* slist, const uint64_t* soff, cudaStream_t st) {
+                       void* slist_, const uint64_t* soff, cudaStream_t st) {
+    uint2* slist = static_cast<uint2*>(slist_);
     if (!n_reads) return;
     const uint32_t n_buckets = 1u << h;
     const size_t smem = (n_buckets + 15) & ~(size_t)15;
     if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sort_lists_kernel), smem)) return;
-    fill_sentinels_kernel<<<1, 64, 0, st>>>(slist, 64);            // the block reads past the end walk
+    fill_sentinels_kernel<<<1, 128, 0, st>>>(slist, 128);          // the block reads past the end walk
     const unsigned grid = n_reads < 148u * 8u ? n_reads : 148u * 8u;
     sort_lists_kernel<<<grid, 256, smem, st>>>(list, list_off, list_len, n_reads, n_buckets, slist, soff);
 }
 
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
-                      const uint32_t* slist, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
+                      const void* slist_, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
                       uint32_t* work_counter, cudaStream_t st) {
     if (!n_reads) return 0;
+    const uint2* slist = static_cast<const uint2*>(slist_);
     PFN_cuTensorMapEncodeTiled encode = encode_fn();
     if (!encode) return -2;
     // the index as a 3-D tensor of 32-bit words: [row][half][word]; a box = S rows x 2 halves x 512 B
@@ -407,7 +476,7 @@ int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t strid
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -3;
-    return launch_tiled_t<4, 11>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
+    return launch_tiled_t<2, 23>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
 }
 
 }  // namespace mk

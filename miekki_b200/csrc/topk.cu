@@ -9,6 +9,16 @@
 // the heap, so skipping it early (with a possibly stale minimum, which can only be lower)
 // is exact.
 //
+// Ties.  With saturated sketches (5 Mbp genomes at -h 17) genome_size is 0 (quirk G2), every
+// intersection is 0 and, at -s 0, every genome is a candidate that replaces the heap's minimum:
+// N pops and pushes per read, one at a time.  But when all K keys of a full heap equal the key of
+// the candidate, every comparison of pop_heap / push_heap is false and the two calls reduce to a
+// fixed move: a[p0] <- a[p1] <- ... <- a[K-1] <- candidate along the chain of right children
+// p0 = 0, p1 = 2, p2 = 6, ... (tie_chain below replays __adjust_heap on equal keys once).  A step
+// of 128 genomes whose m candidates all tie with such a heap is therefore applied at once: the
+// chain ends up holding the last candidates of the step (shifted by m when m is shorter than the
+// chain).  Any other step takes the general replay.
+//
 // Sharding: the heap state is read from / written to `heap`/`len`,
 // so shards are chained in ascending id order; only the last link applies sort_heap.
 #include "common.cuh"
@@ -57,6 +67,25 @@ __device__ __forceinline__ void pop(HitDev* a, int n) {
     adjust(a, 0, n - 1, v);
 }
 
+// positions a[p0] <- a[p1] <- ... <- a[K-1] of one pop_heap + push_heap on K equal keys
+// (bits/stl_heap.h:224-250 with every comparison false); returns the chain length
+__device__ int tie_chain(int K, int* pos) {
+    int n = 0, child = 0;
+    const int len = K - 1;
+    pos[n++] = 0;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);            // the right child: "a[child] > a[child - 1]" is false
+        pos[n++] = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        pos[n++] = child - 1;
+    }
+    if (K == 1) n = 0;                      // the popped element is the last one itself
+    pos[n++] = K - 1;
+    return n;
+}
+
 __global__ void __launch_bounds__(WARPS * 32)
 topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_genomes, uint32_t n_pad,
             uint32_t first_id, const uint32_t* __restrict__ sketch_size,
@@ -64,7 +93,10 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
             uint32_t min_score, double min_intersection, HitDev* __restrict__ heap_io,
             uint32_t* __restrict__ len_io, int finalize) {
     __shared__ HitDev heaps[WARPS][MAX_RESULTS];
+    __shared__ int chain[8], chain_len;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) chain_len = tie_chain((int)K, chain);
+    __syncthreads();
     const uint32_t q = blockIdx.x * WARPS + warp;
     if (q >= n_reads) return;
     HitDev* hp = heaps[warp];
@@ -72,6 +104,14 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
     for (uint32_t i = lane; i < len; i += 32) hp[i] = heap_io[(uint64_t)q * K + i];
     __syncwarp();
     double hmin = len ? hp[0].intersection : 0.0;
+    const int P = chain_len;
+    // all K keys of the full heap are equal (to hmin): the tie shortcut applies
+    auto all_equal = [&]() {
+        bool eq = len >= K;
+        for (uint32_t i = lane; i < len && eq; i += 32) eq = hp[i].intersection == hmin;
+        return __all_sync(0xffffffffu, eq);
+    };
+    bool uniform = all_equal();
     const uint32_t* cq = counts + (uint64_t)q * n_pad;
 
     // 128 genomes per step: every lane scores four consecutive ids from one 16-byte load, and
@@ -108,6 +148,39 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
             }
         }
         uint32_t m = __ballot_sync(0xffffffffu, mine != 0);
+        if (m && uniform) {
+            // every candidate of the step ties with the K equal keys of the heap?
+            bool tie = true;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) tie = tie && (!((mine >> j) & 1u) || x[j] == hmin);
+            if (__all_sync(0xffffffffu, tie)) {
+                // rank of this lane's candidates among the step's, in id order
+                const uint32_t cnt = __popc(mine);
+                uint32_t before = cnt;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, before, o);
+                    if (lane >= o) before += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, before, 31);
+                before -= cnt;
+                const uint32_t used = total < (uint32_t)P ? total : (uint32_t)P;   // candidates that stay
+                if (lane == 0)                                                     // shorter than the chain: shift
+                    for (int i = 0; i + (int)used < P; ++i) hp[chain[i]] = hp[chain[i + used]];
+                __syncwarp();
+                uint32_t rank = before;
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!((mine >> j) & 1u)) continue;
+                    if (rank + used >= total)                                      // one of the last `used`
+                        hp[chain[P - (total - rank)]] = HitDev{first_id + base + (uint32_t)j, scv[j], jac[j], x[j]};
+                    ++rank;
+                }
+                __syncwarp();
+                m = 0;                                                             // heap stays full and uniform
+            }
+        }
+        const bool replay = m != 0;
         while (m) {                                                    // lanes, then ids within a lane: ascending id
             const int src = __ffs((int)m) - 1;
             m &= m - 1;
@@ -136,6 +209,10 @@ topk_kernel(const uint32_t* __restrict__ counts, uint32_t n_reads, uint32_t n_ge
                 len = __shfl_sync(0xffffffffu, len, 0);
                 hmin = __shfl_sync(0xffffffffu, hmin, 0);
             }
+        }
+        if (replay) {
+            __syncwarp();
+            uniform = all_equal();
         }
         cur = nxt;
     }
