@@ -10,8 +10,8 @@ OBJ := build/obj
 LIB := miekki_b200/libmiekki_b200.so
 CLI := miekki_b200/cli/miekki
 CU := $(SRC)/api.cu $(SRC)/sketch.cu $(SRC)/scan.cu $(SRC)/scan_tiled.cu $(SRC)/topk.cu $(SRC)/exact.cu
-OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
-HDRS := $(SRC)/common.cuh $(SRC)/scan_common.cuh $(SRC)/kernels.h include/miekki_b200.h
+OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU)) $(OBJ)/pack.o
+HDRS := $(SRC)/common.cuh $(SRC)/scan_common.cuh $(SRC)/kernels.h $(SRC)/pack.h include/miekki_b200.h
 
 TOOLS := benchmarks/make_dump
 
@@ -25,6 +25,11 @@ benchmarks/make_dump: benchmarks/make_dump.cpp include/miekki_b200.h $(LIB)
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+
+# host-side sequence packer: plain C++ (its AVX2 kernel is selected at run time)
+$(OBJ)/pack.o: $(SRC)/pack.cpp $(SRC)/pack.h
+	@mkdir -p $(OBJ)
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -cudart static -ccbin $(CXX) -o $@ $(OBJS) -lpthread

@@ -21,6 +21,7 @@
 
 #include "../../include/miekki_b200.h"
 #include "kernels.h"
+#include "pack.h"
 
 using namespace mk;
 
@@ -417,6 +418,11 @@ struct BatchView {
     const uint64_t* h_len;
     uint32_t n;
     uint64_t max_len, bases;
+    // sequences packed on the host (pack.h) instead of chars / d_coff
+    const uint32_t* packed = nullptr;   // word w of sequence s at packed[woff(s) + w], woff as in dense_sketch
+    const PackExcDev* exc = nullptr;
+    uint32_t n_exc = 0, seq0 = 0;
+    const uint8_t* pvalid = nullptr;
 };
 BatchView view_of(const mk_batch* b, uint32_t first, uint32_t n) {
     BatchView v{b->chars, b->d_coff + first, b->d_len + first, b->h_len.data() + first, n, 0, 0};
@@ -476,8 +482,13 @@ int dense_sketch(mk_ctx* c, const BatchView& v, bool bloom_insert, DenseOut* out
         c->stats.kernel_launches += 2;
     }
     launch_fill_u64(keys, (uint64_t)n * c->B, ~0ull, c->stream);
-    launch_encode_planes(v.chars, v.d_coff, v.d_len, d_woff, n, v.max_len, (int)c->k,
-                         static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, c->stream);
+    if (v.packed)
+        launch_expand_planes(v.packed, v.exc, v.n_exc, v.seq0, v.pvalid, v.d_len, d_woff, n, v.max_len, (int)c->k,
+                             static_cast<uint32_t*>(c->planeF.p), c->stream);
+    else
+        launch_encode_planes(v.chars, v.d_coff, v.d_len, d_woff, n, v.max_len, (int)c->k,
+                             static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, c->stream);
+    if (v.packed && v.n_exc) c->stats.kernel_launches += 1;
     launch_sketch_dense(static_cast<uint32_t*>(c->planeF.p), static_cast<uint32_t*>(c->planeF.p) + 1, v.d_len,
                         d_woff, n, v.max_len, (int)c->k, (int)c->h, keys, ks, c->stream);
     static const bool split = [] {
@@ -543,7 +554,165 @@ int host_stats(mk_ctx* c) {
     return MK_OK;
 }
 
-int index_add_view(mk_ctx* c, const mk_batch* b) {
+// Genomes packed on the host (pack.h): 0.25 B per base over PCIe instead of 1 B.
+struct PackedBatch {
+    uint32_t* d_words = nullptr;     // one allocation: words | len[n] | pvalid[n]
+    uint64_t* d_len = nullptr;
+    uint8_t* d_pvalid = nullptr;
+    PackExcDev* d_exc = nullptr;     // second allocation (its size is known after packing)
+    cudaStream_t stream = nullptr;
+    std::vector<uint64_t> h_len, h_woff;     // h_woff: n + 1, words per sequence = ceil(len / 16) + 2
+    std::vector<uint32_t> h_exc_off;         // n + 1: exceptions of sequence i
+    uint32_t n = 0, n_exc = 0;
+    uint64_t bases = 0;
+};
+void packed_release(PackedBatch* pb) {
+    if (!pb) return;
+    if (pb->d_words) cudaFreeAsync(pb->d_words, pb->stream);
+    if (pb->d_exc) cudaFreeAsync(pb->d_exc, pb->stream);
+    delete pb;
+}
+BatchView view_of(const PackedBatch* pb, uint32_t first, uint32_t n) {
+    BatchView v{nullptr, nullptr, pb->d_len + first, pb->h_len.data() + first, n, 0, 0};
+    for (uint32_t i = 0; i < n; ++i) {
+        v.max_len = std::max(v.max_len, v.h_len[i]);
+        v.bases += v.h_len[i];
+    }
+    v.packed = pb->d_words + pb->h_woff[first];
+    v.exc = pb->d_exc + pb->h_exc_off[first];
+    v.n_exc = pb->h_exc_off[first + n] - pb->h_exc_off[first];
+    v.seq0 = first;
+    v.pvalid = pb->d_pvalid + first;
+    return v;
+}
+
+// Packs sequences [0, n) on a team of host threads straight into pinned staging and copies the
+// pieces over as they are ready.  Returns MK_OK with *out == nullptr when packing does not pay
+// (more than one word in eight needs the general encoder: lower-case or N-rich input): the
+// caller then uploads the characters as they are.
+int upload_packed(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, PackedBatch** out,
+                  cudaStream_t st) {
+    *out = nullptr;
+    PackedBatch* pb = new PackedBatch();
+    pb->n = n;
+    pb->stream = st;
+    pb->h_len.assign(lens, lens + n);
+    pb->h_woff.resize((size_t)n + 1);
+    uint64_t words = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        pb->h_woff[i] = words;
+        words += (lens[i] + 15) / 16 + 2;
+        pb->bases += lens[i];
+    }
+    pb->h_woff[n] = words;
+    const size_t words_bytes = (words * 4 + 255) / 256 * 256;
+    const size_t total = words_bytes + (size_t)n * 8 + std::max<size_t>(n, 1);
+    auto bail = [&](cudaError_t e) {
+        packed_release(pb);
+        return fail(c, e == cudaErrorMemoryAllocation ? MK_ERR_NOMEM : MK_ERR_CUDA, std::string("packed upload: ") + cudaGetErrorString(e));
+    };
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&pb->d_words), total, st);
+    if (e != cudaSuccess) return bail(e);
+    pb->d_len = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pb->d_words) + words_bytes);
+    pb->d_pvalid = reinterpret_cast<uint8_t*>(pb->d_len + n);
+    // pieces of 512 Ki words (8 MB of characters -> 2 MB packed)
+    constexpr uint64_t PIECE_WORDS = 512 << 10;
+    struct Piece { uint32_t seq; uint64_t w0, w1; };
+    std::vector<Piece> pieces;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t nw = (lens[i] + 15) / 16;
+        for (uint64_t w = 0; w < nw; w += PIECE_WORDS) pieces.push_back({i, w, std::min(nw, w + PIECE_WORDS)});
+    }
+    static const unsigned TEAM = [] {
+        const char* ev = getenv("MIEKKI_PACK_THREADS");
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return (unsigned)std::min(64, std::max(1, ev ? atoi(ev) : (int)std::min(32u, hw)));
+    }();
+    const unsigned team = (unsigned)std::min<size_t>(TEAM, std::max<size_t>(1, pieces.size()));
+    int r = reserve_pinned(c, PIECE_WORDS * 4 * 2 * team);
+    if (r != MK_OK) { packed_release(pb); return r; }
+    uint32_t* ring = static_cast<uint32_t*>(c->pinned);
+    std::atomic<size_t> next{0};
+    std::atomic<int> cuda_err{(int)cudaSuccess};
+    struct Exc { uint32_t seq; PackException x; };
+    std::vector<std::vector<Exc>> found(team);
+    auto worker = [&](unsigned t) {
+        cudaSetDevice(c->device);
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        bool used[2] = {false, false};
+        cudaError_t err = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+        std::vector<PackException> exc;
+        int slot = 0;
+        while (err == cudaSuccess && cuda_err.load(std::memory_order_relaxed) == (int)cudaSuccess) {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= pieces.size()) break;
+            const Piece& pc = pieces[i];
+            uint32_t* stage = ring + ((size_t)2 * t + slot) * PIECE_WORDS;
+            if (used[slot]) err = cudaEventSynchronize(ev[slot]);          // its previous copy has left
+            if (err != cudaSuccess) break;
+            exc.clear();
+            pack_words(seqs[pc.seq], lens[pc.seq], pc.w0, pc.w1, (int)c->k, stage, exc);
+            for (const PackException& x : exc) found[t].push_back({pc.seq, x});
+            err = cudaMemcpyAsync(pb->d_words + pb->h_woff[pc.seq] + pc.w0, stage, (pc.w1 - pc.w0) * 4,
+                                  cudaMemcpyHostToDevice, st);
+            if (err == cudaSuccess) err = cudaEventRecord(ev[slot], st);
+            used[slot] = true;
+            slot ^= 1;
+        }
+        for (int s2 = 0; s2 < 2; ++s2) {
+            if (used[s2] && err == cudaSuccess) err = cudaEventSynchronize(ev[s2]);
+            if (ev[s2]) cudaEventDestroy(ev[s2]);
+        }
+        if (err != cudaSuccess) cuda_err.store((int)err, std::memory_order_relaxed);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < team; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& x : th) x.join();
+    e = (cudaError_t)cuda_err.load();
+    if (e != cudaSuccess) return bail(e);
+    // exceptions in (sequence, word) order, with the offsets of every sequence
+    std::vector<Exc> all;
+    for (auto& v : found) all.insert(all.end(), v.begin(), v.end());
+    if (all.size() > words / 8 + 4 * (size_t)n) {                          // packing does not pay here
+        cudaStreamSynchronize(st);
+        packed_release(pb);
+        return MK_OK;
+    }
+    std::sort(all.begin(), all.end(), [](const Exc& a, const Exc& b) {
+        return a.seq != b.seq ? a.seq < b.seq : a.x.word < b.x.word;
+    });
+    pb->n_exc = (uint32_t)all.size();
+    pb->h_exc_off.assign((size_t)n + 1, 0);
+    std::vector<PackExcDev> dev(all.size());
+    for (size_t i = 0; i < all.size(); ++i) {
+        memcpy(&dev[i].bytes, all[i].x.bytes, 16);
+        dev[i].word = all[i].x.word;
+        dev[i].seq = all[i].seq;
+        dev[i].pad = 0;
+        pb->h_exc_off[all[i].seq + 1] += 1;
+    }
+    for (uint32_t i = 0; i < n; ++i) pb->h_exc_off[i + 1] += pb->h_exc_off[i];
+    std::vector<uint8_t> pvalid(std::max<size_t>(n, 1));
+    for (uint32_t i = 0; i < n; ++i) pvalid[i] = prefix_is_acgt(seqs[i], lens[i], (int)c->k) ? 1 : 0;
+    if (!dev.empty()) {
+        e = cudaMallocAsync(reinterpret_cast<void**>(&pb->d_exc), dev.size() * sizeof(PackExcDev), st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(pb->d_exc, dev.data(), dev.size() * sizeof(PackExcDev), cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(pb->d_len, pb->h_len.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(pb->d_pvalid, pvalid.data(), n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);        // host vectors and the staging ring are reused
+    if (e != cudaSuccess) return bail(e);
+    c->h2d_meta.fetch_add(words * 4 + dev.size() * sizeof(PackExcDev) + (size_t)n * 9, std::memory_order_relaxed);
+    *out = pb;
+    return MK_OK;
+}
+
+// appends the sequences of a batch (characters in HBM) or of a packed batch to the index
+template <class Batch>
+int index_add_any(mk_ctx* c, const Batch* b) {
     for (uint32_t i = 0; i < b->n; ++i)
         if (b->h_len[i] < c->k)
             return fail(c, MK_ERR_ARG, "mk_index_add: sequence shorter than k (the reference's callers skip these, Miekki.cpp:569)");
@@ -579,6 +748,7 @@ int index_add_view(mk_ctx* c, const mk_batch* b) {
     }
     return sync(c);
 }
+int index_add_view(mk_ctx* c, const mk_batch* b) { return index_add_any(c, b); }
 
 // ---- query: reads -> (bucket << 8 | fp) lists ----------------------------------------
 struct Lists {
@@ -1365,23 +1535,41 @@ int mk_index_add(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint3
         first += m;
     }
     TRY(ensure_capacity(c, c->n + n));
-    auto stage = [c, seqs, lens](uint32_t first, uint32_t m) {
-        cudaSetDevice(c->device);
-        mk_batch* b = nullptr;
-        const int r = upload_range(c, seqs + first, lens + first, m, &b, c->copy_stream);
-        return std::make_pair(r, b);
+    // Long sequences are packed to 2 bits per base on the host (pack.h) so that a quarter of the
+    // bytes cross PCIe; short ones, and input that packs badly, go over as characters.
+    // (read per call so that tests can switch: MIEKKI_PACKED_UPLOAD=0 never packs,
+    // MIEKKI_PACK_MIN_LEN = smallest mean sequence length that is packed, default 65,536)
+    const char* pe = getenv("MIEKKI_PACKED_UPLOAD");
+    const bool pack_on = !pe || atoi(pe) != 0;
+    const char* pm = getenv("MIEKKI_PACK_MIN_LEN");
+    const uint64_t pack_min = pm ? strtoull(pm, nullptr, 10) : (1u << 16);
+    struct Staged {
+        int r;
+        mk_batch* b;
+        PackedBatch* pb;
     };
-    std::future<std::pair<int, mk_batch*>> next;
+    auto stage = [c, seqs, lens, pack_on, pack_min](uint32_t first, uint32_t m) {
+        cudaSetDevice(c->device);
+        Staged s{MK_OK, nullptr, nullptr};
+        uint64_t bases = 0;
+        for (uint32_t i = 0; i < m; ++i) bases += lens[first + i];
+        if (pack_on && m && bases / m >= pack_min) s.r = upload_packed(c, seqs + first, lens + first, m, &s.pb, c->copy_stream);
+        if (s.r == MK_OK && !s.pb) s.r = upload_range(c, seqs + first, lens + first, m, &s.b, c->copy_stream);
+        return s;
+    };
+    std::future<Staged> next;
     if (!slices.empty()) next = std::async(std::launch::async, stage, slices[0].first, slices[0].second);
     int rc = MK_OK;
     for (size_t i = 0; i < slices.size(); ++i) {
-        auto [r, b] = next.get();
+        Staged s = next.get();
         if (i + 1 < slices.size())
             next = std::async(std::launch::async, stage, slices[i + 1].first, slices[i + 1].second);
-        if (r == MK_OK && rc == MK_OK) r = index_add_view(c, b);
-        if (b) {
+        int r = s.r;
+        if (r == MK_OK && rc == MK_OK) r = s.pb ? index_add_any(c, s.pb) : index_add_view(c, s.b);
+        if (s.b || s.pb) {
             cudaStreamSynchronize(c->stream);
-            batch_release(b);
+            batch_release(s.b);
+            packed_release(s.pb);
         }
         if (r != MK_OK && rc == MK_OK) rc = r;
     }

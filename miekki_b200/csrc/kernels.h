@@ -28,6 +28,18 @@ constexpr int KEY_TAG_BITS = 24;    // tagged sketch keys, see launch_sketch_den
 void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint64_t* len,
                           const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k,
                           uint32_t* planeF, uint32_t* planeR, cudaStream_t st);
+// Planes of sequences packed on the host (pack.h).  packed[woff[s] + w] = forward digits of word w
+// of sequence s (whole words of upper-case ACGT outside the prefix); exc = the other words as raw
+// bytes (seq relative to the batch, seq0 = first sequence of this view); pvalid[s] = the k-1
+// prefix of sequence s is all ACGTacgt.
+struct PackExcDev {
+    uint4 bytes;
+    uint64_t word;
+    uint32_t seq, pad;
+};
+void launch_expand_planes(const uint32_t* packed, const PackExcDev* exc, uint32_t n_exc, uint32_t seq0,
+                          const uint8_t* pvalid, const uint64_t* len, const uint64_t* woff, uint32_t n_seq,
+                          uint64_t max_len, int k, uint32_t* planes, cudaStream_t st);
 void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const uint64_t* len,
                          const uint64_t* woff, uint32_t n_seq, uint64_t max_len, int k, int h,
                          unsigned long long* keys, int ks, cudaStream_t st);

@@ -127,6 +127,7 @@ struct ReadState {
 __device__ __noinline__ uint2 refill(uint2 pre, uint32_t ptr, uint32_t win, const uint2* __restrict__ slist,
                                      uint32_t lane) {
     const uint32_t cur = ptr >> 5;
+    __syncwarp();                           // every lane is done with the chunk that is replaced
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(win + ((((cur + 1) & 1u) << 5 | lane) << 3)), "r"(pre.x), "r"(pre.y)
                  : "memory");
     pre = __ldg(slist + (((cur + 2) << 5) + lane));

@@ -50,11 +50,9 @@ __device__ __forceinline__ bool prefix_valid(const uint8_t* __restrict__ s, uint
     return ok;
 }
 
-// encode characters [16w, 16w+16) of a sequence into one F word and one R word
-__device__ __forceinline__ void encode_word(const uint8_t* __restrict__ s, uint64_t n, uint64_t w,
-                                            int k, bool pvalid, const uint8_t* lut, uint32_t& F,
-                                            uint32_t& R) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(s + 16 * w);  // start is 16-byte aligned
+// encode characters [16w, 16w+16) of a sequence (given as 16 raw bytes) into one F and one R word
+__device__ __forceinline__ void encode_word_raw(const uint4 raw, uint64_t n, uint64_t w, int k, bool pvalid,
+                                                const uint8_t* lut, uint32_t& F, uint32_t& R) {
     const uint32_t q[4] = {raw.x, raw.y, raw.z, raw.w};
     uint32_t f = 0, r = 0;
     #pragma unroll
@@ -76,6 +74,11 @@ __device__ __forceinline__ void encode_word(const uint8_t* __restrict__ s, uint6
     }
     F = f;
     R = r;
+}
+__device__ __forceinline__ void encode_word(const uint8_t* __restrict__ s, uint64_t n, uint64_t w,
+                                            int k, bool pvalid, const uint8_t* lut, uint32_t& F,
+                                            uint32_t& R) {
+    encode_word_raw(*reinterpret_cast<const uint4*>(s + 16 * w), n, w, k, pvalid, lut, F, R);  // 16-byte aligned start
 }
 
 // Fast path of encode_word: all 16 characters are upper-case A/C/G/T and none lies in the
@@ -133,6 +136,44 @@ encode_planes_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restri
         *reinterpret_cast<uint2*>(planeF + 2 * (woff[s] + w)) = make_uint2(F, R);
         (void)planeR;
     }
+}
+
+// The same planes from sequences packed on the host (pack.h): a packed word holds the forward
+// digits of 16 upper-case A/C/G/T outside the prefix, so F is the word itself and R its digit-wise
+// complement in reverse order; every other word (prefix, ragged end, N, lower case ...) arrives
+// as 16 raw bytes in the exception list and goes through the general encoder afterwards.
+__global__ void __launch_bounds__(256)
+expand_planes_kernel(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ len,
+                     const uint64_t* __restrict__ woff, uint32_t* __restrict__ planes) {
+    const uint32_t s = blockIdx.y;
+    const uint64_t n = len[s];
+    const uint64_t nw = (n + 15) / 16 + 2;       // two zero words of padding
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t F = 0, R = 0;
+        if (16 * w + 16 <= n) {                  // whole words only; the others are exceptions or padding
+            F = packed[woff[s] + w];
+            uint32_t r = __brev(F);
+            r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+            R = ~r;
+        }
+        *reinterpret_cast<uint2*>(planes + 2 * (woff[s] + w)) = make_uint2(F, R);
+    }
+}
+__global__ void __launch_bounds__(256)
+patch_planes_kernel(const PackExcDev* __restrict__ exc, uint32_t n_exc, uint32_t seq0, const uint64_t* __restrict__ len,
+                    const uint64_t* __restrict__ woff, const uint8_t* __restrict__ pvalid, int k,
+                    uint32_t* __restrict__ planes) {
+    __shared__ uint8_t lut[256];
+    fill_lut(lut);
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_exc) return;
+    const PackExcDev e = exc[i];
+    const uint32_t s = e.seq - seq0;
+    uint32_t F, R;
+    encode_word_raw(e.bytes, len[s], e.word, k, pvalid[s] != 0, lut, F, R);
+    *reinterpret_cast<uint2*>(planes + 2 * (woff[s] + e.word)) = make_uint2(F, R);
 }
 
 // one thread = 16 consecutive k-mer start positions (one plane word + two neighbours)
@@ -1033,6 +1074,16 @@ void launch_encode_planes(const uint8_t* chars, const uint64_t* coff, const uint
     const uint64_t nw = (max_len + 15) / 16 + 2;
     dim3 grid(blocks_for(nw, 256, 148 * 16), n_seq);
     encode_planes_kernel<<<grid, 256, 0, st>>>(chars, coff, len, woff, k, planeF, planeR);
+}
+
+void launch_expand_planes(const uint32_t* packed, const PackExcDev* exc, uint32_t n_exc, uint32_t seq0,
+                          const uint8_t* pvalid, const uint64_t* len, const uint64_t* woff, uint32_t n_seq,
+                          uint64_t max_len, int k, uint32_t* planes, cudaStream_t st) {
+    if (!n_seq) return;
+    const uint64_t nw = (max_len + 15) / 16 + 2;
+    expand_planes_kernel<<<dim3(blocks_for(nw, 256, 148 * 16), n_seq), 256, 0, st>>>(packed, len, woff, planes);
+    if (n_exc)
+        patch_planes_kernel<<<(n_exc + 255) / 256, 256, 0, st>>>(exc, n_exc, seq0, len, woff, pvalid, k, planes);
 }
 
 void launch_sketch_dense(const uint32_t* planeF, const uint32_t* planeR, const uint64_t* len,

@@ -87,3 +87,16 @@ def test_corrupt_member_is_reported(exe, tmp_path):
     p.write_bytes(bytes(raw))
     r = subprocess.run([exe, "gzwrite-readonly", str(p), "100000", "4"], capture_output=True)
     assert r.returncode != 0 or b"roundtrip-ok" not in r.stdout
+
+
+def test_host_sequence_packer(tmp_path):
+    """miekki_b200/csrc/pack.cpp (2 bits per base for mk_index_add's upload): every word is either
+    packed exactly or listed as an exception with its raw bytes -- AVX2 and portable kernels,
+    random k, dirty and clean sequences, sub-ranges (tests/cpp/pack_host_test.cpp)."""
+    out = tmp_path / "pack_host_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", str(out),
+                           os.path.join(H.ROOT, "tests", "cpp", "pack_host_test.cpp"),
+                           os.path.join(H.ROOT, "miekki_b200", "csrc", "pack.cpp")])
+    r = subprocess.run([str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr

@@ -867,3 +867,40 @@ def test_tiled_scan_on_case_a_hit_lines(mk, case_a, monkeypatch):
     reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
     for s in (200, 0, 5000):
         assert gpu_hit_lines(ix, reads, s, chunk=64) == open(os.path.join(d, "hits_s%d.txt" % s)).read()
+
+
+@pytest.mark.parametrize("k,h", [(31, 12), (21, 10), (5, 6), (2, 3)])
+def test_packed_upload_equals_oracle(mk, monkeypatch, k, h):
+    """mk_index_add packs long genomes to 2 bits per base on the host (pack.cpp) and ships only the
+    words that need the general encoder -- the k-1 prefix, the ragged last word, words with N /
+    lower case / any other byte -- as raw bytes.  Forced on for short sequences here and compared
+    with the oracle (rows, statistics, every Bloom byte) and with the character path."""
+    rng = np.random.default_rng(31 * k + h)
+    genomes = []
+    for i in range(40):
+        n = int(rng.integers(max(k, 1), 5000)) if i % 4 else int(rng.integers(k, k + 40))
+        s = np.frombuffer(rand_seq(rng, n, special=(i % 3 == 0)), np.uint8).copy()
+        if i % 7 == 0:
+            s[: min(n, 5)] = ord("n")                       # a dirty prefix zeroes the whole prefix word
+        if i % 11 == 0:
+            s[:] = np.frombuffer(bytes(s).lower(), np.uint8)   # packs badly: goes over as characters
+        if i == 13:
+            s = rng.integers(0, 256, n, dtype=np.uint8)     # arbitrary bytes
+        genomes.append(s.tobytes())
+    o = orc.Oracle(k=k, h=h, cap=len(genomes))
+    for s in genomes:
+        o.insert(s)
+    exports = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MIEKKI_PACKED_UPLOAD", mode)
+        monkeypatch.setenv("MIEKKI_PACK_MIN_LEN", "1")
+        ix = mk.Miekki(k=k, h=h, threshold=0)
+        ix.insert_sequences(genomes[:17])
+        ix.insert_sequences(genomes[17:])
+        exports[mode] = ix.export()
+        ix.close()
+    for mode, e in exports.items():
+        assert np.array_equal(e["rows"], o.rows), mode
+        assert np.array_equal(e["sketch_size"], o.sketch_size) and np.array_equal(e["genome_size"], o.genome_size), mode
+        m = min(len(e["bloom"]), len(o.bloom))
+        assert np.array_equal(e["bloom"][:m], o.bloom[:m]), mode
