@@ -74,7 +74,7 @@ def parse_args():
     ap.add_argument("--cpu-reads", type=int, default=2_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-reads", type=int, default=64, help="reads whose hit lists are checked (untimed)")
-    ap.add_argument("--build-e2e-genomes", type=int, default=64,
+    ap.add_argument("--build-e2e-genomes", type=int, default=256,
                     help="genomes pushed through the host->index path to report build Gbp/s e2e")
     # extra blocks (BASELINE configs 3, 4, 5 and the metric's "vs #genomes indexed")
     ap.add_argument("--no-extras", action="store_true", help="headline only")

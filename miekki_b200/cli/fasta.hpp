@@ -77,6 +77,36 @@ public:
         }
     }
 
+    // The loop of Miekki.cpp:559-567 in one pass over the reader's buffer: every line that does
+    // not start with '>' is appended to `ref` (one copy per byte instead of getline's two).
+    void concat_sequence_lines(std::string& ref) {
+        bool at_line_start = true, skipping = false;
+        for (;;) {
+            if (pos_ == len_ && !refill()) break;
+            const unsigned char* base = cur() + pos_;
+            const size_t avail = len_ - pos_;
+            if (at_line_start) {
+                skipping = base[0] == '>';
+                at_line_start = false;
+            }
+            const void* nl = memchr(base, '\n', avail);
+            const size_t seg = nl ? (size_t)((const unsigned char*)nl - base) : avail;
+            if (!skipping) ref.append((const char*)base, seg);
+            pos_ += seg + (nl ? 1 : 0);
+            if (nl) at_line_start = true;
+        }
+        eof_ = true;
+    }
+    // bytes of the file on disk (a lower bound of the text for compressed files)
+    size_t file_bytes() const {
+        const long at = ftell(f_);
+        if (at < 0 || fseek(f_, 0, SEEK_END) != 0) return 0;
+        const long end = ftell(f_);
+        fseek(f_, at, SEEK_SET);
+        return end > 0 ? (size_t)end : 0;
+    }
+    bool is_compressed() const { return compressed_; }
+
     // raw bytes (dump loading)
     size_t read(void* dst, size_t n) {
         size_t done = 0;
@@ -357,11 +387,10 @@ private:
 // appended; records are concatenated without separator (quirk G9).
 inline std::string read_genome_concat(const std::string& path) {
     LineReader in(path);
-    std::string ref, line;
-    while (!in.eof()) {
-        in.getline(line);
-        if (line.empty() || line[0] != '>') ref += line;
-    }
+    std::string ref;
+    const size_t bytes = in.file_bytes();
+    ref.reserve(in.is_compressed() ? bytes * 4 : bytes);       // gzip-1 of DNA text: about 3.5x
+    in.concat_sequence_lines(ref);
     return ref;
 }
 
