@@ -218,7 +218,10 @@ void build_shard(Index& ix, mk_ctx* ctx, const vector<string>& names, size_t lo,
                  vector<string>& kept) {
     // Files are parsed in waves by a team of host threads and inserted in list order, so ids are
     // deterministic; wave i+1 is parsed (inflate, line joins) while wave i is on the GPU.
-    const size_t wave = max<size_t>(32, 4 * (size_t)threads);
+    // (128+ files per wave: mk_index_add then sees several 64-genome slices and overlaps the host
+    // packing of one with the sketching of the previous one)
+    const size_t wave = max<size_t>(128, 8 * (size_t)threads);
+    if (hi > lo) mk_index_reserve(ctx, (uint32_t)(hi - lo));     // the matrix is sized once, not regrown
     struct Wave {
         vector<string> seqs;
         vector<char> ok;

@@ -122,6 +122,13 @@ int mk_index_size(const mk_ctx *c, uint32_t *n) {
     return MK_OK;
 }
 
+int mk_index_reserve(mk_ctx *c, uint32_t n_genomes) {
+    pthread_mutex_lock(&g_mu);
+    ensure_cap(c, n_genomes);
+    pthread_mutex_unlock(&g_mu);
+    return MK_OK;
+}
+
 int mk_index_add(mk_ctx *c, const char *const *seqs, const uint64_t *lens, uint32_t n) {
     for (uint32_t i = 0; i < n; ++i)
         if (lens[i] < c->k) return fail(c, MK_ERR_ARG, "mk_index_add: sequence shorter than k");
