@@ -630,6 +630,12 @@ def main():
             "phases_ms_per_step": {"read_sketch": st3["read_sketch_ms"] / a.c3_steps,
                                    "scan": st3["scan_ms"] / a.c3_steps, "topk": st3["topk_ms"] / a.c3_steps},
             "surviving_buckets_per_read": st3["scan_rows"] / max(1, a.c3_steps * a.c3_reads),
+            # DRAM bytes per algorithmic byte of the scan from the committed ncu capture of this shape
+            # (tiled kernel), when there is one; not measured in this run
+            "dram_bytes_per_algorithmic_byte_ncu": (ncu_traffic({"h": a.c3_hbits, "genomes": gcount,
+                                                                 "read_len": a.c3_read_len, "tiled": True})
+                                                    or {}).get("dram_bytes_per_algorithmic_byte"),
+            "scan_kernel": "scan_tiled_kernel (rows staged once per 46 reads; DESIGN.md section 4)",
             "build_s": c3_build_s, "build_all_ranks": c3_build_all,
             "parity_checked": par3,
         }
@@ -652,12 +658,22 @@ def main():
         genomes = sorted(g for g in per_genome if first <= g < first + a.genomes)[:a.exact_genomes]
         ix.stats_reset()
         pairs, t_exact, checked, exact_ok, kmers = 0, 0.0, 0, True, 0
+        sort_ms, sort_same, exact_ms_total = 0.0, True, 0.0
         for g in genomes:
             rec = ix.synth(SEED, g, 1, a.genome_len)                 # the genome file's one record, in HBM
             rb = ix.upload([seqs[i] for i in per_genome[g]])
+            # the sort-merge variant of set B (radix sort + binary search) on the same pair, for comparison
+            os.environ["MIEKKI_EXACT_SORT"] = "1"
+            before = ix.stats()["exact_ms"]
+            sB, s_inter, s_uni = ix.exact_batch(rec, rb)
+            sort_ms += ix.stats()["exact_ms"] - before
+            os.environ["MIEKKI_EXACT_SORT"] = "0"
+            ix.stats_reset()
             t1 = time.perf_counter()
             nB, inter, uni = ix.exact_batch(rec, rb)
             t_exact += time.perf_counter() - t1
+            exact_ms_total += ix.stats()["exact_ms"]
+            sort_same = sort_same and sB == nB and np.array_equal(s_inter, inter) and np.array_equal(s_uni, uni)
             pairs += len(per_genome[g])
             kmers += a.genome_len - a.k + 1
             if checked < 2:                                          # the oracle redoes two genomes on the CPU
@@ -667,7 +683,7 @@ def main():
                 checked += 1
             rec.free()
             rb.free()
-        st_x = ix.stats()
+        st_x = {"exact_ms": exact_ms_total}
         extras["exact"] = {
             "workload": "C5 in small: hits (top 5, -s %d) of the first %d reads, true k-mer intersection against %d of "
                         "their genomes (5 Mbp each, resident in HBM)" % (a.threshold, ne, len(genomes)),
@@ -683,7 +699,11 @@ def main():
                          "note": "8 B per genome k-mer (the key a sort or a set must move at least once) over the "
                                  "device time of the whole exact phase; the kernel is a random-access insert, "
                                  "bound by L2 atomics, not by streaming bandwidth"},
-            "parity_checked": {"genomes": checked, "ok": exact_ok, "against": "oracle (CPU sets) on the same pairs"},
+            "sort_merge_variant": {"device_ms_per_genome": sort_ms / max(1, len(genomes)), "same_results": sort_same,
+                                   "what": "set B as a radix-sorted array (cub::DeviceRadixSort over 2k bits) with "
+                                           "binary search, MIEKKI_EXACT_SORT=1; the hash sets above are the default"},
+            "parity_checked": {"genomes": checked, "ok": exact_ok and sort_same,
+                               "against": "oracle (CPU sets) on the same pairs"},
         }
 
     # ---- metric vs #genomes indexed (rank 0, single GPU shapes) --------------------------------

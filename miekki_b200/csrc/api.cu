@@ -1954,30 +1954,56 @@ static int exact_device(mk_ctx* c, const mk_batch* gb, const mk_batch* rb, uint6
             tt += read_lens[i] >= k ? std::max<uint64_t>(4, (read_lens[i] - k + 1) * 2) : 1;
         }
         toff[n_reads] = tt;
-        CU(cudaMallocAsync(reinterpret_cast<void**>(&tableB), slotsB * 8, c->stream));
+        // MIEKKI_EXACT_SORT=1: set B as a sorted array (keys -> radix sort -> binary search) instead of
+        // a hash set; same results, kept for the comparison in DESIGN.md section 4 (read per call)
+        const char* se = getenv("MIEKKI_EXACT_SORT");
+        const bool sorted_b = se && atoi(se) != 0 && wins > 0;
+        std::vector<uint64_t> koff((size_t)n_records + 1, 0);
+        for (uint32_t i = 0; i < n_records; ++i) koff[i + 1] = koff[i] + (rec_lens[i] >= k ? rec_lens[i] - k + 1 : 0);
+        const size_t sort_tmp = sorted_b ? exact_sort_temp_bytes(wins, (int)k) : 0;
+        // hash set: 2 slots per window; sorted: keys | sorted keys | koff | cub scratch
+        const size_t b_bytes = sorted_b ? wins * 16 + ((size_t)n_records + 1) * 8 + sort_tmp + 256 : slotsB * 8;
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&tableB), b_bytes, c->stream));
         CU(cudaMallocAsync(reinterpret_cast<void**>(&rtable), std::max<uint64_t>(1, tt) * 8, c->stream));
         CU(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), (1 + 2 * (size_t)n_reads) * 8, c->stream));
         CU(cudaMallocAsync(reinterpret_cast<void**>(&d_toff), ((size_t)n_reads + 1) * 8, c->stream));
         PhaseTimer t(c, PH_EXACT);
-        launch_fill_u64(tableB, slotsB, ~0ull, c->stream);
+        if (!sorted_b) launch_fill_u64(tableB, slotsB, ~0ull, c->stream);
         launch_fill_u64(rtable, tt, ~0ull, c->stream);
         CU(cudaMemsetAsync(d_cnt, 0, (1 + 2 * (size_t)n_reads) * 8, c->stream));
         CU(cudaMemcpyAsync(d_toff, toff.data(), ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         c->stats.kernel_launches += 2;
         const uint32_t YMAX = 32768;
-        for (uint32_t f = 0; f < n_records; f += YMAX) {
-            const uint32_t m = std::min(YMAX, n_records - f);
-            BatchView v = view_of(gb, f, m);
-            launch_exact_insert(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, tableB, slotsB, d_cnt, c->stream);
-            c->stats.kernel_launches += 1;
+        unsigned long long* sortedB = tableB + wins;
+        if (sorted_b) {
+            uint64_t* d_koff = reinterpret_cast<uint64_t*>(tableB + 2 * wins);
+            void* d_tmp = reinterpret_cast<uint8_t*>(d_koff + n_records + 1) + (256 - ((uintptr_t)(d_koff + n_records + 1) & 255)) % 256;
+            CU(cudaMemcpyAsync(d_koff, koff.data(), ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+            if (n_records > YMAX) return fail(c, MK_ERR_ARG, "mk_exact (sorted variant): more than 32,768 records");
+            BatchView v = view_of(gb, 0, n_records);
+            launch_exact_sorted_build(v.chars, v.d_coff, v.d_len, d_koff, n_records, v.max_len, wins, (int)k, tableB,
+                                      sortedB, d_tmp, sort_tmp, d_cnt, c->stream);
+            CU(cudaStreamSynchronize(c->stream));     // koff is a local vector
+            c->stats.kernel_launches += 3;
+        } else {
+            for (uint32_t f = 0; f < n_records; f += YMAX) {
+                const uint32_t m = std::min(YMAX, n_records - f);
+                BatchView v = view_of(gb, f, m);
+                launch_exact_insert(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, tableB, slotsB, d_cnt, c->stream);
+                c->stats.kernel_launches += 1;
+            }
         }
         unsigned long long* d_inter = d_cnt + 1;
         unsigned long long* d_dist = d_cnt + 1 + n_reads;
         for (uint32_t f = 0; f < n_reads; f += YMAX) {
             const uint32_t m = std::min(YMAX, n_reads - f);
             BatchView v = view_of(rb, f, m);
-            launch_exact_reads(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, rtable, d_toff + f, tableB, slotsB,
-                               d_inter + f, d_dist + f, c->stream);
+            if (sorted_b)
+                launch_exact_reads_sorted(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, rtable, d_toff + f, sortedB,
+                                          wins, d_inter + f, d_dist + f, c->stream);
+            else
+                launch_exact_reads(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, rtable, d_toff + f, tableB, slotsB,
+                                   d_inter + f, d_dist + f, c->stream);
             c->stats.kernel_launches += 1;
         }
         CU(cudaGetLastError());

@@ -175,4 +175,16 @@ void launch_exact_reads(const uint8_t* chars, const uint64_t* coff, const uint64
                         const uint64_t* toff, const unsigned long long* tableB, uint64_t slotsB,
                         unsigned long long* inter, unsigned long long* distinctA, cudaStream_t st);
 
+// the sort-merge variant of set B (MIEKKI_EXACT_SORT=1): all windows' k-mers at keys + koff[s],
+// radix-sorted into `sorted`; *distinct += |B|
+size_t exact_sort_temp_bytes(uint64_t n_keys, int k);
+void launch_exact_sorted_build(const uint8_t* chars, const uint64_t* coff, const uint64_t* len, const uint64_t* koff,
+                               uint32_t n_seq, uint64_t max_len, uint64_t n_keys, int k, unsigned long long* keys,
+                               unsigned long long* sorted, void* temp, size_t temp_bytes, unsigned long long* distinct,
+                               cudaStream_t st);
+void launch_exact_reads_sorted(const uint8_t* chars, const uint64_t* coff, const uint64_t* len, uint32_t n_reads,
+                               uint64_t max_len, int k, unsigned long long* rtable, const uint64_t* toff,
+                               const unsigned long long* sortedB, uint64_t nB, unsigned long long* inter,
+                               unsigned long long* distinctA, cudaStream_t st);
+
 }  // namespace mk

@@ -277,8 +277,12 @@ def test_case_a_pipelined_scan_and_topk_slots(mk, case_a):
 
 # ---- exact mode ---------------------------------------------------------------------------
 
+@pytest.mark.parametrize("sort_variant", ["0", "1"])
 @pytest.mark.parametrize("s,fname", [(200, "exact.txt"), (0, "exact_s0.txt")])
-def test_case_a_exact_lines_equal_reference(case_a, s, fname):
+def test_case_a_exact_lines_equal_reference(case_a, s, fname, sort_variant, monkeypatch):
+    """sort_variant = 1: set B as a radix-sorted array with binary search (MIEKKI_EXACT_SORT), the
+    sort-merge wording of BASELINE.json's north_star; 0: the hash sets that ship by default."""
+    monkeypatch.setenv("MIEKKI_EXACT_SORT", sort_variant)
     d, ix, _ = case_a
     k = 31
     names = H.load_list(d)
@@ -304,7 +308,9 @@ def test_case_a_exact_lines_equal_reference(case_a, s, fname):
     assert Counter(lines) == Counter(want)
 
 
-def test_exact_edge_cases(mk):
+@pytest.mark.parametrize("sort_variant", ["0", "1"])
+def test_exact_edge_cases(mk, monkeypatch, sort_variant):
+    monkeypatch.setenv("MIEKKI_EXACT_SORT", sort_variant)
     ix = mk.Miekki(k=31, h=10)
     rng = np.random.default_rng(3)
     g = rand_seq(rng, 5000, special=True)
