@@ -501,31 +501,41 @@ def main():
             self.n = len(rlens)
             self.offsets, self.rlens = offsets, rlens
             self.reads_np = reads_np
-            self.pinned = torch.from_numpy(reads_np).pin_memory()
+            # Two orders of the same reads, used by alternate steps (B = A reversed): consecutive
+            # batches then differ, so a hit list that belongs to another batch (a stale buffer in
+            # the pipelined multi-GPU path) cannot pass the parity check by coincidence.
+            self.pinned = [torch.from_numpy(reads_np).pin_memory(),
+                           torch.from_numpy(np.ascontiguousarray(reads_np[::-1])).pin_memory()]
             self.hits_host = torch.empty((self.n, K * 24), dtype=torch.uint8).pin_memory()
             self.nh_host = torch.empty(self.n, dtype=torch.int32).pin_memory()
             self.d_heap = torch.zeros((self.n, K * 24), dtype=torch.uint8, device="cuda")
             self.d_len = torch.zeros(self.n, dtype=torch.int32, device="cuda")
-            self.resident = index.upload_flat_ptr(self.pinned.data_ptr(), offsets, rlens)
+            self.resident = [index.upload_flat_ptr(p.data_ptr(), offsets, rlens) for p in self.pinned]
+            self.step_no = 0            # steps run so far: step s uses order s & 1
+            self.last_order = 0         # order of the reads of the last end-to-end step
 
         def run_resident(self, steps):
             """`steps` passes over the reads already in HBM; hit lists stay in HBM."""
+            first_step, self.step_no = self.step_no, self.step_no + steps
             if world == 1:
-                for _ in range(steps):
-                    self.ix.query_batch(self.resident, K, 10, self.min_int, fetch=False)
+                for s_ in range(first_step, first_step + steps):
+                    self.ix.query_batch(self.resident[s_ & 1], K, 10, self.min_int, fetch=False)
             else:
                 # scan of step i+1 is in flight while step i's heap is chained through the ranks
-                sharded.pipelined_query(self.ix, (self.resident for _ in range(steps)), self.d_heap, self.d_len,
-                                        K, 10, self.min_int)
+                sharded.pipelined_query(self.ix, (self.resident[s_ & 1] for s_ in range(first_step, first_step + steps)),
+                                        self.d_heap, self.d_len, K, 10, self.min_int)
 
         def run_e2e(self, steps):
             """Same through host buffers: every step uploads its reads from pinned host memory and
             brings the hit lists back to the host."""
+            first_step, self.step_no = self.step_no, self.step_no + steps
+            if steps:
+                self.last_order = (first_step + steps - 1) & 1
             if world == 1:
                 import ctypes as C
                 lib = miekki_b200.lib()
-                for _ in range(steps):
-                    b = self.ix.upload_flat_ptr(self.pinned.data_ptr(), self.offsets, self.rlens)   # H2D
+                for s_ in range(first_step, first_step + steps):
+                    b = self.ix.upload_flat_ptr(self.pinned[s_ & 1].data_ptr(), self.offsets, self.rlens)   # H2D
                     self.ix._ck(lib.mk_query_batch(self.ix._ctx, b._h, K, 10, self.min_int,
                                                    C.c_void_p(self.hits_host.data_ptr()),
                                                    C.c_void_p(self.nh_host.data_ptr())))
@@ -535,7 +545,8 @@ def main():
 
             def uploads():
                 for i in range(steps):
-                    live[i] = self.ix.upload_flat_ptr(self.pinned.data_ptr(), self.offsets, self.rlens)
+                    live[i] = self.ix.upload_flat_ptr(self.pinned[(first_step + i) & 1].data_ptr(), self.offsets,
+                                                      self.rlens)
                     yield live[i]
 
             def fetched(i):                              # last rank: D2H of batch i's hit lists
@@ -568,15 +579,17 @@ def main():
         def parity(self, n_sample, first_id):
             """the hit lists of the LAST end-to-end step (hits_host / nh_host on the last rank)"""
             n_sample = max(1, min(n_sample, self.n))
-            idx = np.unique(np.linspace(0, self.n - 1, n_sample).astype(np.int64))
+            idx = np.unique(np.linspace(0, self.n - 1, n_sample).astype(np.int64))   # positions in the last batch
             L = int(self.rlens[0])
-            seqs = [self.reads_np[i, :L].tobytes() for i in idx]
+            src = (self.n - 1 - idx) if self.last_order else idx                   # the reads at those positions
+            seqs = [self.reads_np[i, :L].tobytes() for i in src]
             got = self.hits_host.numpy().view(miekki_b200.HIT_DTYPE).reshape(self.n, K)
             return check_hit_lists(self.ix, seqs, idx, got, self.nh_host.numpy().view(np.uint32), first_id, 10,
                                    self.min_int, world, rank, dist, torch)
 
         def close(self):
-            self.resident.free()
+            for r in self.resident:
+                r.free()
 
     # ---- headline: config 2 ---------------------------------------------------------------
     w2 = Workload(ix, reads_np, offsets, rlens, 0.5 * a.threshold)

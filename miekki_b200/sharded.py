@@ -81,15 +81,34 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
     heap is chained through the ranks, so the cheap, latency-bound chain hides behind the scan.
     `batches` yields engine batches; `on_result(i)` is called on the last rank when batch i's hit
     lists are final in (heap, lens); `after_chain(i)` on every rank once its own step for batch i
-    is done (its scan has run by then, so the batch may be freed)."""
+    is done (its scan has run by then, so the batch may be freed).
+
+    Consecutive batches travel in alternating buffers: an NCCL send only completes when the next
+    rank has posted its receive, which may be a whole scan later, so the buffer a batch was sent
+    from must not be written again (by the next batch's top-k on the first rank) before that.
+    A buffer is reused two batches later, after the event recorded behind its sends."""
     side = torch.cuda.Stream() if heap.is_cuda else None
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bufs = [(heap, lens), (torch.empty_like(heap), torch.empty_like(lens))]
+    sent = [None, None]
 
     def finish(i, slot):
+        h, l = bufs[i & 1]
+
         def body():
-            chained_topk(engine, heap, lens, nresults, min_score, min_intersection, group, slot)
+            if sent[i & 1] is not None:
+                sent[i & 1].synchronize()           # the sends of batch i - 2 have left this buffer
+            chained_topk(engine, h, l, nresults, min_score, min_intersection, group, slot)
+            if side is not None and rank < world - 1:
+                sent[i & 1] = torch.cuda.Event()
+                sent[i & 1].record(torch.cuda.current_stream())
             if on_result is not None and rank == world - 1:
+                if h is not heap:                   # results are handed over in the caller's tensors
+                    heap.copy_(h)
+                    lens.copy_(l)
+                    if side is not None:
+                        torch.cuda.current_stream().synchronize()
                 on_result(i)
             if after_chain is not None:
                 after_chain(i)
@@ -107,5 +126,14 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
         pending = (i, slot)
     if pending is not None:
         finish(*pending)
+        if on_result is None and rank == world - 1 and (pending[0] & 1):
+            # the last batch went through the second buffer: its hit lists belong in the caller's
+            if side is not None:
+                with torch.cuda.stream(side):
+                    heap.copy_(bufs[1][0])
+                    lens.copy_(bufs[1][1])
+            else:
+                heap.copy_(bufs[1][0])
+                lens.copy_(bufs[1][1])
     if side is not None:
         side.synchronize()
