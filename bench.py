@@ -460,6 +460,7 @@ def main():
         mine = torch.empty(w, dtype=torch.uint8, device="cuda")
         index.bloom_get_ptr(mine.data_ptr(), w)
         merged = sharded.merge_bloom(mine).contiguous()
+        torch.cuda.current_stream().synchronize()      # the fold must have run before the context copies it
         index.bloom_set_ptr(merged.data_ptr(), w)
 
     def build_rates(st, insert_wall):

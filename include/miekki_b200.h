@@ -158,7 +158,9 @@ uint64_t mk_bloom_reach(uint32_t k, uint32_t bloom_log2);
 int mk_bloom_get(mk_ctx *ctx, uint8_t *dst, uint64_t n);
 int mk_bloom_merge(mk_ctx *ctx, const uint8_t *src, uint64_t n);
 int mk_bloom_set(mk_ctx *ctx, const uint8_t *src, uint64_t n);   /* replace the first n bytes */
-/* dst/src of the three calls above may be host or device pointers (unified addressing). */
+/* dst/src of the three calls above may be host or device pointers (unified addressing).  A device
+ * buffer must be complete when the call is made: the copy runs on the context's stream (see
+ * mk_set_stream), which does not wait for work queued on other streams. */
 
 /* ---- query ----------------------------------------------------------------- */
 

@@ -37,6 +37,7 @@ def main():
     mine = torch.empty(w, dtype=torch.uint8, device="cuda")
     ix.bloom_get_ptr(mine.data_ptr(), w)
     merged = sharded.merge_bloom(mine).contiguous()
+    torch.cuda.synchronize()       # the fold ran on torch's stream; the context copies on its own
     ix.bloom_set_ptr(merged.data_ptr(), w)
 
     o = orc.Oracle(k=k, h=h, cap=G)

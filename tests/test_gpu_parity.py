@@ -910,3 +910,65 @@ def test_packed_upload_equals_oracle(mk, monkeypatch, k, h):
         assert np.array_equal(e["sketch_size"], o.sketch_size) and np.array_equal(e["genome_size"], o.genome_size), mode
         m = min(len(e["bloom"]), len(o.bloom))
         assert np.array_equal(e["bloom"][:m], o.bloom[:m]), mode
+
+
+@pytest.mark.parametrize("R", [2, 4, 7])
+def test_pipelined_chain_over_shards_on_one_gpu(mk, R):
+    """The data path of sharded.pipelined_query without NCCL: R contexts on one GPU hold contiguous
+    shards (19 genomes or fewer each at R = 4: one 32-genome group), every batch is scanned with
+    mk_scan_async (batch i + 1 before batch i's heap step) and the heap goes through the shards
+    with mk_topk_slot on device buffers.  Same genomes and reads as tests/nccl_worker.py."""
+    import torch
+    from miekki_b200 import sharded, synth
+    k, h, G, GL = 31, 12, 75, 60_000
+    rng = np.random.default_rng(42)
+    genomes = [synth.genome(g, GL) for g in range(G - 15)]
+    for j in range(15):
+        genomes.append(synth.substitute(np.frombuffer(genomes[3 * j], np.uint8), 0.01 + 0.002 * j, rng).tobytes())
+    reads = [s for _, s in synth.sample_reads(genomes, 330, 1500, sub_rate=0.01, block=9)]
+    o = orc.Oracle(k=k, h=h, cap=G)
+    for s in genomes:
+        o.insert(s)
+    engines = []
+    for r in range(R):
+        first, count = sharded.shard_range(G, r, R)
+        ix = mk.Miekki(k=k, h=h, threshold=200)
+        ix.set_shard(first)
+        ix.insert_sequences(genomes[first:first + count])
+        engines.append(ix)
+    merged = sharded.fold_bloom([torch.from_numpy(e.bloom_get()) for e in engines]).numpy()
+    m = min(len(merged), len(o.bloom))
+    assert np.array_equal(merged[:m], o.bloom[:m])
+    for e in engines:
+        e.bloom_set(merged)
+    K, nb = 10, 3
+    per = len(reads) // nb
+    for thr in (200, 0):
+        batches = [[e.upload(reads[b * per:(b + 1) * per]) for b in range(nb)] for e in engines]
+        bufs = [(torch.zeros((per, K * 24), dtype=torch.uint8, device="cuda"),
+                 torch.zeros(per, dtype=torch.int32, device="cuda")) for _ in range(2)]
+        got, pending = {}, None
+
+        def finish(i, slots):
+            hp, ln = bufs[i & 1]
+            for r, e in enumerate(engines):
+                e.topk_slot_ptr(slots[r], hp.data_ptr(), ln.data_ptr(), K, 10, 0.5 * thr, chain_in=r > 0,
+                                finalize=r == R - 1)
+            got[i] = (hp.cpu().numpy().view(mk.HIT_DTYPE).reshape(per, K).copy(), ln.cpu().numpy().view(np.uint32).copy())
+        for i in range(nb):
+            slots = [e.scan_async(batches[r][i]) for r, e in enumerate(engines)]
+            if pending is not None:
+                finish(*pending)
+            pending = (i, slots)
+        finish(*pending)
+        for b in range(nb):
+            hh, ll = got[b]
+            for j in range(per):
+                oc, _ = o.counts(reads[b * per + j])
+                want = o.filter(oc, K, 10, 0.5 * thr)
+                assert orc.format_hit_line(">r", hh[j, :ll[j]]) == orc.format_hit_line(">r", want), (R, thr, b, j)
+        for bs in batches:
+            for bt in bs:
+                bt.free()
+    for e in engines:
+        e.close()
