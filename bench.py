@@ -627,8 +627,9 @@ def main():
         # -s 0: at -h 17 every 5 Mbp sketch is saturated, genome_size = 0 (quirk G2) and the default
         # -s leaves every list empty; -s 0 keeps the all-ties heap order in play
         w3 = Workload(ix3, r3, o3, l3, 0.0)
-        d3_ms, _, st3 = w3.timed(w3.run_resident, a.c3_steps, 1)
-        _, e3_wall_ms, _ = w3.timed(w3.run_e2e, 1, 1)
+        # two warm-up steps: the pipelined path alternates between two sets of buffers, both are sized before timing
+        d3_ms, _, st3 = w3.timed(w3.run_resident, a.c3_steps, 2)
+        _, e3_wall_ms, _ = w3.timed(w3.run_e2e, 2, 2)
         par3 = w3.parity(16, gfirst)
         c3_kbp = a.c3_reads * a.c3_read_len / 1e3
         extras["c3_strong"] = {
@@ -638,7 +639,7 @@ def main():
                                                                       100 * a.c3_sub_rate),
             "scaling": "strong", "steps": a.c3_steps, "ms_per_step": d3_ms / a.c3_steps,
             "job_kbp_per_s": c3_kbp * a.c3_steps / (d3_ms / 1e3),
-            "e2e_job_kbp_per_s": c3_kbp / (e3_wall_ms / 1e3),
+            "e2e_job_kbp_per_s": 2 * c3_kbp / (e3_wall_ms / 1e3),
             "scan_gbs_algorithmic_this_rank": st3["scan_row_bytes"] / max(st3["scan_ms"], 1e-9) / 1e6,
             "scan_frac_of_peak": st3["scan_row_bytes"] / max(st3["scan_ms"], 1e-9) / 1e6 / peak,
             "phases_ms_per_step": {"read_sketch": st3["read_sketch_ms"] / a.c3_steps,

@@ -622,16 +622,11 @@ struct Candidate {
     double jaccard, intersection;
 };
 
-// Miekki.cpp:792-859 for one genome file; returns the text block of its lines
-string ground_truth(Index& ix, mk_ctx* ctx, const string& file, vector<Candidate>& v) {
+// Miekki.cpp:823-859 for one genome file whose records (:801-822) are already parsed; returns the
+// text block of its lines
+string ground_truth(mk_ctx* ctx, const string& file, const vector<string>& recs, vector<Candidate>& v) {
     ostringstream os;
     if (v.empty()) return "";
-    if (!exists_test(file)) {
-        #pragma omp critical(msg)
-        cout << "File problem: " << file << endl;                // :796-799
-        return "";
-    }
-    vector<string> recs = mkcli::read_genome_records(file, ix.k);
     vector<const char*> rp(recs.size()), qp(v.size());
     vector<uint64_t> rl(recs.size()), ql(v.size());
     for (size_t i = 0; i < recs.size(); ++i) { rp[i] = recs[i].data(); rl[i] = recs[i].size(); }
@@ -652,20 +647,58 @@ string ground_truth(Index& ix, mk_ctx* ctx, const string& file, vector<Candidate
     return os.str();
 }
 
-// genomes are independent: one host thread per GPU works through them
+// Genomes are independent.  Their files are read and cut into records by the host team a wave
+// ahead of the device (the reference re-reads the file inside ground_truth_batch, :800-822), and
+// one host thread per GPU works through the parsed wave.
 void ground_truth_all(Index& ix, map<uint32_t, vector<Candidate>>& per_genome) {
     vector<pair<uint32_t, vector<Candidate>*>> work;
-    for (auto& kv : per_genome) work.push_back({kv.first, &kv.second});
+    for (auto& kv : per_genome)
+        work.push_back({kv.first, &kv.second});
     vector<string> text(work.size());
     const int R = (int)ix.shard.size();
-    LoopError err;
-    #pragma omp parallel for num_threads(R) schedule(dynamic, 1)
-    for (size_t i = 0; i < work.size(); ++i)
-        err.run([&] {
-            text[i] = ground_truth(ix, ix.shard[(size_t)omp_get_thread_num() % ix.shard.size()],
-                                   ix.file_names[work[i].first], *work[i].second);
-        });
-    err.rethrow();
+    const size_t wave = max<size_t>(16, 4 * (size_t)ix.threads);
+    struct Parsed {
+        vector<vector<string>> recs;
+        vector<char> ok;
+    };
+    auto parse = [&](size_t w0) {
+        Parsed p;
+        const size_t m = min(wave, work.size() - w0);
+        p.recs.resize(m);
+        p.ok.assign(m, 0);
+        LoopError err;
+        #pragma omp parallel for num_threads(ix.threads) schedule(dynamic, 1)
+        for (size_t i = 0; i < m; ++i) {
+            if (work[w0 + i].second->empty()) continue;
+            const string& file = ix.file_names[work[w0 + i].first];
+            if (!exists_test(file)) {
+                #pragma omp critical(msg)
+                cout << "File problem: " << file << endl;        // :796-799
+                continue;
+            }
+            err.run([&] {
+                p.recs[i] = mkcli::read_genome_records(file, ix.k);
+                p.ok[i] = 1;
+            });
+        }
+        err.rethrow();
+        return p;
+    };
+    future<Parsed> next;
+    if (!work.empty()) next = async(launch::async, parse, (size_t)0);
+    for (size_t w0 = 0; w0 < work.size(); w0 += wave) {
+        Parsed cur = next.get();
+        if (w0 + wave < work.size()) next = async(launch::async, parse, w0 + wave);
+        LoopError err;
+        #pragma omp parallel for num_threads(R) schedule(dynamic, 1)
+        for (size_t i = 0; i < cur.recs.size(); ++i)
+            if (cur.ok[i])
+                err.run([&] {
+                    text[w0 + i] = ground_truth(ix.shard[(size_t)omp_get_thread_num() % ix.shard.size()],
+                                                ix.file_names[work[w0 + i].first], cur.recs[i], *work[w0 + i].second);
+                });
+        err.rethrow();
+    }
     for (const string& s : text) *ix.out << s;
     per_genome.clear();
 }
