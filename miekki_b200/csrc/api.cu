@@ -767,7 +767,7 @@ struct Lists {
 // 1 forces the choice where legal (tests, A/B measurements).
 constexpr uint64_t TILED_MAX_ENTRIES = 16380;
 bool want_tiled(const mk_ctx* c, const uint64_t* lens, uint32_t n) {
-    if (c->n == 0 || c->h > (uint32_t)TILED_MAX_H || c->h < 5 || n == 0) return false;
+    if (c->n == 0 || c->h > (uint32_t)TILED_MAX_H || c->h < 5 || n == 0 || !tiled_scan_available()) return false;
     const char* e = getenv("MIEKKI_SCAN_TILED");
     if (e && atoi(e) == 0) return false;
     uint64_t total = 0;

@@ -143,6 +143,8 @@ struct TiledPlan {
     int grid;
 };
 int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes, TiledPlan* out);
+// the driver exports cuTensorMapEncodeTiled (looked up once, no link-time dependency on libcuda)
+bool tiled_scan_available();
 // entries a sorted list of `entries` entries occupies with its sentinels
 uint32_t sorted_list_capacity(uint64_t entries);
 // list (bucket << 8 | fp, any order) -> slist + soff[q] (8-byte entries {bucket * 1024, fp * 32}):

@@ -417,6 +417,8 @@ int launch_tiled_t(const TiledPlan& plan, const CUtensorMap& map, const uint2* s
 
 }  // namespace
 
+bool tiled_scan_available() { return encode_fn() != nullptr; }
+
 uint32_t sorted_list_capacity(uint64_t entries) { return (uint32_t)(((entries + 63) & ~63ull) + 128); }
 
 int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes, TiledPlan* out) {
