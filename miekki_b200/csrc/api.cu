@@ -762,28 +762,24 @@ struct Lists {
 
 // Which scan kernel serves a batch of reads?  The tiled kernel streams every row of the index once
 // per tile of reads instead of one row per (read, bucket) pair: worth it when the reads of a tile
-// together cover the bucket space a few times over (long reads at small -h), legal when the list
-// sort fits shared memory (-h <= 17) and no list exceeds the tiled counters.  MIEKKI_SCAN_TILED=0 /
-// 1 forces the choice where legal (tests, A/B measurements).
-constexpr uint64_t TILED_MAX_ENTRIES = 16380;
+// together cover the bucket space a few times over (long reads or whole genomes at small -h) and
+// there are enough (read tile, genome tile) items to fill the GPU; legal when the list sort fits
+// shared memory (-h <= 17).  MIEKKI_SCAN_TILED=0 / 1 forces the choice where legal (tests, A/B
+// measurements).
 bool want_tiled(const mk_ctx* c, const uint64_t* lens, uint32_t n) {
     if (c->n == 0 || c->h > (uint32_t)TILED_MAX_H || c->h < 5 || n == 0 || !tiled_scan_available()) return false;
     const char* e = getenv("MIEKKI_SCAN_TILED");
     if (e && atoi(e) == 0) return false;
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t ent = std::min<uint64_t>(lens[i] > c->k ? lens[i] - c->k : 0, c->B);
-        if (ent > TILED_MAX_ENTRIES) return false;
-        total += ent;
-    }
     if (e && atoi(e) == 1) return true;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) total += std::min<uint64_t>(lens[i] > c->k ? lens[i] - c->k : 0, c->B);
     TiledPlan plan{};
     if (tiled_plan(c->n, (int)c->h, c->sm_count, c->smem_optin, &plan) != 0) return false;
     // expected (read, row) pairs per staged row: 0.9 = share of k-mers that end up as list entries
     const double cover = 0.9 * (double)plan.tile_reads * ((double)total / n) / (double)c->B;
-    return cover >= 2.0 && c->n >= 768 && n >= 4 * plan.tile_reads;
+    const uint64_t items = (uint64_t)((n + plan.tile_reads - 1) / plan.tile_reads) * plan.n_gt;
+    return cover >= 2.0 && c->n >= 768 && items >= 2 * (uint64_t)c->sm_count;
 }
-constexpr uint64_t SPARSE_MAX_KMERS = 12288;   // 16384-slot table at load <= 0.75
 
 // small pinned staging areas for per-call metadata (two, alternating): uploads from them never
 // make the host wait for work already queued on the stream, which mk_scan_async relies on

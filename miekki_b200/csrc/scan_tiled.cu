@@ -109,6 +109,37 @@ struct TileCounters {
     }
 };
 
+// 14 planes overflow after 4,095 blocks of four rows: a read with a longer list (a whole genome as
+// a query) has its counts written out before that (checked once per stage) and starts again from zero; the
+// first write stores, later ones add (RN_ADD in ReadState::rn).  Out of line: it runs once per
+// 16,380 list entries and at the end of an item.
+constexpr uint32_t FLUSH_BLOCKS = 4095;
+struct TileConst {                               // launch constants the flush needs, kept in shared memory
+    uint32_t* counts;
+    uint32_t n_pad, n_groups, n_gt, n_reads;
+};
+// slot = index of the read inside the tile (warp * J + j); rt / gt = the item (from the stage's meta)
+__device__ __noinline__ void flush_counts(TileCounters cnt, uint32_t nblk, bool add, const TileConst* tc, uint32_t rt,
+                                          uint32_t gt, uint32_t tile_reads, uint32_t slot, uint32_t lane) {
+    const uint32_t q = rt * tile_reads + slot;
+    const uint32_t glo = (uint32_t)(((uint64_t)gt * tc->n_groups) / tc->n_gt);
+    const uint32_t ghi = (uint32_t)(((uint64_t)(gt + 1) * tc->n_groups) / tc->n_gt);
+    if (q >= tc->n_reads || glo + lane >= ghi) return;      // a read past the end of the batch / a lane without a group
+    uint32_t P[32];
+    cnt.planes(nblk, P);
+    transpose32(P);                              // P[i] = count of genome 32 (glo + lane) + i
+    uint4* o = reinterpret_cast<uint4*>(tc->counts + (uint64_t)q * tc->n_pad + 32ull * (glo + lane));
+    #pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        uint4 w = make_uint4(P[4 * v], P[4 * v + 1], P[4 * v + 2], P[4 * v + 3]);
+        if (add) {
+            const uint4 old = o[v];
+            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+        }
+        o[v] = w;
+    }
+}
+
 // A sorted list entry is two words, the shared-memory offsets the scan needs: {bucket * ROW_BYTES,
 // fp * 32}.  A warp keeps a window of 64 entries of each of its reads in shared memory (two chunks
 // of 32, one entry per lane and chunk); an entry fetch is one broadcast 8-byte load, and the
@@ -121,8 +152,9 @@ struct ReadState {
     uint32_t x0, x1, x2;          // equality planes of the rows gathered so far (r of them)
     uint2 pre;                    // this lane's entry of the chunk after the two in the window
     uint32_t ptr;                 // absolute index (in slist) of the next entry; lists start at multiples of 64
-    uint32_t rn;                  // r << 24 | nblk
+    uint32_t rn;                  // r << 24 | RN_ADD | nblk
 };
+constexpr uint32_t RN_ADD = 1u << 23, RN_NBLK = RN_ADD - 1;
 
 // The window holds the chunk of `ptr` and the next one.  When ptr enters the newer chunk, the
 // prefetched chunk replaces the older one and the chunk after it is requested: once per 32
@@ -175,7 +207,7 @@ __device__ __forceinline__ void run_stage(ReadState& s, uint32_t stage_end, uint
     if (r == 2) goto L2;
     if (r == 3) goto L3;
 L0:
-    if (!take(s, e, stage_end, win, slist, lane)) { s.rn &= 0xFFFFFFu; return; }
+    if (!take(s, e, stage_end, win, slist, lane)) { s.rn &= 0xFFFFFFu; return; }   // r = 0, RN_ADD / nblk kept
     s.x0 = match(e, row_base, mask_tab);
 L1:
     if (!take(s, e, stage_end, win, slist, lane)) { s.rn = (s.rn & 0xFFFFFFu) | (1u << 24); return; }
@@ -186,8 +218,8 @@ L2:
 L3:
     if (!take(s, e, stage_end, win, slist, lane)) { s.rn = (s.rn & 0xFFFFFFu) | (3u << 24); return; }
     x3 = match(e, row_base, mask_tab);
-    s.cnt.add4(s.x0, s.x1, s.x2, x3, s.rn & 0xFFFFFFu);
-    ++s.rn;                                                       // nblk: far from the r field
+    s.cnt.add4(s.x0, s.x1, s.x2, x3, s.rn & RN_NBLK);
+    ++s.rn;                                                       // nblk: stays below RN_ADD (flushed in time)
     goto L0;
 }
 
@@ -205,8 +237,16 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restr
     uint64_t* full = reinterpret_cast<uint64_t*>(windows + (size_t)NWARPS * J * WINDOW_BYTES);
     uint64_t* empty = full + stages;
     TileMeta* meta = reinterpret_cast<TileMeta*>(empty + stages);
+    TileConst* tc = reinterpret_cast<TileConst*>(meta + stages);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tc->counts = counts;
+        tc->n_pad = n_pad;
+        tc->n_groups = n_groups;
+        tc->n_gt = n_gt;
+        tc->n_reads = n_reads;
+    }
     // mask_tab[fp][p] = (fp bit p) ? 0 : ~0
     for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x)
         mask_tab[i] = ((i >> 3) >> (i & 7)) & 1u ? 0u : 0xFFFFFFFFu;
@@ -284,32 +324,29 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restr
             const uint32_t row_base = ring_addr + (uint32_t)stage * stage_bytes + lane * 16u - row0 * ROW_BYTES;
             const uint32_t stage_end = (row0 + S) * ROW_BYTES;
             #pragma unroll
-            for (int j = 0; j < J; ++j)
+            for (int j = 0; j < J; ++j) {
                 run_stage(rs[j], stage_end, row_base, mt_addr, win_addr + (uint32_t)j * WINDOW_BYTES, slist, lane);
+                // a stage adds at most S / 4 blocks: write the counts out before the planes can overflow
+                if ((rs[j].rn & RN_NBLK) + S / 4 + 1 > FLUSH_BLOCKS && !(flags & T_LAST)) {
+                    flush_counts(rs[j].cnt, rs[j].rn & RN_NBLK, (rs[j].rn & RN_ADD) != 0, tc, rt, gt, RT, warp * J + j, lane);
+                    rs[j].cnt.reset();
+                    rs[j].rn = (rs[j].rn & ~RN_NBLK) | RN_ADD;
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);       // stage may be refilled
             if (++stage == stages) { stage = 0; phase ^= 1; }
             if (flags & T_LAST) {
-                const uint32_t glo = (uint32_t)(((uint64_t)gt * n_groups) / n_gt);
-                const uint32_t ghi = (uint32_t)(((uint64_t)(gt + 1) * n_groups) / n_gt);
                 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const uint32_t q = rt * RT + warp * J + j;
                     // the rows still waiting in the block of four (absent ones count as no match)
                     const uint32_t r = rs[j].rn >> 24;
-                    uint32_t nblk = rs[j].rn & 0xFFFFFFu;
+                    uint32_t nblk = rs[j].rn & RN_NBLK;
                     if (r) {
                         rs[j].cnt.add4(rs[j].x0, r > 1 ? rs[j].x1 : 0u, r > 2 ? rs[j].x2 : 0u, 0u, nblk);
                         ++nblk;
                     }
-                    if (q < n_reads && glo + lane < ghi) {
-                        uint32_t P[32];
-                        rs[j].cnt.planes(nblk, P);
-                        transpose32(P);                       // P[i] = count of genome 32 (glo + lane) + i
-                        uint4* o = reinterpret_cast<uint4*>(counts + (uint64_t)q * n_pad + 32ull * (glo + lane));
-                        #pragma unroll
-                        for (int v = 0; v < 8; ++v) o[v] = make_uint4(P[4 * v], P[4 * v + 1], P[4 * v + 2], P[4 * v + 3]);
-                    }
+                    flush_counts(rs[j].cnt, nblk, (rs[j].rn & RN_ADD) != 0, tc, rt, gt, RT, warp * J + j, lane);
                 }
             }
         }
@@ -441,7 +478,7 @@ int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes,
     while (S & (S - 1)) S &= S - 1;                       // power of two
     S = std::min<uint32_t>(std::min<uint32_t>(S, 256), n_rows);
     out->S = S;
-    const size_t fixed = MASK_TAB_BYTES + (size_t)out->tile_reads * WINDOW_BYTES + 256;
+    const size_t fixed = MASK_TAB_BYTES + (size_t)out->tile_reads * WINDOW_BYTES + 256;   // 256: TileConst, alignment
     const size_t per_stage = (size_t)S * ROW_BYTES + 2 * sizeof(uint64_t) + sizeof(TileMeta);
     int stages = (int)((smem_optin_bytes - fixed) / per_stage);
     stages = std::min(stages, 64);

@@ -972,3 +972,36 @@ def test_pipelined_chain_over_shards_on_one_gpu(mk, R):
                 bt.free()
     for e in engines:
         e.close()
+
+
+def test_tiled_scan_flushes_counters_of_long_lists(mk, monkeypatch):
+    """Lists longer than the tiled kernel's 14 counter planes can count (16,380 entries): the counts
+    are written out in passes (store, then add).  -h 15, sequences of 20-70 kbp (lists of up to
+    ~29,000 entries) against a random matrix in which one genome equals the query's own sketch, so
+    that counts really exceed 16,383."""
+    rng = np.random.default_rng(77)
+    k, h, N = 31, 15, 1100
+    B = 1 << h
+    rows = rng.integers(0, 256, (B, N), dtype=np.uint8)
+    reads = [rand_seq(rng, n) for n in (70_000, 20_000, 45_000, 900, 64_000)] + [rand_seq(rng, 3000) for _ in range(60)]
+    for col, s in ((5, reads[0]), (700, reads[4])):          # a genome that is the query itself
+        fp, _, _ = orc.sketch(s, k, h)
+        rows[:, col] = fp
+    ss = rng.integers(1, B + 1, N).astype(np.uint32)
+    gs = rng.integers(0, 5_000_000, N).astype(np.uint64)
+    o = orc.Oracle(k=k, h=h, cap=N)
+    bloom = np.ones(len(o.bloom), np.uint8)
+    o.load(rows, gs, bloom, ss)
+    ix = mk.Miekki(k=k, h=h, threshold=0)
+    ix.import_(rows, gs, bloom, ss)
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", "1")
+    monkeypatch.setenv("MIEKKI_SCAN_NARROW_GROUPS", "0")
+    counts, surv = ix.query_counts(reads)
+    assert counts[0, 5] == surv[0] and surv[0] > 20_000 and counts[4, 700] == surv[4] > 16_384
+    for i, s in enumerate(reads[:8]):
+        oc, oa = o.counts(s)
+        assert surv[i] == oa and np.array_equal(counts[i], oc), i
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", "0")
+    c2, s2 = ix.query_counts(reads)
+    assert np.array_equal(counts, c2) and np.array_equal(surv, s2)
+    ix.close()
