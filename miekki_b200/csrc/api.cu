@@ -758,6 +758,7 @@ struct Lists {
     // tiled scan (scan_tiled.cu): the same lists sorted by bucket, each ending in sentinels
     void* slist = nullptr;
     uint64_t* soff = nullptr;   // device, n
+    bool long_lists = false;    // some list may exceed the tiled kernel's 14 counter planes
 };
 
 // Which scan kernel serves a batch of reads?  The tiled kernel streams every row of the index once
@@ -780,6 +781,8 @@ bool want_tiled(const mk_ctx* c, const uint64_t* lens, uint32_t n) {
     const uint64_t items = (uint64_t)((n + plan.tile_reads - 1) / plan.tile_reads) * plan.n_gt;
     return cover >= 2.0 && c->n >= 768 && items >= 2 * (uint64_t)c->sm_count;
 }
+
+constexpr uint64_t SPARSE_MAX_KMERS = 12288;   // 16384-slot table at load <= 0.75
 
 // small pinned staging areas for per-call metadata (two, alternating): uploads from them never
 // make the host wait for work already queued on the stream, which mk_scan_async relies on
@@ -925,6 +928,9 @@ int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists*
             CU(cudaGetLastError());
             out->slist = d_slist;
             out->soff = d_soff;
+            out->long_lists = false;
+            for (uint32_t i = 0; i < n && !out->long_lists; ++i)
+                out->long_lists = std::min<uint64_t>(b_len[i] > c->k ? b_len[i] - c->k : 0, c->B) > TILED_SHORT_ENTRIES;
         }
     }
     for (uint32_t i = 0; i < n; ++i) c->stats.bases_queried += b_len[i];
@@ -952,8 +958,8 @@ int scan_reads(mk_ctx* c, const Lists& L, uint32_t q0, uint32_t nq, const ScanPl
         TiledPlan tp{};
         r = tiled_plan(c->n, (int)c->h, c->sm_count, c->smem_optin, &tp);
         if (r == 0)
-            r = launch_scan_tiled(tp, c->rows, c->stride, c->n, (int)c->h, L.slist, L.soff + q0, nq, out, c->d_work,
-                                  c->stream);
+            r = launch_scan_tiled(tp, c->rows, c->stride, c->n, (int)c->h, L.slist, L.soff + q0, nq, L.long_lists, out,
+                                  c->d_work, c->stream);
     } else {
         r = launch_scan(plan, c->rows, c->stride, c->n, L.list, L.list_off + q0, L.list_len + q0, nq, out, c->d_work,
                         c->stream);

@@ -133,6 +133,7 @@ int launch_scan(const ScanPlan& plan, const uint8_t* rows, uint64_t stride, uint
 // owns a tile of reads x 1,024 genomes and streams every row of its genome tile through shared
 // memory once (TMA tensor copies), each staged row serving all reads of the tile that hit it.
 constexpr int TILED_MAX_H = 17;      // the list sort keeps one byte per bucket in shared memory
+constexpr uint64_t TILED_SHORT_ENTRIES = 16380;   // lists up to here fit the 14 counter planes without a flush
 struct TiledPlan {
     int J, warps;           // reads per consumer warp, consumer warps
     uint32_t tile_reads;    // J * warps
@@ -154,7 +155,7 @@ constexpr size_t SORTED_ENTRY_BYTES = 8;
 void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
                        void* slist, const uint64_t* soff, cudaStream_t st);
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
-                      const void* slist, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
+                      const void* slist, const uint64_t* soff, uint32_t n_reads, bool long_lists, uint32_t* counts,
                       uint32_t* work_counter, cudaStream_t st);
 
 // ---- topk.cu --------------------------------------------------------------------

@@ -223,7 +223,9 @@ L3:
     goto L0;
 }
 
-template <int J, int NWARPS>
+// LONG: lists may exceed TILED_SHORT_ENTRIES entries; the counters are then checked once per stage
+// and written out in passes (measured: 15 % slower, so reads that cannot need it do without)
+template <int J, int NWARPS, bool LONG>
 __global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
 scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restrict__ slist,
                   const uint64_t* __restrict__ soff, uint32_t n_reads, uint32_t n_groups, uint32_t n_pad,
@@ -327,7 +329,7 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restr
             for (int j = 0; j < J; ++j) {
                 run_stage(rs[j], stage_end, row_base, mt_addr, win_addr + (uint32_t)j * WINDOW_BYTES, slist, lane);
                 // a stage adds at most S / 4 blocks: write the counts out before the planes can overflow
-                if ((rs[j].rn & RN_NBLK) + S / 4 + 1 > FLUSH_BLOCKS && !(flags & T_LAST)) {
+                if (LONG && (rs[j].rn & RN_NBLK) + S / 4 + 1 > FLUSH_BLOCKS && !(flags & T_LAST)) {
                     flush_counts(rs[j].cnt, rs[j].rn & RN_NBLK, (rs[j].rn & RN_ADD) != 0, tc, rt, gt, RT, warp * J + j, lane);
                     rs[j].cnt.reset();
                     rs[j].rn = (rs[j].rn & ~RN_NBLK) | RN_ADD;
@@ -346,7 +348,21 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restr
                         rs[j].cnt.add4(rs[j].x0, r > 1 ? rs[j].x1 : 0u, r > 2 ? rs[j].x2 : 0u, 0u, nblk);
                         ++nblk;
                     }
-                    flush_counts(rs[j].cnt, nblk, (rs[j].rn & RN_ADD) != 0, tc, rt, gt, RT, warp * J + j, lane);
+                    if constexpr (LONG) {
+                        flush_counts(rs[j].cnt, nblk, (rs[j].rn & RN_ADD) != 0, tc, rt, gt, RT, warp * J + j, lane);
+                    } else {
+                        const uint32_t q = rt * RT + warp * J + j;
+                        const uint32_t glo = (uint32_t)(((uint64_t)gt * n_groups) / n_gt);
+                        const uint32_t ghi = (uint32_t)(((uint64_t)(gt + 1) * n_groups) / n_gt);
+                        if (q < n_reads && glo + lane < ghi) {
+                            uint32_t P[32];
+                            rs[j].cnt.planes(nblk, P);
+                            transpose32(P);                   // P[i] = count of genome 32 (glo + lane) + i
+                            uint4* o = reinterpret_cast<uint4*>(counts + (uint64_t)q * n_pad + 32ull * (glo + lane));
+                            #pragma unroll
+                            for (int v = 0; v < 8; ++v) o[v] = make_uint4(P[4 * v], P[4 * v + 1], P[4 * v + 2], P[4 * v + 3]);
+                        }
+                    }
                 }
             }
         }
@@ -439,17 +455,17 @@ PFN_cuTensorMapEncodeTiled encode_fn() {
     return fn;
 }
 
-template <int J, int NWARPS>
+template <int J, int NWARPS, bool LONG>
 int launch_tiled_t(const TiledPlan& plan, const CUtensorMap& map, const uint2* slist, const uint64_t* soff,
                    uint32_t n_reads, uint32_t n_genomes, uint32_t n_rows, uint32_t* counts, uint32_t* work_counter,
                    cudaStream_t st) {
-    if (!smem_optin(reinterpret_cast<const void*>(scan_tiled_kernel<J, NWARPS>), plan.smem)) return -1;
+    if (!smem_optin(reinterpret_cast<const void*>(scan_tiled_kernel<J, NWARPS, LONG>), plan.smem)) return -1;
     const uint32_t n_groups = (n_genomes + 31) / 32;
     const uint32_t n_rt = (n_reads + plan.tile_reads - 1) / plan.tile_reads;
     const uint64_t items = (uint64_t)n_rt * plan.n_gt;
     int grid = plan.grid;
     if ((uint64_t)grid > items) grid = (int)items;
-    scan_tiled_kernel<J, NWARPS><<<grid, (NWARPS + 1) * 32, plan.smem, st>>>(
+    scan_tiled_kernel<J, NWARPS, LONG><<<grid, (NWARPS + 1) * 32, plan.smem, st>>>(
         map, slist, soff, n_reads, n_groups, n_groups * 32, plan.n_gt, n_rt, n_rows, plan.S, plan.stages, counts,
         work_counter);
     return 0;
@@ -502,7 +518,7 @@ void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uin
 }
 
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
-                      const void* slist_, const uint64_t* soff, uint32_t n_reads, uint32_t* counts,
+                      const void* slist_, const uint64_t* soff, uint32_t n_reads, bool long_lists, uint32_t* counts,
                       uint32_t* work_counter, cudaStream_t st) {
     if (!n_reads) return 0;
     const uint2* slist = static_cast<const uint2*>(slist_);
@@ -519,7 +535,9 @@ int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t strid
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -3;
-    return launch_tiled_t<2, 23>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
+    if (long_lists)
+        return launch_tiled_t<2, 23, true>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
+    return launch_tiled_t<2, 23, false>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
 }
 
 }  // namespace mk
