@@ -370,42 +370,37 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restr
 }
 
 // ---- lists sorted by bucket ------------------------------------------------------------------
-// One CTA per read: the entries are scattered into a dense byte table in shared memory (one byte
-// per bucket, 255 = absent: a fingerprint of 255 never enters a list) and read back in bucket
-// order; a run of sentinels follows.  Needs 2^h bytes of shared memory: -h <= 17.
+// One CTA per read: the entries are scattered into shared memory -- one fingerprint byte per
+// bucket plus a bitmap of the buckets that are present -- and read back in bucket order by
+// walking the bitmap (2^h / 32 words, 7 % of their bits set at config 3); a run of sentinels
+// follows.  Needs 2^h + 2^h / 8 bytes of shared memory: -h <= 17.  Only the bitmap is cleared.
 __global__ void __launch_bounds__(256)
 sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
                   const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t n_buckets,
                   uint2* __restrict__ slist, const uint64_t* __restrict__ soff) {
-    extern __shared__ __align__(16) uint8_t dense[];
+    extern __shared__ __align__(16) uint8_t dense[];                 // fp byte per bucket | bitmap
     __shared__ uint32_t warp_tot[8];
-    const uint32_t padded = (n_buckets + 15) & ~15u;
-    const uint32_t n_words = padded / 4;
-    // a warp owns a contiguous run of table words, walked 32 words (one per lane) at a time
+    const uint32_t padded = (n_buckets + 127) & ~127u;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(dense + padded);
+    const uint32_t n_words = padded / 32;
+    // a warp owns a contiguous run of bitmap words, walked 32 words (one per lane) at a time
     const uint32_t seg = ((n_words + 7) / 8 + 31) & ~31u;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t w0 = warp * seg, w1 = min(n_words, w0 + seg);
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(dense);
-    auto present = [](uint32_t v) {            // bytes of the word that hold a fingerprint
-        uint32_t n = 0;
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) n += ((v >> (8 * k)) & 0xFFu) != 0xFFu;
-        return n;
-    };
     for (uint32_t q = blockIdx.x; q < n_reads; q += gridDim.x) {
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < padded / 16; i += blockDim.x)
-            reinterpret_cast<uint4*>(dense)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) bitmap[i] = 0;
         __syncthreads();
         const uint32_t L = list_len[q];
         const uint32_t* src = list + list_off[q];
         for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
-            const uint32_t e = src[i];
-            dense[e >> 8] = (uint8_t)e;
+            const uint32_t e = src[i], b = e >> 8;
+            dense[b] = (uint8_t)e;
+            atomicOr(bitmap + (b >> 5), 1u << (b & 31));
         }
         __syncthreads();
         uint32_t mine = 0;
-        for (uint32_t w = w0 + lane; w < w1; w += 32) mine += present(words[w]);
+        for (uint32_t w = w0 + lane; w < w1; w += 32) mine += __popc(bitmap[w]);
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
         if (lane == 0) warp_tot[warp] = mine;
@@ -415,8 +410,8 @@ sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict_
         uint2* dst = slist + soff[q];
         for (uint32_t wb = w0; wb < w1; wb += 32) {                  // uniform trip count over the warp
             const uint32_t w = wb + lane;
-            const uint32_t v = w < w1 ? words[w] : 0xFFFFFFFFu;
-            const uint32_t cnt = present(v);
+            uint32_t m = w < w1 ? bitmap[w] : 0u;
+            const uint32_t cnt = __popc(m);
             uint32_t incl = cnt;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -424,10 +419,10 @@ sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict_
                 if (lane >= (uint32_t)o) incl += t;
             }
             uint32_t at = running + incl - cnt;
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t f = (v >> (8 * k)) & 0xFFu;
-                if (f != 0xFFu) dst[at++] = make_uint2((4 * w + k) * ROW_BYTES, f << 5);
+            while (m) {
+                const uint32_t b = 32 * w + (uint32_t)__ffs((int)m) - 1;
+                m &= m - 1;
+                dst[at++] = make_uint2(b * ROW_BYTES, (uint32_t)dense[b] << 5);
             }
             running += __shfl_sync(0xffffffffu, incl, 31);
         }
@@ -483,6 +478,7 @@ int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes,
     // registers per thread at 768 threads
     out->J = 2;
     out->warps = 23;
+    if (const char* e = getenv("MIEKKI_TILED_WARPS")) out->warps = atoi(e) == 21 ? 21 : atoi(e) == 19 ? 19 : 23;   // A/B
     out->tile_reads = (uint32_t)(out->J * out->warps);
     const uint32_t n_rows = 1u << h;
     const uint32_t G = (n_genomes + 31) / 32;
@@ -510,7 +506,8 @@ void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uin
     uint2* slist = static_cast<uint2*>(slist_);
     if (!n_reads) return;
     const uint32_t n_buckets = 1u << h;
-    const size_t smem = (n_buckets + 15) & ~(size_t)15;
+    const size_t padded = (n_buckets + 127) & ~(size_t)127;
+    const size_t smem = padded + padded / 8;                       // fp bytes + bitmap
     if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sort_lists_kernel), smem)) return;
     fill_sentinels_kernel<<<1, 128, 0, st>>>(slist, 128);          // the block reads past the end walk
     const unsigned grid = n_reads < 148u * 8u ? n_reads : 148u * 8u;
@@ -537,6 +534,10 @@ int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t strid
         return -3;
     if (long_lists)
         return launch_tiled_t<2, 23, true>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
+    if (plan.warps == 21)
+        return launch_tiled_t<2, 21, false>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
+    if (plan.warps == 19)
+        return launch_tiled_t<2, 19, false>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
     return launch_tiled_t<2, 23, false>(plan, map, slist, soff, n_reads, n_genomes, n_rows, counts, work_counter, st);
 }
 
