@@ -223,7 +223,14 @@ int mk_sketch(mk_ctx *ctx, const char *seq, uint64_t len, uint8_t *fp, uint64_t 
 int mk_exact(mk_ctx *ctx, const char *const *records, const uint64_t *rec_lens, uint32_t n_records,
              const char *const *reads, const uint64_t *read_lens, uint32_t n_reads,
              uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct);
-/* Same with the records and the reads already in HBM (mk_batch_upload / mk_batch_synth). */
+/* The same for n_genomes genome files in one call (query_file_exact flushes its candidates genome
+ * by genome, Miekki.cpp:745-754): genome g owns the next rec_count[g] entries of records / rec_lens
+ * and the next read_count[g] entries of reads / read_lens; nb_inter / nb_union are per read in that
+ * order, genome_distinct (may be NULL) per genome.  One upload, no host round trip between genomes. */
+int mk_exact_many(mk_ctx *ctx, uint32_t n_genomes, const char *const *records, const uint64_t *rec_lens,
+                  const uint32_t *rec_count, const char *const *reads, const uint64_t *read_lens,
+                  const uint32_t *read_count, uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct);
+/* Same as mk_exact with the records and the reads already in HBM (mk_batch_upload / mk_batch_synth). */
 int mk_exact_batch(mk_ctx *ctx, const mk_batch *records, const mk_batch *reads,
                    uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct);
 

@@ -84,6 +84,7 @@ SIGNATURES = {
     "mk_query_counts": (_i, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "mk_sketch": (_i, [_vp, C.c_char_p, _u64, _vp, _vp, C.POINTER(_u32)]),
     "mk_exact": (_i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, C.POINTER(_u64)]),
+    "mk_exact_many": (_i, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mk_index_export_rows": (_i, [_vp, _u64, _u64, _vp, _u64]),
     "mk_index_import_begin": (_i, [_vp, _u32]),
     "mk_index_import_rows": (_i, [_vp, _u64, _u64, _vp, _u64]),
@@ -402,6 +403,25 @@ class Miekki:
         self._ck(lib().mk_exact(self._ctx, ra, _ptr(rl), len(records), qa, _ptr(ql), len(reads),
                                 _ptr(inter), _ptr(uni), C.byref(nb)))
         return nb.value, inter[: len(reads)], uni[: len(reads)]
+
+    def exact_many(self, genomes):
+        """genomes: [(records, reads)] -> [(|B|, nb_inter[], nb_union[])] in one call (mk_exact_many)."""
+        recs = [r for g in genomes for r in g[0]]
+        reads = [r for g in genomes for r in g[1]]
+        ra, rl = _seq_arrays(recs)
+        qa, ql = _seq_arrays(reads)
+        rc = np.array([len(g[0]) for g in genomes] or [0], np.uint32)
+        qc = np.array([len(g[1]) for g in genomes] or [0], np.uint32)
+        inter = np.zeros(max(1, len(reads)), np.uint64)
+        uni = np.zeros(max(1, len(reads)), np.uint64)
+        nb = np.zeros(max(1, len(genomes)), np.uint64)
+        self._ck(lib().mk_exact_many(self._ctx, len(genomes), ra, _ptr(rl), _ptr(rc), qa, _ptr(ql), _ptr(qc),
+                                     _ptr(inter), _ptr(uni), _ptr(nb)))
+        out, q0 = [], 0
+        for g, (_, rd) in enumerate(genomes):
+            out.append((int(nb[g]), inter[q0:q0 + len(rd)], uni[q0:q0 + len(rd)]))
+            q0 += len(rd)
+        return out
 
     def exact_batch(self, records: Batch, reads: Batch):
         """Same with both sides already in HBM (mk_exact_batch)."""

@@ -622,29 +622,43 @@ struct Candidate {
     double jaccard, intersection;
 };
 
-// Miekki.cpp:823-859 for one genome file whose records (:801-822) are already parsed; returns the
-// text block of its lines
-string ground_truth(mk_ctx* ctx, const string& file, const vector<string>& recs, vector<Candidate>& v) {
-    ostringstream os;
-    if (v.empty()) return "";
-    vector<const char*> rp(recs.size()), qp(v.size());
-    vector<uint64_t> rl(recs.size()), ql(v.size());
-    for (size_t i = 0; i < recs.size(); ++i) { rp[i] = recs[i].data(); rl[i] = recs[i].size(); }
-    for (size_t i = 0; i < v.size(); ++i) { qp[i] = v[i].seq.data(); ql[i] = v[i].seq.size(); }
-    vector<uint64_t> inter(v.size()), uni(v.size());
-    uint64_t nB = 0;
-    if (mk_exact(ctx, rp.data(), rl.data(), (uint32_t)recs.size(), qp.data(), ql.data(), (uint32_t)v.size(),
-                 inter.data(), uni.data(), &nB) != MK_OK)
-        die(ctx, "mk_exact");
-    for (size_t i = 0; i < v.size(); ++i) {
-        const double nb_inter = (double)inter[i], nb_union = (double)uni[i];
-        if (nb_inter > 0) {                                      // :843
-            const double real_jax = nb_inter / nb_union;         // :845-846
-            os << real_jax << "\t" << v[i].jaccard << "\t" << nb_inter << "\t" << v[i].intersection << "\t"
-               << v[i].head << "\t" << file << "\n";             // :853
-        }
+// Miekki.cpp:823-859 for the genome files of one wave that went to one GPU: their records
+// (:801-822) are already parsed; one mk_exact_many call, then the text block of each genome.
+struct GenomeJob {
+    const string* file;
+    const vector<string>* recs;
+    vector<Candidate>* cand;
+    string* text;
+};
+void ground_truth_many(mk_ctx* ctx, vector<GenomeJob>& jobs) {
+    if (jobs.empty()) return;
+    vector<const char*> rp, qp;
+    vector<uint64_t> rl, ql;
+    vector<uint32_t> rc, qc;
+    for (const GenomeJob& j : jobs) {
+        for (const string& r : *j.recs) { rp.push_back(r.data()); rl.push_back(r.size()); }
+        for (const Candidate& c : *j.cand) { qp.push_back(c.seq.data()); ql.push_back(c.seq.size()); }
+        rc.push_back((uint32_t)j.recs->size());
+        qc.push_back((uint32_t)j.cand->size());
     }
-    return os.str();
+    vector<uint64_t> inter(qp.size()), uni(qp.size());
+    if (mk_exact_many(ctx, (uint32_t)jobs.size(), rp.data(), rl.data(), rc.data(), qp.data(), ql.data(), qc.data(),
+                      inter.data(), uni.data(), nullptr) != MK_OK)
+        die(ctx, "mk_exact_many");
+    size_t q = 0;
+    for (const GenomeJob& j : jobs) {
+        ostringstream os;
+        for (const Candidate& c : *j.cand) {
+            const double nb_inter = (double)inter[q], nb_union = (double)uni[q];
+            ++q;
+            if (nb_inter > 0) {                                  // :843
+                const double real_jax = nb_inter / nb_union;     // :845-846
+                os << real_jax << "\t" << c.jaccard << "\t" << nb_inter << "\t" << c.intersection << "\t" << c.head
+                   << "\t" << *j.file << "\n";                   // :853
+            }
+        }
+        *j.text = os.str();
+    }
 }
 
 // Genomes are independent.  Their files are read and cut into records by the host team a wave
@@ -689,14 +703,15 @@ void ground_truth_all(Index& ix, map<uint32_t, vector<Candidate>>& per_genome) {
     for (size_t w0 = 0; w0 < work.size(); w0 += wave) {
         Parsed cur = next.get();
         if (w0 + wave < work.size()) next = async(launch::async, parse, w0 + wave);
+        // the wave's genomes dealt round-robin to the GPUs, one call per GPU
+        vector<vector<GenomeJob>> jobs((size_t)R);
+        for (size_t i = 0, n_ok = 0; i < cur.recs.size(); ++i)
+            if (cur.ok[i] && !work[w0 + i].second->empty())
+                jobs[n_ok++ % (size_t)R].push_back({&ix.file_names[work[w0 + i].first], &cur.recs[i], work[w0 + i].second,
+                                                    &text[w0 + i]});
         LoopError err;
-        #pragma omp parallel for num_threads(R) schedule(dynamic, 1)
-        for (size_t i = 0; i < cur.recs.size(); ++i)
-            if (cur.ok[i])
-                err.run([&] {
-                    text[w0 + i] = ground_truth(ix.shard[(size_t)omp_get_thread_num() % ix.shard.size()],
-                                                ix.file_names[work[w0 + i].first], cur.recs[i], *work[w0 + i].second);
-                });
+        #pragma omp parallel for num_threads(R) schedule(static, 1)
+        for (int r = 0; r < R; ++r) err.run([&] { ground_truth_many(ix.shard[(size_t)r], jobs[(size_t)r]); });
         err.rethrow();
     }
     for (const string& s : text) *ix.out << s;

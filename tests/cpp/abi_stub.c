@@ -300,3 +300,19 @@ int mk_exact(mk_ctx *c, const char *const *records, const uint64_t *rec_lens, ui
     mko_free(setB);
     return MK_OK;
 }
+
+int mk_exact_many(mk_ctx *c, uint32_t n_genomes, const char *const *records, const uint64_t *rec_lens,
+                  const uint32_t *rec_count, const char *const *reads, const uint64_t *read_lens,
+                  const uint32_t *read_count, uint64_t *nb_inter, uint64_t *nb_union, uint64_t *genome_distinct) {
+    uint64_t r0 = 0, q0 = 0;
+    for (uint32_t g = 0; g < n_genomes; ++g) {
+        uint64_t nB = 0;
+        int rc = mk_exact(c, records + r0, rec_lens + r0, rec_count[g], reads + q0, read_lens + q0, read_count[g],
+                          nb_inter + q0, nb_union + q0, &nB);
+        if (rc != MK_OK) return rc;
+        if (genome_distinct) genome_distinct[g] = nB;
+        r0 += rec_count[g];
+        q0 += read_count[g];
+    }
+    return MK_OK;
+}

@@ -328,6 +328,14 @@ def test_exact_edge_cases(mk, monkeypatch, sort_variant):
     assert nB == onB and [(int(a), int(u)) for a, u in zip(inter, uni)] == ores
     gb.free()
     rb.free()
+    # several genome files in one call (mk_exact_many): per genome the same numbers
+    g2 = rand_seq(rng, 7000, special=True)
+    many = [(recs, reads), ([g2[:3000], g2[3000:]], [g2[10:500], g[100:400], b"ACGT"]), ([], [g[:100]]),
+            ([g2], [])]
+    got = ix.exact_many(many)
+    for (rr, qq), (nB, inter, uni) in zip(many, got):
+        oB, ores2 = orc.exact(rr, qq, 31)
+        assert nB == oB and [(int(a), int(u)) for a, u in zip(inter, uni)] == ores2
     ix.close()
 
 
