@@ -2030,28 +2030,42 @@ static int exact_device(mk_ctx* c, const mk_batch* gb, const mk_batch* rb, uint6
     return r;
 }
 
-// Several genomes in one call (mk_exact_many): records and reads of all of them are resident, one
-// hash table (sized for the largest genome) is reused, nothing waits for the host between genomes
-// and the counters come back in one copy.
-static int exact_many_device(mk_ctx* c, const mk_batch* gb, const uint32_t* rec_count, const mk_batch* rb,
-                             const uint32_t* read_count, uint32_t n_genomes, uint64_t* nb_inter, uint64_t* nb_union,
-                             uint64_t* genome_distinct) {
+// Several genomes in one call (mk_exact_many): one hash table (sized for the largest genome) is
+// reused, nothing waits for the host between genomes, the counters come back in one copy -- and the
+// genomes travel in sub-batches of about 32 MB on the copy stream, so that the upload of one
+// sub-batch runs beside the kernels of the previous one.
+int mk_exact_many(mk_ctx* c, uint32_t n_genomes, const char* const* records, const uint64_t* rec_lens,
+                  const uint32_t* rec_count, const char* const* reads, const uint64_t* read_lens,
+                  const uint32_t* read_count, uint64_t* nb_inter, uint64_t* nb_union, uint64_t* genome_distinct) {
+    if (!c || (n_genomes && (!rec_count || !read_count))) return fail(c, MK_ERR_ARG, "mk_exact_many: NULL argument");
+    uint64_t n_records = 0, n_reads64 = 0;
+    for (uint32_t g = 0; g < n_genomes; ++g) {
+        n_records += rec_count[g];
+        n_reads64 += read_count[g];
+    }
+    if (n_records > 0xFFFFFFFFull || n_reads64 > 0xFFFFFFFFull) return fail(c, MK_ERR_ARG, "mk_exact_many: too many sequences");
+    if ((n_records && (!records || !rec_lens)) || (n_reads64 && (!reads || !read_lens || !nb_inter || !nb_union)))
+        return fail(c, MK_ERR_ARG, "mk_exact_many: NULL argument");
+    Guard guard(c);
+    const uint32_t n_reads = (uint32_t)n_reads64, k = c->k;
     unsigned long long *tableB = nullptr, *rtable = nullptr, *d_cnt = nullptr;
     uint64_t* d_toff = nullptr;
-    const uint32_t n_reads = rb->n, k = c->k;
+    mk_batch* rb = nullptr;
+    std::vector<mk_batch*> subs;
     auto body = [&]() -> int {
+        TRY(upload_range(c, reads, read_lens, n_reads, &rb));
         std::vector<uint64_t> wins(n_genomes, 0);
         uint64_t max_wins = 0;
         for (uint32_t g = 0, r0 = 0; g < n_genomes; r0 += rec_count[g], ++g) {
             for (uint32_t i = 0; i < rec_count[g]; ++i)
-                if (gb->h_len[r0 + i] >= k) wins[g] += gb->h_len[r0 + i] - k + 1;
+                if (rec_lens[r0 + i] >= k) wins[g] += rec_lens[r0 + i] - k + 1;
             max_wins = std::max(max_wins, wins[g]);
         }
         std::vector<uint64_t> toff((size_t)n_reads + 1);
         uint64_t tt = 0;
         for (uint32_t i = 0; i < n_reads; ++i) {
             toff[i] = tt;
-            tt += rb->h_len[i] >= k ? std::max<uint64_t>(4, (rb->h_len[i] - k + 1) * 2) : 1;
+            tt += read_lens[i] >= k ? std::max<uint64_t>(4, (read_lens[i] - k + 1) * 2) : 1;
         }
         toff[n_reads] = tt;
         const size_t n_cnt = (size_t)n_genomes + 2 * (size_t)n_reads;      // |B| per genome | inter | |A| per read
@@ -2067,32 +2081,49 @@ static int exact_many_device(mk_ctx* c, const mk_batch* gb, const uint32_t* rec_
         unsigned long long* d_inter = d_cnt + n_genomes;
         unsigned long long* d_dist = d_inter + n_reads;
         const uint32_t YMAX = 32768;
-        for (uint32_t g = 0, r0 = 0, q0 = 0; g < n_genomes; r0 += rec_count[g], q0 += read_count[g], ++g) {
-            const uint64_t slotsB = std::max<uint64_t>(16, wins[g] * 2);
-            launch_fill_u64(tableB, slotsB, ~0ull, c->stream);
-            c->stats.kernel_launches += 1;
-            for (uint32_t f = 0; f < rec_count[g]; f += YMAX) {
-                const uint32_t m = std::min(YMAX, rec_count[g] - f);
-                BatchView v = view_of(gb, r0 + f, m);
-                launch_exact_insert(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, tableB, slotsB, d_cnt + g, c->stream);
-                c->stats.kernel_launches += 1;
+        uint32_t g0 = 0, r0 = 0, q0 = 0;
+        while (g0 < n_genomes) {
+            // the next sub-batch of genomes: about 32 MB of records
+            uint32_t g1 = g0, nrec = 0;
+            uint64_t bytes = 0;
+            while (g1 < n_genomes && (g1 == g0 || bytes < (32ull << 20))) {
+                for (uint32_t i = 0; i < rec_count[g1]; ++i) bytes += rec_lens[r0 + nrec + i];
+                nrec += rec_count[g1];
+                ++g1;
             }
-            for (uint32_t f = 0; f < read_count[g]; f += YMAX) {
-                const uint32_t m = std::min(YMAX, read_count[g] - f);
-                BatchView v = view_of(rb, q0 + f, m);
-                launch_exact_reads(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, rtable, d_toff + q0 + f, tableB, slotsB,
-                                   d_inter + q0 + f, d_dist + q0 + f, c->stream);
+            mk_batch* gb = nullptr;
+            // returns when the copy has landed; the kernels of the previous sub-batch keep running
+            TRY(upload_range(c, records + r0, rec_lens + r0, nrec, &gb, c->copy_stream));
+            subs.push_back(gb);
+            for (uint32_t g = g0, rr = 0; g < g1; rr += rec_count[g], q0 += read_count[g], ++g) {
+                const uint64_t slotsB = std::max<uint64_t>(16, wins[g] * 2);
+                launch_fill_u64(tableB, slotsB, ~0ull, c->stream);
                 c->stats.kernel_launches += 1;
+                for (uint32_t f = 0; f < rec_count[g]; f += YMAX) {
+                    const uint32_t m = std::min(YMAX, rec_count[g] - f);
+                    BatchView v = view_of(gb, rr + f, m);
+                    launch_exact_insert(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, tableB, slotsB, d_cnt + g, c->stream);
+                    c->stats.kernel_launches += 1;
+                }
+                for (uint32_t f = 0; f < read_count[g]; f += YMAX) {
+                    const uint32_t m = std::min(YMAX, read_count[g] - f);
+                    BatchView v = view_of(rb, q0 + f, m);
+                    launch_exact_reads(v.chars, v.d_coff, v.d_len, m, v.max_len, (int)k, rtable, d_toff + q0 + f, tableB,
+                                       slotsB, d_inter + q0 + f, d_dist + q0 + f, c->stream);
+                    c->stats.kernel_launches += 1;
+                }
             }
+            r0 += nrec;
+            g0 = g1;
         }
         CU(cudaGetLastError());
         std::vector<unsigned long long> cnt(std::max<size_t>(1, n_cnt));
         CU(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         c->stats.d2h_bytes += cnt.size() * 8;
-        for (uint32_t g = 0, q0 = 0; g < n_genomes; q0 += read_count[g], ++g) {
+        for (uint32_t g = 0, qq = 0; g < n_genomes; qq += read_count[g], ++g) {
             if (genome_distinct) genome_distinct[g] = cnt[g];
-            for (uint32_t i = q0; i < q0 + read_count[g]; ++i) {
+            for (uint32_t i = qq; i < qq + read_count[g]; ++i) {
                 nb_inter[i] = cnt[n_genomes + i];
                 nb_union[i] = cnt[g] + (cnt[n_genomes + n_reads + i] - cnt[n_genomes + i]);   // |B| + |A \ B|
             }
@@ -2106,28 +2137,7 @@ static int exact_many_device(mk_ctx* c, const mk_batch* gb, const uint32_t* rec_
     if (rtable) cudaFreeAsync(rtable, c->stream);
     if (d_cnt) cudaFreeAsync(d_cnt, c->stream);
     if (d_toff) cudaFreeAsync(d_toff, c->stream);
-    return r;
-}
-
-int mk_exact_many(mk_ctx* c, uint32_t n_genomes, const char* const* records, const uint64_t* rec_lens,
-                  const uint32_t* rec_count, const char* const* reads, const uint64_t* read_lens,
-                  const uint32_t* read_count, uint64_t* nb_inter, uint64_t* nb_union, uint64_t* genome_distinct) {
-    if (!c || (n_genomes && (!rec_count || !read_count))) return fail(c, MK_ERR_ARG, "mk_exact_many: NULL argument");
-    uint64_t n_records = 0, n_reads = 0;
-    for (uint32_t g = 0; g < n_genomes; ++g) {
-        n_records += rec_count[g];
-        n_reads += read_count[g];
-    }
-    if (n_records > 0xFFFFFFFFull || n_reads > 0xFFFFFFFFull) return fail(c, MK_ERR_ARG, "mk_exact_many: too many sequences");
-    if ((n_records && (!records || !rec_lens)) || (n_reads && (!reads || !read_lens || !nb_inter || !nb_union)))
-        return fail(c, MK_ERR_ARG, "mk_exact_many: NULL argument");
-    Guard g(c);
-    mk_batch *gb = nullptr, *rb = nullptr;
-    int r = upload_range(c, records, rec_lens, (uint32_t)n_records, &gb);
-    if (r == MK_OK) r = upload_range(c, reads, read_lens, (uint32_t)n_reads, &rb);
-    if (r == MK_OK) r = exact_many_device(c, gb, rec_count, rb, read_count, n_genomes, nb_inter, nb_union, genome_distinct);
-    cudaStreamSynchronize(c->stream);
-    batch_release(gb);
+    for (mk_batch* gb : subs) batch_release(gb);
     batch_release(rb);
     return r;
 }
