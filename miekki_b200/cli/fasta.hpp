@@ -97,6 +97,34 @@ public:
         }
         eof_ = true;
     }
+    // The loop of Miekki.cpp:801-822 in one pass over the reader's buffer: lines are appended to the
+    // current record; at a line that starts with '>' the record is closed if it holds at least k
+    // characters (a shorter one is kept and runs into the next record, quirk G16).
+    void split_records(std::vector<std::string>& recs, uint32_t k, size_t reserve_bytes) {
+        std::string ref;
+        ref.reserve(reserve_bytes);
+        bool at_line_start = true, header = false;
+        for (;;) {
+            if (pos_ == len_ && !refill()) break;
+            const unsigned char* base = cur() + pos_;
+            const size_t avail = len_ - pos_;
+            if (at_line_start) {
+                header = base[0] == '>';
+                at_line_start = false;
+                if (header && ref.size() >= k) {
+                    recs.push_back(std::move(ref));
+                    ref.clear();
+                }
+            }
+            const void* nl = memchr(base, '\n', avail);
+            const size_t seg = nl ? (size_t)((const unsigned char*)nl - base) : avail;
+            if (!header) ref.append((const char*)base, seg);
+            pos_ += seg + (nl ? 1 : 0);
+            if (nl) at_line_start = true;
+        }
+        eof_ = true;
+        if (ref.size() >= k) recs.push_back(std::move(ref));
+    }
     // bytes of the file on disk (a lower bound of the text for compressed files)
     size_t file_bytes() const {
         const long at = ftell(f_);
@@ -400,19 +428,8 @@ inline std::string read_genome_concat(const std::string& path) {
 inline std::vector<std::string> read_genome_records(const std::string& path, uint32_t k) {
     LineReader in(path);
     std::vector<std::string> recs;
-    std::string ref, line;
-    while (!in.eof()) {
-        in.getline(line);
-        if (!line.empty() && line[0] == '>') {
-            if (ref.size() >= k) {
-                recs.push_back(std::move(ref));
-                ref.clear();
-            }
-        } else {
-            ref += line;
-        }
-    }
-    if (ref.size() >= k) recs.push_back(std::move(ref));
+    const size_t bytes = in.file_bytes();
+    in.split_records(recs, k, in.is_compressed() ? bytes * 4 : bytes);
     return recs;
 }
 
