@@ -35,6 +35,18 @@ class OracleEngine:
     def scan(self, reads):
         self.counts = [self.o.counts(s)[0] for s in reads]
 
+    # the pipelined pair of binding.Miekki: two count tiles, alternating
+    def scan_async(self, reads):
+        self.slot = getattr(self, "slot", 0) ^ 1
+        if not hasattr(self, "tiles"):
+            self.tiles = {}
+        self.tiles[self.slot] = [self.o.counts(s)[0] for s in reads]
+        return self.slot
+
+    def topk_slot_ptr(self, slot, heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize):
+        self.counts = self.tiles[slot]
+        self.topk_ptr(heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize)
+
     def topk_ptr(self, heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize):
         import ctypes as C
         n = len(self.counts)
@@ -76,6 +88,57 @@ def _worker(rank, world, port, case, k, h, b, thresholds, q):
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _pipelined_worker(rank, world, port, case, k, h, b, n_batches, q):
+    """sharded.pipelined_query over n_batches distinct read batches (scan of batch i + 1 enqueued
+    before batch i's heap is chained; consecutive batches in alternating buffers)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from miekki_b200 import sharded
+        from oracle import oracle as orc
+        d = os.path.join(H.GOLDEN, case)
+        genomes = [H.genome_like_reference(os.path.join(d, f)) for f in H.load_list(d)]
+        first, count = sharded.shard_range(len(genomes), rank, world)
+        eng = OracleEngine(genomes[first:first + count], first, k, h, b)
+        eng.set_bloom(sharded.merge_bloom(eng.bloom_tensor()))
+        reads = H.reads_like_reference(os.path.join(d, "reads.fa"), k)
+        per = len(reads) // n_batches
+        parts = [reads[i * per:(i + 1) * per] for i in range(n_batches)]
+        heap = torch.zeros((per, 10 * 24), dtype=torch.uint8)
+        lens = torch.zeros(per, dtype=torch.int32)
+        lines = {}
+
+        def on_result(i):
+            hn = heap.numpy()
+            lines[i] = "".join(orc.format_hit_line(hd, hn[j].view(orc.HIT_DTYPE)[: int(lens[j])])
+                               for j, (hd, _) in enumerate(parts[i]))
+        sharded.pipelined_query(eng, ([s for _, s in p] for p in parts), heap, lens, 10, 10, 0.0, on_result=on_result)
+        if rank == world - 1:
+            q.put("".join(lines[i] for i in range(n_batches)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_three_rank_pipelined_batches_reproduce_reference_lines():
+    """-s 0 (every candidate competes: heap order decides), 3 ranks, 4 batches of 14 reads."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipelined_worker, args=(r, 3, port, "caseA", 31, 12, 33, 4, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = open(os.path.join(H.GOLDEN, "caseA", "hits_s0.txt")).read().split("\n")
+    n = (len(want) - 1) // 4 * 4
+    assert out.split("\n")[:n] == want[:n] and n >= 52
 
 
 def _free_port():
