@@ -410,11 +410,11 @@ def main():
         print(json.dumps({"impl": a.impl, "error": "no CUDA device: this bench needs a B200"}))
         return 1
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
     import miekki_b200
     from miekki_b200 import sharded, synth
+    if world > 1:
+        sharded.nccl_env_defaults()              # one P2P channel: a waiting receive holds one SM, not many
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nproc = os.cpu_count() or 1
     K = K_RESULTS
 

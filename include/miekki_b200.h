@@ -203,6 +203,14 @@ int mk_scan_async(mk_ctx *ctx, const mk_batch *reads, int *slot);
 int mk_topk_slot(mk_ctx *ctx, int slot, uint32_t nresults, uint32_t min_score,
                  double min_intersection, mk_hit *heap_io, uint32_t *len_io, int chain_in,
                  int finalize);
+/* mk_topk_slot for reads [first_read, first_read + n_reads) of the slot's batch only (clipped to
+ * the batch); heap_io / len_io address read first_read.  A chain over shards passes a batch on in
+ * tiles of reads this way: shard r steps tile t while shard r + 1 steps tile t - 1, and the last
+ * batch of a run drains in one heap step plus one tile per further shard instead of one whole
+ * heap step per shard. */
+int mk_topk_slot_range(mk_ctx *ctx, int slot, uint32_t first_read, uint32_t n_reads,
+                       uint32_t nresults, uint32_t min_score, double min_intersection,
+                       mk_hit *heap_io, uint32_t *len_io, int chain_in, int finalize);
 
 /* Test hook: raw shared-fingerprint counts, the matrix Miekki::query_sequences returns
  * (Miekki.cpp:352): counts[i * N + g].  surviving (may be NULL) receives A(q), the number of

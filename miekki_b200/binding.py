@@ -78,6 +78,7 @@ SIGNATURES = {
     "mk_topk": (_i, [_vp, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_scan_async": (_i, [_vp, _vp, C.POINTER(_i)]),
     "mk_topk_slot": (_i, [_vp, _i, _u32, _u32, _d, _vp, _vp, _i, _i]),
+    "mk_topk_slot_range": (_i, [_vp, _i, _u32, _u32, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_query": (_i, [_vp, _vp, _vp, _u32, _u32, _u32, _d, _vp, _vp]),
     "mk_query_batch": (_i, [_vp, _vp, _u32, _u32, _d, _vp, _vp]),
     "mk_query_chain": (_i, [_vp, _vp, _u32, _u32, _d, _vp, _vp, _i]),
@@ -365,12 +366,20 @@ class Miekki:
         return slot.value
 
     def topk_slot_ptr(self, slot: int, heap_ptr: int, len_ptr: int, nresults=10, min_score=10,
-                      min_intersection=None, chain_in=False, finalize=True):
+                      min_intersection=None, chain_in=False, finalize=True, first=0, count=None):
+        """Heap step on the counts of `slot`; with first / count, on that range of the batch's
+        reads only (the pointers then address read `first`)."""
         if min_intersection is None:
             min_intersection = 0.5 * self.threshold
-        self._ck(lib().mk_topk_slot(self._ctx, slot, nresults, min_score, float(min_intersection),
-                                    C.c_void_p(heap_ptr), C.c_void_p(len_ptr), 1 if chain_in else 0,
-                                    1 if finalize else 0))
+        if first == 0 and count is None:
+            self._ck(lib().mk_topk_slot(self._ctx, slot, nresults, min_score, float(min_intersection),
+                                        C.c_void_p(heap_ptr), C.c_void_p(len_ptr), 1 if chain_in else 0,
+                                        1 if finalize else 0))
+        else:
+            self._ck(lib().mk_topk_slot_range(self._ctx, slot, first, 0xFFFFFFFF if count is None else count,
+                                              nresults, min_score, float(min_intersection),
+                                              C.c_void_p(heap_ptr), C.c_void_p(len_ptr),
+                                              1 if chain_in else 0, 1 if finalize else 0))
 
     def topk(self, heap: np.ndarray, lens: np.ndarray, **kw):
         assert heap.dtype == HIT_DTYPE and heap.flags.c_contiguous and lens.dtype == np.uint32

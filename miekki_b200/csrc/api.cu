@@ -1200,25 +1200,30 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
     return MK_OK;
 }
 
-// bounded-heap step on the counts of `slot`, on the aux stream; waits for that stream only
-int topk_slot(mk_ctx* c, int slot, uint32_t K, uint32_t min_score, double min_int, mk_hit* heap_io,
-              uint32_t* len_io, bool chain_in, int finalize) {
+// bounded-heap step on the counts of `slot`, on the aux stream; waits for that stream only.
+// [first, first + count) is the range of the batch's reads to step (heap_io / len_io address
+// read `first`): a chain over shards passes the batch on in tiles, so that the shards work on
+// different tiles at the same time.
+int topk_slot(mk_ctx* c, int slot, uint32_t first, uint32_t count, uint32_t K, uint32_t min_score, double min_int,
+              mk_hit* heap_io, uint32_t* len_io, bool chain_in, int finalize) {
     if (K < 1 || K > 64) return fail(c, MK_ERR_ARG, "nresults must be in [1, 64]");
     if (slot < 0 || slot > 1) return fail(c, MK_ERR_ARG, "mk_topk: bad slot");
-    const uint32_t n = c->slot_reads[slot];
+    const uint32_t total = c->slot_reads[slot];
+    if (first >= total) return MK_OK;            // the range is clipped to the batch
+    const uint32_t n = std::min(count, total - first);
     if (n == 0) return MK_OK;
     if (!heap_io || !len_io) return fail(c, MK_ERR_ARG, "mk_topk needs heap_io and len_io");
     cudaStream_t st = c->aux_stream;
     // the heap scratch is per slot as well: two batches may be in flight
     DevBuf& hb = slot ? c->heap2 : c->heap;
     DevBuf& lb = slot ? c->heap_len2 : c->heap_len;
-    if ((size_t)n * K * sizeof(HitDev) > hb.cap || (size_t)n * 4 > lb.cap) {
+    if ((size_t)total * K * sizeof(HitDev) > hb.cap || (size_t)total * 4 > lb.cap) {
         CU(cudaStreamSynchronize(st));
-        TRY(reserve(c, hb, (size_t)n * K * sizeof(HitDev)));
-        TRY(reserve(c, lb, (size_t)n * 4));
+        TRY(reserve(c, hb, (size_t)total * K * sizeof(HitDev)));
+        TRY(reserve(c, lb, (size_t)total * 4));
     }
-    auto* d_heap = static_cast<HitDev*>(hb.p);
-    auto* d_hlen = static_cast<uint32_t*>(lb.p);
+    auto* d_heap = static_cast<HitDev*>(hb.p) + (size_t)first * K;
+    auto* d_hlen = static_cast<uint32_t*>(lb.p) + first;
     CU(cudaStreamWaitEvent(st, c->slot_ev[slot], 0));
     if (chain_in) {
         CU(cudaMemcpyAsync(d_heap, heap_io, (size_t)n * K * sizeof(HitDev), cudaMemcpyDefault, st));
@@ -1228,9 +1233,10 @@ int topk_slot(mk_ctx* c, int slot, uint32_t K, uint32_t min_score, double min_in
     }
     if (c->n > 0 || finalize) {      // an empty shard still passes the heap on / sorts it
         PhaseTimer t(c, PH_TOPK, st);
-        launch_topk(static_cast<uint32_t*>((slot ? c->counts2 : c->counts).p), n, c->n, c->first_id,
-                    c->d_sketch_size, c->d_genome_size, c->d_ratio, K, min_score, min_int, d_heap, d_hlen,
-                    finalize, st);
+        const uint64_t n_pad = (c->n + 31) / 32 * 32;
+        launch_topk(static_cast<uint32_t*>((slot ? c->counts2 : c->counts).p) + (size_t)first * n_pad, n, c->n,
+                    c->first_id, c->d_sketch_size, c->d_genome_size, c->d_ratio, K, min_score, min_int, d_heap,
+                    d_hlen, finalize, st);
         c->stats.kernel_launches += 1;
         CU(cudaGetLastError());
     }
@@ -1863,14 +1869,23 @@ int mk_topk(mk_ctx* c, uint32_t nresults, uint32_t min_score, double min_interse
             uint32_t* len_io, int chain_in, int finalize) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
-    return topk_slot(c, c->last_slot, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
+    return topk_slot(c, c->last_slot, 0, UINT32_MAX, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
 }
 
 int mk_topk_slot(mk_ctx* c, int slot, uint32_t nresults, uint32_t min_score, double min_intersection,
                  mk_hit* heap_io, uint32_t* len_io, int chain_in, int finalize) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
-    return topk_slot(c, slot, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
+    return topk_slot(c, slot, 0, UINT32_MAX, nresults, min_score, min_intersection, heap_io, len_io, chain_in != 0, finalize);
+}
+
+int mk_topk_slot_range(mk_ctx* c, int slot, uint32_t first_read, uint32_t n_reads, uint32_t nresults,
+                       uint32_t min_score, double min_intersection, mk_hit* heap_io, uint32_t* len_io, int chain_in,
+                       int finalize) {
+    if (!c) return MK_ERR_ARG;
+    Guard g(c);
+    return topk_slot(c, slot, first_read, n_reads, nresults, min_score, min_intersection, heap_io, len_io,
+                     chain_in != 0, finalize);
 }
 
 int mk_query_counts(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint32_t n, uint32_t* counts,

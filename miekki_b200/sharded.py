@@ -15,10 +15,21 @@ The functions are backend-agnostic: tensors live on the GPU with NCCL, or on the
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
 HIT_BYTES = 24          # sizeof(mk_hit)
+
+
+def nccl_env_defaults() -> None:
+    """Call before `init_process_group("nccl")`.  A receive posted for the next heap is a kernel
+    that spins on its SMs until the previous rank sends, which may be a whole scan later; with
+    NCCL's default of many P2P channels it takes that many SMs away from the scan meanwhile
+    (config 3 on 2 GPUs: 665 ms per step instead of 604).  One channel moves a 24 MB heap in
+    about a millisecond, which is all the chain needs."""
+    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "1")
 
 
 def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
@@ -45,8 +56,21 @@ def merge_bloom(local: torch.Tensor, group=None) -> torch.Tensor:
     return fold_bloom(tables)
 
 
+def _exchange(op, tensors, peer, group) -> None:
+    """One batched P2P call for the tensors of a tile (a single NCCL group launch; unbatched
+    sends on the default group are serialised with every other collective)."""
+    for w in dist.batch_isend_irecv([dist.P2POp(op, t, peer, group) for t in tensors]):
+        w.wait()                  # NCCL: the current stream waits; gloo: the host does
+
+
+def drain_tiles(n_reads: int, world: int) -> int:
+    """How many read tiles the last batch of a run is chained in: enough that a tile's heap step
+    is a small fraction of the batch's, never tiles of fewer than 1,024 reads."""
+    return max(1, min(2 * world, n_reads // 1024))
+
+
 def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, min_score: int,
-                 min_intersection: float, group=None, slot: int | None = None) -> None:
+                 min_intersection: float, group=None, slot: int | None = None, tiles: int = 1) -> None:
     """heap: uint8 [n_reads, nresults * 24], lens: int32 [n_reads], on the engine's device.
     `engine.topk_ptr(heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in,
     finalize)` applies this rank's stored counts to the heap state in place
@@ -54,29 +78,42 @@ def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, 
     caller has already enqueued the next batch's scan with `scan_async`).
     After the call the LAST rank holds the final hit lists.
 
+    tiles > 1 (needs `slot`): the batch travels in that many tiles of reads, each stepped with
+    `topk_slot_ptr(..., first=, count=)` and sent on at once, so rank r steps tile t while rank
+    r + 1 steps tile t - 1.  Reads are independent in the heap step, so the result is the same;
+    the chain then takes one batch-sized heap step plus (world - 1) tile-sized ones instead of
+    `world` batch-sized ones.  Worth it when the GPUs have nothing else to do (the last batch of
+    a run); beside a running scan every tile would wait for SMs of its own.
+
     On GPUs the receive is followed by a wait on the current stream only, so when this runs
     under `torch.cuda.stream(side_stream)` the main stream keeps scanning."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if rank > 0:
-        dist.recv(heap, src=rank - 1, group=group)
-        dist.recv(lens, src=rank - 1, group=group)
-        if heap.is_cuda:
-            torch.cuda.current_stream().synchronize()      # the engine reads the buffers next
+    n = heap.shape[0]
+    tiles = max(1, min(tiles, n)) if slot is not None and world > 1 else 1
     kw = dict(chain_in=rank > 0, finalize=rank == world - 1)
-    if slot is None:
-        engine.topk_ptr(heap.data_ptr(), lens.data_ptr(), nresults, min_score, min_intersection, **kw)
-    else:
-        engine.topk_slot_ptr(slot, heap.data_ptr(), lens.data_ptr(), nresults, min_score,
-                             min_intersection, **kw)
-    if rank < world - 1:
-        dist.send(heap, dst=rank + 1, group=group)
-        dist.send(lens, dst=rank + 1, group=group)
+    for t in range(tiles):
+        a, b = t * n // tiles, (t + 1) * n // tiles
+        h, l = heap[a:b], lens[a:b]
+        if rank > 0:
+            _exchange(dist.irecv, (h, l), rank - 1, group)
+            if heap.is_cuda:
+                torch.cuda.current_stream().synchronize()      # the engine reads the buffers next
+        if slot is None:
+            engine.topk_ptr(heap.data_ptr(), lens.data_ptr(), nresults, min_score, min_intersection, **kw)
+        elif tiles == 1:
+            engine.topk_slot_ptr(slot, heap.data_ptr(), lens.data_ptr(), nresults, min_score,
+                                 min_intersection, **kw)
+        else:
+            engine.topk_slot_ptr(slot, h.data_ptr(), l.data_ptr(), nresults, min_score, min_intersection,
+                                 first=a, count=b - a, **kw)
+        if rank < world - 1:
+            _exchange(dist.isend, (h, l), rank + 1, group)
 
 
 def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nresults: int,
                     min_score: int, min_intersection: float, on_result=None, after_chain=None,
-                    group=None) -> None:
+                    group=None, last_tiles: int | None = None) -> None:
     """Software pipeline over read batches: the scan of batch i+1 is enqueued before batch i's
     heap is chained through the ranks, so the cheap, latency-bound chain hides behind the scan.
     `batches` yields engine batches; `on_result(i)` is called on the last rank when batch i's hit
@@ -86,20 +123,23 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
     Consecutive batches travel in alternating buffers: an NCCL send only completes when the next
     rank has posted its receive, which may be a whole scan later, so the buffer a batch was sent
     from must not be written again (by the next batch's top-k on the first rank) before that.
-    A buffer is reused two batches later, after the event recorded behind its sends."""
+    A buffer is reused two batches later, after the event recorded behind its sends.
+
+    The last batch has no scan to hide behind: it is chained in `last_tiles` tiles of reads
+    (default `drain_tiles`), see chained_topk."""
     side = torch.cuda.Stream() if heap.is_cuda else None
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     bufs = [(heap, lens), (torch.empty_like(heap), torch.empty_like(lens))]
     sent = [None, None]
 
-    def finish(i, slot):
+    def finish(i, slot, tiles=1):
         h, l = bufs[i & 1]
 
         def body():
             if sent[i & 1] is not None:
                 sent[i & 1].synchronize()           # the sends of batch i - 2 have left this buffer
-            chained_topk(engine, h, l, nresults, min_score, min_intersection, group, slot)
+            chained_topk(engine, h, l, nresults, min_score, min_intersection, group, slot, tiles)
             if side is not None and rank < world - 1:
                 sent[i & 1] = torch.cuda.Event()
                 sent[i & 1].record(torch.cuda.current_stream())
@@ -125,7 +165,7 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
             finish(*pending)
         pending = (i, slot)
     if pending is not None:
-        finish(*pending)
+        finish(*pending, tiles=drain_tiles(heap.shape[0], world) if last_tiles is None else last_tiles)
         if on_result is None and rank == world - 1 and (pending[0] & 1):
             # the last batch went through the second buffer: its hit lists belong in the caller's
             if side is not None:

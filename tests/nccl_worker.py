@@ -22,6 +22,7 @@ from oracle import oracle as orc  # noqa: E402
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
+    sharded.nccl_env_defaults()
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     k, h, G, GL = 31, 12, 75, 60_000
     rng = np.random.default_rng(42)
@@ -58,7 +59,8 @@ def main():
             torch.cuda.current_stream().synchronize()
             got[i] = (heap.cpu().numpy().view(miekki_b200.HIT_DTYPE).reshape(per, K).copy(),
                       lens.cpu().numpy().view(np.uint32).copy())
-        sharded.pipelined_query(ix, iter(batches), heap, lens, K, 10, 0.5 * thr, on_result=on_result)
+        # the last batch is chained in 3 tiles of reads (mk_topk_slot_range), the others whole
+        sharded.pipelined_query(ix, iter(batches), heap, lens, K, 10, 0.5 * thr, on_result=on_result, last_tiles=3)
         if rank == world - 1:
             assert sorted(got) == list(range(nb))
             for b in range(nb):

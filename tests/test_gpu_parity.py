@@ -248,6 +248,29 @@ def test_case_a_read_slices_bound_list_memory(mk, case_a, monkeypatch):
     monkeypatch.delenv("MIEKKI_LIST_BUDGET_ENTRIES")
 
 
+def test_case_a_topk_slot_in_read_ranges(mk, case_a):
+    """mk_topk_slot_range: the heap step over a batch in ragged ranges of reads (in any order,
+    pointers addressing the range's first read) gives the lists of the whole-batch step; a range
+    past the batch is clipped to nothing."""
+    d, ix, _ = case_a
+    reads = [s for _, s in H.reads_like_reference(os.path.join(d, "reads.fa"), 31)]
+    n = len(reads)
+    b = ix.upload(reads)
+    for s in (200, 0):
+        want = ix.query(reads, 10, 10, 0.5 * s)
+        heap = np.zeros((n, 10), mk.HIT_DTYPE)
+        lens = np.zeros(n, np.uint32)
+        slot = ix.scan_async(b)
+        for first, count in ((17, 9), (0, 17), (26, None), (n, 5), (n + 3, 1)):
+            off = min(first, n - 1)
+            ix.topk_slot_ptr(slot, heap[off:].ctypes.data, lens[off:].ctypes.data, 10, 10, 0.5 * s,
+                             first=first, count=count)
+        ix.sync()
+        for i in range(n):
+            assert heap[i, :lens[i]].tobytes() == want[i].tobytes(), (s, i)
+    b.free()
+
+
 def test_case_a_pipelined_scan_and_topk_slots(mk, case_a):
     """mk_scan_async / mk_topk_slot: two read batches in flight (scan of the second enqueued
     before the first one's heap step) give the same lists as the plain query."""

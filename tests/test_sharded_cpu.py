@@ -43,8 +43,10 @@ class OracleEngine:
         self.tiles[self.slot] = [self.o.counts(s)[0] for s in reads]
         return self.slot
 
-    def topk_slot_ptr(self, slot, heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize):
-        self.counts = self.tiles[slot]
+    def topk_slot_ptr(self, slot, heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize,
+                      first=0, count=None):
+        # a range of the batch's reads; the pointers address read `first` (mk_topk_slot_range)
+        self.counts = self.tiles[slot][first:None if count is None else first + count]
         self.topk_ptr(heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize)
 
     def topk_ptr(self, heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in, finalize):
@@ -115,7 +117,9 @@ def _pipelined_worker(rank, world, port, case, k, h, b, n_batches, q):
             hn = heap.numpy()
             lines[i] = "".join(orc.format_hit_line(hd, hn[j].view(orc.HIT_DTYPE)[: int(lens[j])])
                                for j, (hd, _) in enumerate(parts[i]))
-        sharded.pipelined_query(eng, ([s for _, s in p] for p in parts), heap, lens, 10, 10, 0.0, on_result=on_result)
+        # the last batch travels in 3 tiles of reads (5 + 4 + 5), the others whole
+        sharded.pipelined_query(eng, ([s for _, s in p] for p in parts), heap, lens, 10, 10, 0.0, on_result=on_result,
+                                last_tiles=3)
         if rank == world - 1:
             q.put("".join(lines[i] for i in range(n_batches)))
         dist.barrier()
