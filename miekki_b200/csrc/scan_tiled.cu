@@ -374,29 +374,41 @@ scan_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const uint2* __restr
 // bucket plus a bitmap of the buckets that are present -- and read back in bucket order by
 // walking the bitmap (2^h / 32 words, 7 % of their bits set at config 3); a run of sentinels
 // follows.  Needs 2^h + 2^h / 8 bytes of shared memory: -h <= 17.  Only the bitmap is cleared.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict__ list_off,
                   const uint32_t* __restrict__ list_len, uint32_t n_reads, uint32_t n_buckets,
                   uint2* __restrict__ slist, const uint64_t* __restrict__ soff) {
     extern __shared__ __align__(16) uint8_t dense[];                 // fp byte per bucket | bitmap
-    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t warp_tot[32];
     const uint32_t padded = (n_buckets + 127) & ~127u;
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(dense + padded);
     const uint32_t n_words = padded / 32;
     // a warp owns a contiguous run of bitmap words, walked 32 words (one per lane) at a time
-    const uint32_t seg = ((n_words + 7) / 8 + 31) & ~31u;
+    const uint32_t n_warps = blockDim.x >> 5;
+    const uint32_t seg = ((n_words + n_warps - 1) / n_warps + 31) & ~31u;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t w0 = warp * seg, w1 = min(n_words, w0 + seg);
+    const uint32_t w0 = min(n_words, warp * seg), w1 = min(n_words, w0 + seg);
     for (uint32_t q = blockIdx.x; q < n_reads; q += gridDim.x) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) bitmap[i] = 0;
         __syncthreads();
         const uint32_t L = list_len[q];
         const uint32_t* src = list + list_off[q];
-        for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
-            const uint32_t e = src[i], b = e >> 8;
-            dense[b] = (uint8_t)e;
-            atomicOr(bitmap + (b >> 5), 1u << (b & 31));
+        // four entries in flight per thread: the loads are what this loop waits for
+        for (uint32_t i0 = threadIdx.x; i0 < L; i0 += 4 * blockDim.x) {
+            uint32_t e[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * blockDim.x;
+                e[u] = i < L ? src[i] : 0xFFFFFFFFu;
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * blockDim.x >= L) continue;
+                const uint32_t b = e[u] >> 8;
+                dense[b] = (uint8_t)e[u];
+                atomicOr(bitmap + (b >> 5), 1u << (b & 31));
+            }
         }
         __syncthreads();
         uint32_t mine = 0;
@@ -405,8 +417,10 @@ sort_lists_kernel(const uint32_t* __restrict__ list, const uint64_t* __restrict_
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
         if (lane == 0) warp_tot[warp] = mine;
         __syncthreads();
-        uint32_t running = 0;
-        for (uint32_t w = 0; w < warp; ++w) running += warp_tot[w];
+        // entries before this warp's run: the totals of the warps below it
+        uint32_t running = lane < warp ? warp_tot[lane] : 0u;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) running += __shfl_xor_sync(0xffffffffu, running, o);
         uint2* dst = slist + soff[q];
         for (uint32_t wb = w0; wb < w1; wb += 32) {                  // uniform trip count over the warp
             const uint32_t w = wb + lane;
@@ -511,7 +525,9 @@ void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uin
     if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sort_lists_kernel), smem)) return;
     fill_sentinels_kernel<<<1, 128, 0, st>>>(slist, 128);          // the block reads past the end walk
     const unsigned grid = n_reads < 148u * 8u ? n_reads : 148u * 8u;
-    sort_lists_kernel<<<grid, 256, smem, st>>>(list, list_off, list_len, n_reads, n_buckets, slist, soff);
+    // a table that leaves room for one CTA per SM only gets all the warps an SM can hold
+    const unsigned threads = smem > 113 * 1024 ? 1024u : smem > 56 * 1024 ? 512u : 256u;
+    sort_lists_kernel<<<grid, threads, smem, st>>>(list, list_off, list_len, n_reads, n_buckets, slist, soff);
 }
 
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,

@@ -867,7 +867,7 @@ compact_list_kernel(const unsigned long long* __restrict__ anc, const uint8_t* _
 //   slot = bucket << 40 | fp << 32 | position ; ~0 = empty.  Linear probing; a slot is claimed
 //   by its bucket with atomicCAS and then lowered with atomicMin, which orders (fp, position)
 //   because the bucket bits above them are equal.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 sketch_reads_kernel(const uint8_t* __restrict__ chars, const uint64_t* __restrict__ coff,
                     const uint64_t* __restrict__ len, const uint32_t* __restrict__ read_ids,
                     uint32_t n_ids, uint32_t max_words, uint32_t slots, SketchParams p,
@@ -1229,7 +1229,8 @@ int launch_sketch_reads(const uint8_t* chars, const uint64_t* coff, const uint64
     if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sketch_reads_kernel), smem)) return -2;
     const unsigned grid = n_ids < 148u * 32u ? n_ids : 148u * 32u;
     // a long read owns most of an SM's shared memory: give it enough warps to hide latency
-    const unsigned threads = slots >= 8192 ? 512u : slots >= 4096 ? 256u : 128u;
+    // (a 16,384-slot table is the only CTA on its SM)
+    const unsigned threads = slots >= 16384 ? 1024u : slots >= 8192 ? 512u : slots >= 4096 ? 256u : 128u;
     sketch_reads_kernel<<<grid, threads, smem, st>>>(chars, coff, len, read_ids, n_ids, words, slots, p,
                                                  bloom, list_off, list, list_len);
     return 0;
