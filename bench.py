@@ -650,6 +650,10 @@ def main():
             "dram_bytes_per_algorithmic_byte_ncu": (ncu_traffic({"h": a.c3_hbits, "genomes": gcount,
                                                                  "read_len": a.c3_read_len, "tiled": True})
                                                     or {}).get("dram_bytes_per_algorithmic_byte"),
+            "scan_bound_ncu": {k: (ncu_traffic({"h": a.c3_hbits, "genomes": gcount, "read_len": a.c3_read_len,
+                                                "tiled": True}) or {}).get(k)
+                               for k in ("shared_memory_pipe_pct", "issue_slots_busy_pct",
+                                         "dram_throughput_pct_of_theoretical")},
             "scan_kernel": "scan_tiled_kernel (rows staged once per 46 reads; DESIGN.md section 4)",
             "build_s": c3_build_s, "build_all_ranks": c3_build_all,
             "parity_checked": par3,
@@ -825,7 +829,13 @@ def main():
                          "traffic_source": ((traffic or {}).get("source", "") +
                                             " -- ncu capture of this configuration, scaled by the algorithmic "
                                             "bytes of this run's launches; not measured in this run")
-                                           if traffic else "no ncu capture of this configuration is committed"},
+                                           if traffic else "no ncu capture of this configuration is committed",
+                         # SURVEY 8(d)'s second bound: one byte compare per algorithmic byte, against the issue rate
+                         "second_bound": {"what": "byte compares (one per algorithmic byte; 32 genomes per lane "
+                                                  "and LOP3 in the bit-plane layout) against the SM issue rate",
+                                          "byte_compares_per_s": scan_gbs * 1e9,
+                                          "issue_slots_busy_pct_ncu": (traffic or {}).get("issue_slots_busy_pct"),
+                                          "source": "same ncu capture as traffic"}},
             "parity_checked": parity,
             "cpu_baseline": cpu,
             "clocks": clocks,
