@@ -435,6 +435,10 @@ def main():
     stream = torch.cuda.Stream(priority=-1)
     torch.cuda.set_stream(stream)
     ix.set_stream(stream.cuda_stream)
+    if world > 1:
+        # one SM for the NCCL kernels of the heap chain: they do not fit beside a ring-scan CTA and
+        # would wait for the next batch's scan to end (2 GPUs: 136.4 -> 134.3 ms per step)
+        ix.set_scan_spare_sms(1)
 
     def build_shard(index, first, count, genome_len):
         """count synthetic genomes (ids first ..) generated on the device and inserted;
@@ -573,8 +577,18 @@ def main():
             dev_ms = ev0.elapsed_time(ev1)
             st = self.ix.stats()
             t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+            # every rank's own scan time and step time: under the power cap GPUs of one box differ by a
+            # few per cent and the job runs at the pace of the slowest
+            mine = torch.tensor([st["scan_ms"] / max(1, steps), dev_ms / max(1, steps)], dtype=torch.float64,
+                                device="cuda")
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                every = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(every, mine)
+            else:
+                every = [mine]
+            self.per_rank = {"scan_ms_per_step": [round(float(e[0]), 2) for e in every],
+                             "step_ms": [round(float(e[1]), 2) for e in every]}
             return float(t[0]), float(t[1]), st
 
         def parity(self, n_sample, first_id):
@@ -598,6 +612,7 @@ def main():
     if rank == 0:
         sampler.start()
     dev_ms, wall_ms, st = w2.timed(w2.run_resident, a.steps, a.warmup)
+    per_rank = w2.per_rank
     clocks = sampler.stop() if rank == 0 else None
     e2e_dev_ms, e2e_wall_ms, st_e2e = w2.timed(w2.run_e2e, a.steps, max(3, a.warmup))
     parity = w2.parity(a.parity_reads, first)
@@ -629,6 +644,7 @@ def main():
         w3 = Workload(ix3, r3, o3, l3, 0.0)
         # two warm-up steps: the pipelined path alternates between two sets of buffers, both are sized before timing
         d3_ms, _, st3 = w3.timed(w3.run_resident, a.c3_steps, 2)
+        per_rank3 = w3.per_rank
         _, e3_wall_ms, _ = w3.timed(w3.run_e2e, 2, 2)
         par3 = w3.parity(16, gfirst)
         c3_kbp = a.c3_reads * a.c3_read_len / 1e3
@@ -645,6 +661,7 @@ def main():
             "phases_ms_per_step": {"read_sketch": st3["read_sketch_ms"] / a.c3_steps,
                                    "scan": st3["scan_ms"] / a.c3_steps, "topk": st3["topk_ms"] / a.c3_steps},
             "surviving_buckets_per_read": st3["scan_rows"] / max(1, a.c3_steps * a.c3_reads),
+            "per_rank": per_rank3,
             # DRAM bytes per algorithmic byte of the scan from the committed ncu capture of this shape
             # (tiled kernel), when there is one; not measured in this run
             "dram_bytes_per_algorithmic_byte_ncu": (ncu_traffic({"h": a.c3_hbits, "genomes": gcount,
@@ -842,6 +859,7 @@ def main():
             "phases_ms_per_step": {"read_sketch": st["read_sketch_ms"] / a.steps, "scan": st["scan_ms"] / a.steps,
                                    "topk": st["topk_ms"] / a.steps},
             "surviving_buckets_per_read": st["scan_rows"] / max(1, a.steps * a.reads),
+            "per_rank": per_rank,
             "build": {"workload": "C4 point: %d x %.1f Mbp genomes per GPU, -k %d -h %d (config 3 adds -h %d)"
                                   % (a.genomes, a.genome_len / 1e6, a.k, a.hbits, a.c3_hbits),
                       "kernel_gbp_per_s": build_mine["kernel_gbp_per_s"],

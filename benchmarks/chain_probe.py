@@ -4,7 +4,8 @@
 substitutions at -s 0, two batches through mk_scan_async / mk_topk_slot exactly as
 sharded.pipelined_query issues them on one rank.  Host wall clock per call, once as the first rank
 of a chain (chain_in = 0) and once as a later rank (chain_in = 1, heap state of a previous shard),
-whole batch and in tiles of reads.  Prints one JSON line."""
+whole batch and in tiles of reads; then PROBE_STEPS batches in steady state, pipelined and through
+mk_query_batch.  Prints one JSON line."""
 import json
 import os
 import sys
@@ -83,6 +84,35 @@ def main():
     ix.sync()
     out["topk_alone_ms"] = t(lambda: ix.topk_slot_ptr(s, heap.ctypes.data, lens.ctypes.data, K, 10, 0.0,
                                                       chain_in=True, finalize=True))
+    # steady state: PROBE_STEPS batches through the pipelined pair (scan of batch i + 1 enqueued before
+    # batch i's heap step, as sharded.pipelined_query does) against the same batches through mk_query_batch
+    steps = int(os.environ.get("PROBE_STEPS", "6"))
+    min_int = float(os.environ.get("PROBE_MIN_INT", "0"))
+
+    def pipelined():
+        pending = None
+        for i in range(steps):
+            s_ = ix.scan_async(batches[i & 1])
+            if pending is not None:
+                ix.topk_slot_ptr(pending, heap.ctypes.data, lens.ctypes.data, K, 10, min_int, chain_in=False, finalize=True)
+            pending = s_
+        ix.topk_slot_ptr(pending, heap.ctypes.data, lens.ctypes.data, K, 10, min_int, chain_in=False, finalize=True)
+        ix.sync()
+
+    def plain():
+        for i in range(steps):
+            ix.query_batch(batches[i & 1], K, 10, min_int, fetch=False)
+        ix.sync()
+
+    ix.set_shard(0)
+    for name, f in (("pipelined", pipelined), ("query_batch", plain)):
+        f()
+        ix.stats_reset()
+        ms = t(f)
+        st = ix.stats()
+        out["steady_" + name] = {"ms_per_step": round(ms / steps, 2), "scan_ms_per_step": round(st["scan_ms"] / steps, 2),
+                                 "read_sketch_ms_per_step": round(st["read_sketch_ms"] / steps, 2),
+                                 "topk_ms_per_step": round(st["topk_ms"] / steps, 2)}
     print(json.dumps(out))
     ix.close()
 

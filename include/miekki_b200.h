@@ -200,6 +200,12 @@ int mk_topk(mk_ctx *ctx, uint32_t nresults, uint32_t min_score, double min_inter
  * mk_topk_slot for a slot before its tile is scanned into again.  `reads` must stay alive
  * until the scan has run (e.g. until the matching mk_topk_slot returned). */
 int mk_scan_async(mk_ctx *ctx, const mk_batch *reads, int *slot);
+/* Optional, ahead of mk_scan_async: enqueues the read sketch of the batch the NEXT mk_scan_async
+ * will be given (which then only enqueues the scan), so that a caller who has to wait for
+ * something else before it may scan -- the previous batch's heap from another shard -- does not
+ * leave the sketch for afterwards.  Returns at once.  The index must not change in between; any
+ * other batch passed to mk_scan_async is simply sketched there as usual. */
+int mk_sketch_async(mk_ctx *ctx, const mk_batch *reads);
 int mk_topk_slot(mk_ctx *ctx, int slot, uint32_t nresults, uint32_t min_score,
                  double min_intersection, mk_hit *heap_io, uint32_t *len_io, int chain_in,
                  int finalize);

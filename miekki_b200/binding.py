@@ -77,6 +77,7 @@ SIGNATURES = {
     "mk_scan": (_i, [_vp, _vp]),
     "mk_topk": (_i, [_vp, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_scan_async": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "mk_sketch_async": (_i, [_vp, _vp]),
     "mk_topk_slot": (_i, [_vp, _i, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_topk_slot_range": (_i, [_vp, _i, _u32, _u32, _u32, _u32, _d, _vp, _vp, _i, _i]),
     "mk_query": (_i, [_vp, _vp, _vp, _u32, _u32, _u32, _d, _vp, _vp]),
@@ -364,6 +365,10 @@ class Miekki:
         slot = C.c_int(0)
         self._ck(lib().mk_scan_async(self._ctx, batch._h, C.byref(slot)))
         return slot.value
+
+    def sketch_async(self, batch: Batch) -> None:
+        """Enqueue the read sketch of the batch the next scan_async will be given."""
+        self._ck(lib().mk_sketch_async(self._ctx, batch._h))
 
     def topk_slot_ptr(self, slot: int, heap_ptr: int, len_ptr: int, nresults=10, min_score=10,
                       min_intersection=None, chain_in=False, finalize=True, first=0, count=None):

@@ -54,6 +54,11 @@ struct mk_batch {
     uint32_t n = 0;
     uint64_t bytes = 0;           // padded size of chars
     uint64_t bases = 0, max_len = 0;
+    uint64_t serial = next_serial();   // tells a batch from a later one at the same address
+    static uint64_t next_serial() {
+        static std::atomic<uint64_t> n{0};
+        return ++n;
+    }
 };
 
 struct mk_ctx {
@@ -99,6 +104,16 @@ struct mk_ctx {
     cudaEvent_t slot_ev[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
     cudaEvent_t sk_ev = nullptr;
+    // mk_sketch_async: lists of the batch the next mk_scan_async will be given, built ahead of it
+    struct PreparedLists {
+        uint64_t serial = 0;
+        int slot = -1;
+        uint32_t *list = nullptr, *list_len = nullptr;
+        uint64_t *list_off = nullptr, *soff = nullptr;
+        void* slist = nullptr;
+        bool long_lists = false;
+        cudaEvent_t ev = nullptr;
+    } prep;
     void* meta_pin[2] = {nullptr, nullptr};
     size_t meta_pin_cap[2] = {0, 0};
     int meta_flip = 0;
@@ -713,6 +728,7 @@ int upload_packed(mk_ctx* c, const char* const* seqs, const uint64_t* lens, uint
 // appends the sequences of a batch (characters in HBM) or of a packed batch to the index
 template <class Batch>
 int index_add_any(mk_ctx* c, const Batch* b) {
+    c->prep.serial = 0;        // lists sketched ahead saw the old index
     for (uint32_t i = 0; i < b->n; ++i)
         if (b->h_len[i] < c->k)
             return fail(c, MK_ERR_ARG, "mk_index_add: sequence shorter than k (the reference's callers skip these, Miekki.cpp:569)");
@@ -1141,6 +1157,69 @@ int query_device(mk_ctx* c, const mk_batch* b, uint32_t K, uint32_t min_score, d
     return sync(c);
 }
 
+// Read sketch (+ list sort) of batch b into the list buffers of `slot`.  Short reads are sketched
+// on the sketch stream, so that the work overlaps the scan still running on the main stream, and
+// the main stream is made to wait for it (or, with done != nullptr, `done` is recorded instead and
+// the caller waits later); long reads need the main-stream dense scratch and are sketched in line.
+int sketch_for_slot(mk_ctx* c, const mk_batch* b, int slot, Lists* L, cudaEvent_t done) {
+    const uint32_t n = b->n;
+    bool has_long = false;
+    for (uint32_t i = 0; i < n && !has_long; ++i) has_long = b->h_len[i] > c->k + SPARSE_MAX_KMERS;
+    if (has_long) {
+        if (done) return 1;                          // not ahead of the scan: the caller falls back
+        c->bl_set = slot;
+        int r = build_lists(c, b, 0, n, L);
+        c->bl_set = 0;
+        TRY(r);
+        TRY(account_lists(c, *L, n, nullptr));
+        return MK_OK;
+    }
+    if (!c->sk_ev) CU(cudaEventCreateWithFlags(&c->sk_ev, cudaEventDisableTiming));
+    if (c->slot_used[slot]) CU(cudaStreamWaitEvent(c->sk_stream, c->slot_ev[slot], 0));   // last scan of this slot
+    // No wait on the main stream: it may hold the previous batch's scan, beside which this
+    // sketch is meant to run.  The reads themselves are complete: every call that creates a
+    // batch returns only after its copies have finished.
+    c->bl_stream = c->sk_stream;
+    c->bl_set = slot;
+    int r = build_lists(c, b, 0, n, L);
+    if (r == MK_OK) r = account_lists(c, *L, n, nullptr, c->sk_stream);
+    c->bl_stream = nullptr;
+    c->bl_set = 0;
+    TRY(r);
+    if (done) {
+        CU(cudaEventRecord(done, c->sk_stream));
+    } else {
+        CU(cudaEventRecord(c->sk_ev, c->sk_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->sk_ev, 0));
+    }
+    return MK_OK;
+}
+
+// mk_sketch_async: the lists of the batch the NEXT mk_scan_async will be given
+int sketch_ahead(mk_ctx* c, const mk_batch* b) {
+    c->prep.serial = 0;
+    if (b->n == 0) return MK_OK;
+    const int slot = c->next_slot ^ 1;
+    if (!c->slot_ev[0]) {
+        CU(cudaEventCreateWithFlags(&c->slot_ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->slot_ev[1], cudaEventDisableTiming));
+    }
+    if (!c->prep.ev) CU(cudaEventCreateWithFlags(&c->prep.ev, cudaEventDisableTiming));
+    Lists L{};
+    const int r = sketch_for_slot(c, b, slot, &L, c->prep.ev);
+    if (r == 1) return MK_OK;                   // long reads: mk_scan_async sketches them itself
+    TRY(r);
+    c->prep.serial = b->serial;
+    c->prep.slot = slot;
+    c->prep.list = L.list;
+    c->prep.list_off = L.list_off;
+    c->prep.list_len = L.list_len;
+    c->prep.slist = L.slist;
+    c->prep.soff = L.soff;
+    c->prep.long_lists = L.long_lists;
+    return MK_OK;
+}
+
 // sketch + scan of a whole batch with the counts kept in HBM (for the chained top-k).
 // Asynchronous: everything is enqueued on the ctx stream, the counts go to one of two tiles
 // ("slots") so that the top-k of one batch can run (aux stream) while the next batch scans.
@@ -1158,34 +1237,20 @@ int scan_all_async(mk_ctx* c, const mk_batch* b, int* slot_out) {
         CU(cudaEventCreateWithFlags(&c->slot_ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->slot_ev[1], cudaEventDisableTiming));
     }
-    // The sketch runs on the sketch stream into the list buffers of this slot, so that it
-    // overlaps the scan of the previous batch (still running on the main stream).  Long reads
-    // need the main-stream dense scratch and are sketched in line.
-    bool has_long = false;
-    for (uint32_t i = 0; i < n && !has_long; ++i) has_long = b->h_len[i] > c->k + SPARSE_MAX_KMERS;
     Lists L{};
-    if (has_long) {
-        c->bl_set = slot;
-        int r = build_lists(c, b, 0, n, &L);
-        c->bl_set = 0;
-        TRY(r);
-        TRY(account_lists(c, L, n, nullptr));
+    if (c->prep.serial == b->serial && c->prep.slot == slot) {
+        // mk_sketch_async has built this batch's lists already (on the sketch stream)
+        L.list = c->prep.list;
+        L.list_off = c->prep.list_off;
+        L.list_len = c->prep.list_len;
+        L.slist = c->prep.slist;
+        L.soff = c->prep.soff;
+        L.long_lists = c->prep.long_lists;
+        CU(cudaStreamWaitEvent(c->stream, c->prep.ev, 0));
     } else {
-        if (!c->sk_ev) CU(cudaEventCreateWithFlags(&c->sk_ev, cudaEventDisableTiming));
-        if (c->slot_used[slot]) CU(cudaStreamWaitEvent(c->sk_stream, c->slot_ev[slot], 0));   // last scan of this slot
-        // No wait on the main stream: it may hold the previous batch's scan, beside which this
-        // sketch is meant to run.  The reads themselves are complete: every call that creates a
-        // batch returns only after its copies have finished.
-        c->bl_stream = c->sk_stream;
-        c->bl_set = slot;
-        int r = build_lists(c, b, 0, n, &L);
-        if (r == MK_OK) r = account_lists(c, L, n, nullptr, c->sk_stream);
-        c->bl_stream = nullptr;
-        c->bl_set = 0;
-        TRY(r);
-        CU(cudaEventRecord(c->sk_ev, c->sk_stream));
-        CU(cudaStreamWaitEvent(c->stream, c->sk_ev, 0));
+        TRY(sketch_for_slot(c, b, slot, &L, nullptr));
     }
+    c->prep.serial = 0;
     DevBuf& tile = slot ? c->counts2 : c->counts;
     if (c->n > 0) {
         ScanPlan plan{};
@@ -1700,6 +1765,7 @@ static int import_end(mk_ctx* c, const uint64_t* genome_size, const uint8_t* blo
 int mk_index_import_begin(mk_ctx* c, uint32_t n) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
+    c->prep.serial = 0;        // lists sketched ahead saw the old index
     return import_begin(c, n);
 }
 
@@ -1716,6 +1782,7 @@ int mk_index_import_end(mk_ctx* c, const uint64_t* genome_size, const uint8_t* b
                         const uint32_t* sketch_size) {
     if (!c) return MK_ERR_ARG;
     Guard g(c);
+    c->prep.serial = 0;        // lists sketched ahead saw the old index
     if (!c->import_open) return fail(c, MK_ERR_STATE, "mk_index_import_end: call mk_index_import_begin first");
     if (c->importing && (!genome_size || !sketch_size))
         return fail(c, MK_ERR_ARG, "mk_index_import_end: NULL argument");
@@ -1797,6 +1864,7 @@ uint64_t mk_bloom_reach(uint32_t k, uint32_t bloom_log2) {
 int mk_bloom_get(mk_ctx* c, uint8_t* dst, uint64_t n) {
     if (!c || !dst) return MK_ERR_ARG;
     Guard g(c);
+    c->prep.serial = 0;        // lists sketched ahead saw the old index
     if (n > c->window) return fail(c, MK_ERR_ARG, "mk_bloom_get: n exceeds the window");
     CU(cudaMemcpyAsync(dst, c->bloom, n, cudaMemcpyDefault, c->stream));
     c->stats.d2h_bytes += n;
@@ -1806,6 +1874,7 @@ int mk_bloom_get(mk_ctx* c, uint8_t* dst, uint64_t n) {
 int mk_bloom_set(mk_ctx* c, const uint8_t* src, uint64_t n) {
     if (!c || !src) return MK_ERR_ARG;
     Guard g(c);
+    c->prep.serial = 0;        // lists sketched ahead saw the old index
     if (n > c->window) return fail(c, MK_ERR_ARG, "mk_bloom_set: n exceeds the window");
     CU(cudaMemcpyAsync(c->bloom, src, n, cudaMemcpyDefault, c->stream));
     c->stats.h2d_bytes += n;
@@ -1815,6 +1884,7 @@ int mk_bloom_set(mk_ctx* c, const uint8_t* src, uint64_t n) {
 int mk_bloom_merge(mk_ctx* c, const uint8_t* src, uint64_t n) {
     if (!c || !src) return MK_ERR_ARG;
     Guard g(c);
+    c->prep.serial = 0;        // lists sketched ahead saw the old index
     if (n > c->window || n % 16) return fail(c, MK_ERR_ARG, "mk_bloom_merge: n must be a multiple of 16 within the window");
     TRY(reserve(c, c->misc, n));
     CU(cudaMemcpyAsync(c->misc.p, src, n, cudaMemcpyDefault, c->stream));
@@ -1863,6 +1933,12 @@ int mk_scan_async(mk_ctx* c, const mk_batch* reads, int* slot) {
     if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_scan_async: NULL argument");
     Guard g(c);
     return scan_all_async(c, reads, slot);
+}
+
+int mk_sketch_async(mk_ctx* c, const mk_batch* reads) {
+    if (!c || !reads) return fail(c, MK_ERR_ARG, "mk_sketch_async: NULL argument");
+    Guard g(c);
+    return sketch_ahead(c, reads);
 }
 
 int mk_topk(mk_ctx* c, uint32_t nresults, uint32_t min_score, double min_intersection, mk_hit* heap_io,

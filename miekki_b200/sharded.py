@@ -15,7 +15,9 @@ The functions are backend-agnostic: tensors live on the GPU with NCCL, or on the
 """
 from __future__ import annotations
 
+import json
 import os
+import time
 
 import torch
 import torch.distributed as dist
@@ -70,7 +72,8 @@ def drain_tiles(n_reads: int, world: int) -> int:
 
 
 def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, min_score: int,
-                 min_intersection: float, group=None, slot: int | None = None, tiles: int = 1) -> None:
+                 min_intersection: float, group=None, slot: int | None = None, tiles: int = 1,
+                 trace: list | None = None) -> None:
     """heap: uint8 [n_reads, nresults * 24], lens: int32 [n_reads], on the engine's device.
     `engine.topk_ptr(heap_ptr, len_ptr, nresults, min_score, min_intersection, chain_in,
     finalize)` applies this rank's stored counts to the heap state in place
@@ -99,6 +102,8 @@ def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, 
             _exchange(dist.irecv, (h, l), rank - 1, group)
             if heap.is_cuda:
                 torch.cuda.current_stream().synchronize()      # the engine reads the buffers next
+        if trace is not None:
+            trace.append(("received", t, time.perf_counter()))
         if slot is None:
             engine.topk_ptr(heap.data_ptr(), lens.data_ptr(), nresults, min_score, min_intersection, **kw)
         elif tiles == 1:
@@ -107,13 +112,15 @@ def chained_topk(engine, heap: torch.Tensor, lens: torch.Tensor, nresults: int, 
         else:
             engine.topk_slot_ptr(slot, h.data_ptr(), l.data_ptr(), nresults, min_score, min_intersection,
                                  first=a, count=b - a, **kw)
+        if trace is not None:
+            trace.append(("stepped", t, time.perf_counter()))
         if rank < world - 1:
             _exchange(dist.isend, (h, l), rank + 1, group)
 
 
 def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nresults: int,
                     min_score: int, min_intersection: float, on_result=None, after_chain=None,
-                    group=None, last_tiles: int | None = None) -> None:
+                    group=None, last_tiles: int | None = None, tiles: int | None = None) -> None:
     """Software pipeline over read batches: the scan of batch i+1 is enqueued before batch i's
     heap is chained through the ranks, so the cheap, latency-bound chain hides behind the scan.
     `batches` yields engine batches; `on_result(i)` is called on the last rank when batch i's hit
@@ -125,13 +132,24 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
     from must not be written again (by the next batch's top-k on the first rank) before that.
     A buffer is reused two batches later, after the event recorded behind its sends.
 
-    The last batch has no scan to hide behind: it is chained in `last_tiles` tiles of reads
-    (default `drain_tiles`), see chained_topk."""
+    Every batch is chained in `tiles` tiles of reads (default: one per rank, tiles of >= 1,024
+    reads), so that a rank steps tile t while the next one steps tile t - 1 and the chain takes
+    about two heap steps instead of `world`; the last batch, which has no scan to hide behind, in
+    `last_tiles` (default `drain_tiles`).  See chained_topk.
+
+    On GPUs the engine should leave one SM out of the scan's grid (`set_scan_spare_sms(1)`): the
+    NCCL kernels of the chain do not fit beside a persistent scan CTA and would otherwise wait
+    for the scan of the next batch to end, and the rank waiting for the heap with them."""
     side = torch.cuda.Stream() if heap.is_cuda else None
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     bufs = [(heap, lens), (torch.empty_like(heap), torch.empty_like(lens))]
     sent = [None, None]
+    # MIEKKI_CHAIN_TRACE=<prefix>: host time stamps of every batch's steps on this rank, one JSON line
+    # per call appended to <prefix>.rank<r> (when did the heap arrive, when was it stepped)
+    trace_to = os.environ.get("MIEKKI_CHAIN_TRACE")
+    events = [] if trace_to else None
+    t_origin = time.perf_counter()
 
     def finish(i, slot, tiles=1):
         h, l = bufs[i & 1]
@@ -139,7 +157,10 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
         def body():
             if sent[i & 1] is not None:
                 sent[i & 1].synchronize()           # the sends of batch i - 2 have left this buffer
-            chained_topk(engine, h, l, nresults, min_score, min_intersection, group, slot, tiles)
+            tr = [] if events is not None else None
+            chained_topk(engine, h, l, nresults, min_score, min_intersection, group, slot, tiles, tr)
+            if events is not None:
+                events.append({"batch": i, "steps": [(w, t, round(1e3 * (x - t_origin), 2)) for w, t, x in tr]})
             if side is not None and rank < world - 1:
                 sent[i & 1] = torch.cuda.Event()
                 sent[i & 1].record(torch.cuda.current_stream())
@@ -159,11 +180,24 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
             body()
 
     pending = None
-    for i, b in enumerate(batches):
-        slot = engine.scan_async(b)
+    it = iter(batches)
+    nxt = next(it, None)
+    sketch_ahead = getattr(engine, "sketch_async", None)
+    i = 0
+    while nxt is not None:
+        slot = engine.scan_async(nxt)
+        if events is not None:
+            events.append({"batch": i, "scan_enqueued": round(1e3 * (time.perf_counter() - t_origin), 2)})
+        # The next batch is sketched now, beside the scan just enqueued: the chain step below may
+        # return only when that scan has ended (a later rank waits for the previous rank's heap),
+        # and a sketch enqueued then would run with the GPU otherwise idle.
+        nxt = next(it, None)
+        if nxt is not None and sketch_ahead is not None:
+            sketch_ahead(nxt)
         if pending is not None:
-            finish(*pending)
+            finish(*pending, tiles=max(1, min(world, heap.shape[0] // 1024)) if tiles is None else tiles)
         pending = (i, slot)
+        i += 1
     if pending is not None:
         finish(*pending, tiles=drain_tiles(heap.shape[0], world) if last_tiles is None else last_tiles)
         if on_result is None and rank == world - 1 and (pending[0] & 1):
@@ -177,3 +211,6 @@ def pipelined_query(engine, batches, heap: torch.Tensor, lens: torch.Tensor, nre
                 lens.copy_(bufs[1][1])
     if side is not None:
         side.synchronize()
+    if events is not None:
+        with open("%s.rank%d" % (trace_to, rank), "a") as f:
+            f.write(json.dumps({"total_ms": round(1e3 * (time.perf_counter() - t_origin), 2), "events": events}) + "\n")

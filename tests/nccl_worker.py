@@ -33,6 +33,7 @@ def main():
     first, count = sharded.shard_range(G, rank, world)
     ix = miekki_b200.Miekki(k=k, h=h, threshold=200, device=local)
     ix.set_shard(first)
+    ix.set_scan_spare_sms(1)       # as bench.py does: room for the NCCL kernels of the chain
     ix.insert_sequences(genomes[first:first + count])
     w = ix.bloom_window()
     mine = torch.empty(w, dtype=torch.uint8, device="cuda")
@@ -60,7 +61,7 @@ def main():
             got[i] = (heap.cpu().numpy().view(miekki_b200.HIT_DTYPE).reshape(per, K).copy(),
                       lens.cpu().numpy().view(np.uint32).copy())
         # the last batch is chained in 3 tiles of reads (mk_topk_slot_range), the others whole
-        sharded.pipelined_query(ix, iter(batches), heap, lens, K, 10, 0.5 * thr, on_result=on_result, last_tiles=3)
+        sharded.pipelined_query(ix, iter(batches), heap, lens, K, 10, 0.5 * thr, on_result=on_result, tiles=2, last_tiles=3)
         if rank == world - 1:
             assert sorted(got) == list(range(nb))
             for b in range(nb):

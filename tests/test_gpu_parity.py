@@ -248,6 +248,44 @@ def test_case_a_read_slices_bound_list_memory(mk, case_a, monkeypatch):
     monkeypatch.delenv("MIEKKI_LIST_BUDGET_ENTRIES")
 
 
+@pytest.mark.parametrize("tiled", ["0", "1"])
+def test_case_a_sketch_ahead_of_the_scan(mk, case_a, monkeypatch, tiled):
+    """mk_sketch_async: the lists of the next batch are built before mk_scan_async is called with it
+    (both scan kernels); a different batch than the one sketched ahead is sketched as usual, and so
+    is a batch sketched ahead of an index change."""
+    monkeypatch.setenv("MIEKKI_SCAN_TILED", tiled)
+    d, ix, _ = case_a
+    reads = [s for _, s in H.reads_like_reference(os.path.join(d, "reads.fa"), 31)]
+    parts = [reads[:20], reads[20:], reads[7:31]]
+    batches = [ix.upload(p) for p in parts]
+    want = [ix.query(p, 10, 10, 100.0) for p in parts]
+
+    def step(slot, i):
+        heap = np.zeros((len(parts[i]), 10), mk.HIT_DTYPE)
+        lens = np.zeros(len(parts[i]), np.uint32)
+        ix.topk_slot_ptr(slot, heap.ctypes.data, lens.ctypes.data, 10, 10, 100.0)
+        for j in range(len(parts[i])):
+            assert heap[j, :lens[j]].tobytes() == want[i][j].tobytes(), (i, j)
+
+    ix.sketch_async(batches[0])
+    s0 = ix.scan_async(batches[0])             # uses the lists sketched ahead
+    ix.sketch_async(batches[1])                # beside the scan of batch 0
+    step(s0, 0)
+    s1 = ix.scan_async(batches[1])
+    ix.sketch_async(batches[0])                # sketched ahead, but batch 2 comes next
+    step(s1, 1)
+    s2 = ix.scan_async(batches[2])
+    step(s2, 2)
+    launches = ix.stats()["kernel_launches"]
+    ix.sketch_async(batches[1])
+    assert ix.stats()["kernel_launches"] > launches
+    s3 = ix.scan_async(batches[1])
+    step(s3, 1)
+    ix.sync()
+    for b in batches:
+        b.free()
+
+
 def test_case_a_topk_slot_in_read_ranges(mk, case_a):
     """mk_topk_slot_range: the heap step over a batch in ragged ranges of reads (in any order,
     pointers addressing the range's first read) gives the lists of the whole-batch step; a range

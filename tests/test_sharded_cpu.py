@@ -36,7 +36,13 @@ class OracleEngine:
         self.counts = [self.o.counts(s)[0] for s in reads]
 
     # the pipelined pair of binding.Miekki: two count tiles, alternating
+    def sketch_async(self, reads):
+        self.sketched_ahead = reads            # mk_sketch_async: the batch the next scan_async gets
+
     def scan_async(self, reads):
+        ahead = getattr(self, "sketched_ahead", None)
+        assert ahead is None or ahead is reads, "sketch_async was given another batch than the next scan"
+        self.sketched_ahead = None
         self.slot = getattr(self, "slot", 0) ^ 1
         if not hasattr(self, "tiles"):
             self.tiles = {}
@@ -117,9 +123,9 @@ def _pipelined_worker(rank, world, port, case, k, h, b, n_batches, q):
             hn = heap.numpy()
             lines[i] = "".join(orc.format_hit_line(hd, hn[j].view(orc.HIT_DTYPE)[: int(lens[j])])
                                for j, (hd, _) in enumerate(parts[i]))
-        # the last batch travels in 3 tiles of reads (5 + 4 + 5), the others whole
+        # the last batch travels in 3 tiles of reads (5 + 4 + 5), the others in 2
         sharded.pipelined_query(eng, ([s for _, s in p] for p in parts), heap, lens, 10, 10, 0.0, on_result=on_result,
-                                last_tiles=3)
+                                tiles=2, last_tiles=3)
         if rank == world - 1:
             q.put("".join(lines[i] for i in range(n_batches)))
         dist.barrier()
