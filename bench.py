@@ -667,10 +667,12 @@ def main():
             "dram_bytes_per_algorithmic_byte_ncu": (ncu_traffic({"h": a.c3_hbits, "genomes": gcount,
                                                                  "read_len": a.c3_read_len, "tiled": True})
                                                     or {}).get("dram_bytes_per_algorithmic_byte"),
-            "scan_bound_ncu": {k: (ncu_traffic({"h": a.c3_hbits, "genomes": gcount, "read_len": a.c3_read_len,
-                                                "tiled": True}) or {}).get(k)
+            # what binds the tiled kernel, from its committed ncu capture (12,500 genomes: the pipe
+            # utilisation is a property of the kernel, not of the shard's width)
+            "scan_bound_ncu": {k: (ncu_traffic({"h": a.c3_hbits, "read_len": a.c3_read_len, "tiled": True})
+                                   or {}).get(k)
                                for k in ("shared_memory_pipe_pct", "issue_slots_busy_pct",
-                                         "dram_throughput_pct_of_theoretical")},
+                                         "dram_throughput_pct_of_theoretical", "source")},
             "scan_kernel": "scan_tiled_kernel (rows staged once per 46 reads; DESIGN.md section 4)",
             "build_s": c3_build_s, "build_all_ranks": c3_build_all,
             "parity_checked": par3,
