@@ -939,7 +939,8 @@ int build_lists(mk_ctx* c, const mk_batch* b, uint32_t first, uint32_t n, Lists*
             CU(cudaMemcpyAsync(d_soff, soff, (size_t)n * 8, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(c->meta_ev[c->meta_flip], st));
             c->stats.h2d_bytes += (size_t)n * 8;
-            launch_sort_lists(list, d_off, d_len, n, (int)c->h, d_slist, d_soff, st);
+            if (launch_sort_lists(list, d_off, d_len, n, (int)c->h, d_slist, d_soff, st) != 0)
+                return fail(c, MK_ERR_CUDA, "sort_lists launch configuration failed (shared-memory opt-in)");
             c->stats.kernel_launches += 2;
             CU(cudaGetLastError());
             out->slist = d_slist;

@@ -152,7 +152,7 @@ uint32_t sorted_list_capacity(uint64_t entries);
 // ascending buckets, then sentinels.  soff[q] >= 128 and a multiple of 64: the first 128 entries of
 // slist are a block of sentinels.
 constexpr size_t SORTED_ENTRY_BYTES = 8;
-void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
+int launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
                        void* slist, const uint64_t* soff, cudaStream_t st);
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,
                       const void* slist, const uint64_t* soff, uint32_t n_reads, bool long_lists, uint32_t* counts,

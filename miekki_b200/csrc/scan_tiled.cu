@@ -515,19 +515,20 @@ int tiled_plan(uint32_t n_genomes, int h, int sm_count, size_t smem_optin_bytes,
     return 0;
 }
 
-void launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
-                       void* slist_, const uint64_t* soff, cudaStream_t st) {
+int launch_sort_lists(const uint32_t* list, const uint64_t* list_off, const uint32_t* list_len, uint32_t n_reads, int h,
+                      void* slist_, const uint64_t* soff, cudaStream_t st) {
     uint2* slist = static_cast<uint2*>(slist_);
-    if (!n_reads) return;
+    if (!n_reads) return 0;
     const uint32_t n_buckets = 1u << h;
     const size_t padded = (n_buckets + 127) & ~(size_t)127;
     const size_t smem = padded + padded / 8;                       // fp bytes + bitmap
-    if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sort_lists_kernel), smem)) return;
+    if (smem > 48 * 1024 && !smem_optin(reinterpret_cast<const void*>(sort_lists_kernel), smem)) return -1;
     fill_sentinels_kernel<<<1, 128, 0, st>>>(slist, 128);          // the block reads past the end walk
     const unsigned grid = n_reads < 148u * 8u ? n_reads : 148u * 8u;
     // a table that leaves room for one CTA per SM only gets all the warps an SM can hold
     const unsigned threads = smem > 113 * 1024 ? 1024u : smem > 56 * 1024 ? 512u : 256u;
     sort_lists_kernel<<<grid, threads, smem, st>>>(list, list_off, list_len, n_reads, n_buckets, slist, soff);
+    return 0;
 }
 
 int launch_scan_tiled(const TiledPlan& plan, const uint8_t* rows, uint64_t stride, uint32_t n_genomes, int h,

@@ -196,3 +196,17 @@ def test_fold_bloom_lowest_rank_wins():
     b = torch.tensor([2, 8, 0, 0], dtype=torch.uint8)
     c = torch.tensor([16, 16, 16, 16], dtype=torch.uint8)
     assert sharded.fold_bloom([a, b, c]).tolist() == [2, 4, 16, 1]
+
+
+def test_drain_tiles_and_nccl_defaults(monkeypatch):
+    from miekki_b200 import sharded
+    assert sharded.drain_tiles(100_000, 8) == 16          # 2 x world tiles ...
+    assert sharded.drain_tiles(20_000, 8) == 16
+    assert sharded.drain_tiles(5_000, 8) == 4             # ... of at least 1,024 reads
+    assert sharded.drain_tiles(14, 3) == 1
+    monkeypatch.delenv("NCCL_MAX_P2P_NCHANNELS", raising=False)
+    sharded.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_P2P_NCHANNELS"] == "1"
+    monkeypatch.setenv("NCCL_MAX_P2P_NCHANNELS", "4")     # the user's own setting wins
+    sharded.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_P2P_NCHANNELS"] == "4"
