@@ -498,6 +498,21 @@ def _random_index_and_long_reads(mk, short_only=False):
         assert np.array_equal(hits[i]["genome"], oh["genome"])
         assert np.array_equal(hits[i]["matches"], oh["matches"])
         np.testing.assert_allclose(hits[i]["intersection"], oh["intersection"], rtol=REL_TOL)
+    # the same reads through the pipelined pair with the sketch enqueued ahead of the scan: a batch
+    # with a read past the shared-memory sketch's reach is left to mk_scan_async (dense read path),
+    # a batch of short reads (ragged, some shorter than k) is sketched ahead
+    for part in (reads, [r for r in reads if len(r) <= 12000]):
+        b = ix.upload(part)
+        heap = np.zeros((len(part), 10), mk.HIT_DTYPE)
+        lens = np.zeros(len(part), np.uint32)
+        ix.sketch_async(b)
+        slot = ix.scan_async(b)
+        ix.topk_slot_ptr(slot, heap.ctypes.data, lens.ctypes.data, 10, 10, 10.0)
+        ix.sync()
+        want = ix.query(part, 10, 10, 10.0)
+        for i in range(len(part)):
+            assert heap[i, :lens[i]].tobytes() == want[i].tobytes(), (i, len(part[i]))
+        b.free()
     ix.close()
 
 
