@@ -536,7 +536,8 @@ def main():
             first_step, self.step_no = self.step_no, self.step_no + steps
             if steps:
                 self.last_order = (first_step + steps - 1) & 1
-            if world == 1:
+            if world == 1 and os.environ.get("MIEKKI_BENCH_E2E_SERIAL"):
+                # one blocking call per step (upload, query, read back in sequence): the simplest use
                 import ctypes as C
                 lib = miekki_b200.lib()
                 for s_ in range(first_step, first_step + steps):
@@ -546,6 +547,8 @@ def main():
                                                    C.c_void_p(self.nh_host.data_ptr())))
                     b.free()
                 return
+            # Streaming use, one GPU or many: the reads of step i + 1 are uploaded (and sketched) while
+            # step i scans, the hit lists of step i come back while step i + 1 scans.
             live = {}
 
             def uploads():
@@ -834,7 +837,12 @@ def main():
             "config": config_of(a, world),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] // a.steps),
-                    "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] // a.steps + (a.reads * (K * 24 + 4) if world > 1 else 0)),
+                    # the streaming path reads the hit lists back with its own copy (not in the library's count)
+                    "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] // a.steps +
+                                              (0 if (world == 1 and os.environ.get("MIEKKI_BENCH_E2E_SERIAL"))
+                                               else a.reads * (K * 24 + 4))),
+                    "path": ("one blocking mk_query_batch per step" if (world == 1 and os.environ.get("MIEKKI_BENCH_E2E_SERIAL"))
+                             else "sharded.pipelined_query: upload of step i + 1 and read-back of step i beside the scan"),
                     "ms_per_step": e2e_wall_ms / a.steps},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": scan_gbs, "peak": peak,
