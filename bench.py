@@ -8,8 +8,12 @@ One step = one pass of the query hot path (read sketch + Bloom mask -> fingerpri
 the bucket-major matrix -> threshold + bounded-heap top-k) over all reads.
 
   value     reads already resident in HBM, hit lists left in HBM (device-timed, CUDA events)
-  e2e       the C-ABI call a host program makes: reads in pinned host memory -> H2D ->
-            query -> hit lists D2H, all inside the timed region
+  e2e       the calls a host program makes: every step's reads go from pinned host memory to
+            the GPU (mk_batch_upload_flat), are queried (mk_sketch_async / mk_scan_async /
+            mk_topk_slot, as sharded.pipelined_query issues them) and the hit lists come back
+            to the host, all inside the timed region; steps are streamed: the copies of
+            step i +- 1 run beside the scan of step i (MIEKKI_BENCH_E2E_SERIAL=1 on one GPU:
+            one blocking mk_query_batch per step instead)
   roofline  the scan kernel: algorithmic bytes (sum_q A(q) * N, counted by the kernel's
             producer of the lists) / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline  the unmodified reference binary (oracle/_ref/Miekki, all host threads) on a
@@ -20,7 +24,8 @@ the bucket-major matrix -> threshold + bounded-heap top-k) over all reads.
 N > 1 (torchrun, one rank per GPU): genome-sharded, weak scaling -- every rank holds its own
 10,000-genome shard (N x 10,000 genomes in total), every rank scans all reads against its
 shard, the bounded heap is chained through the ranks in ascending id order (NCCL send/recv
-of 24 MB), `value` = sum over ranks of the read kbp each scored per second.
+of 24 MB per step, in tiles of reads), `value` = sum over ranks of the read kbp each scored
+per second.
 
 Extra blocks on the same line, measured in the same run (none of them inside the timed region
 of `value`): `c3_strong` (BASELINE config 3: 100,000 genomes at -h 17 in total, split over the
