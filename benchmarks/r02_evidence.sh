@@ -29,3 +29,17 @@ python benchmarks/file_to_index.py > gpurun_out/r02_file_to_index.json
 # here, without a GPU:
 #   ncu -i gpurun_out/r02_tiled_v5.ncu-rep --page details --csv > profiles/r02_scan_tiled_ncu_details.csv
 #   python benchmarks/sass_histogram.py > profiles/r02_sass_histogram.md
+# --- later in the round
+# the ring scan at config 2 under ncu --set full (a full count tile: launch 22)
+A="--steps 2 --warmup 3 --no-cpu-baseline --no-extras --build-e2e-genomes 0"
+python bench.py $A > /dev/null &&
+ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 21 -c 1 -o gpurun_out/r02_scan_c2 python bench.py $A
+# one rank's share of the pipelined multi-GPU path without a second GPU (config 3 on 2 GPUs, config 2)
+python benchmarks/chain_probe.py > gpurun_out/r02_chain_probe.json
+PROBE_H=20 PROBE_GENOMES=10000 PROBE_READS=100000 PROBE_READ_LEN=1000 PROBE_MIN_INT=100 python benchmarks/chain_probe.py > gpurun_out/r02_chain_probe_c2.json
+# build sweep, exact mode and file -> index through the command line
+python benchmarks/build_sweep.py --genomes 4096 --host-genomes 256 > gpurun_out/r02_build_sweep_n1.jsonl
+python benchmarks/exact_cli.py > gpurun_out/r02_exact_cli.json
+python benchmarks/file_to_index.py > gpurun_out/r02_file_to_index_c.json
+# N GPUs with the chain's time stamps:  MIEKKI_CHAIN_TRACE=gpurun_out/chain_trace python -m torch.distributed.run ... bench.py --gpus N
+#   ncu -i gpurun_out/r02_scan_c2.ncu-rep --page details --csv > profiles/r02_scan_ring_c2_ncu_details.csv
