@@ -210,3 +210,38 @@ def test_drain_tiles_and_nccl_defaults(monkeypatch):
     monkeypatch.setenv("NCCL_MAX_P2P_NCHANNELS", "4")     # the user's own setting wins
     sharded.nccl_env_defaults()
     assert os.environ["NCCL_MAX_P2P_NCHANNELS"] == "4"
+
+
+def test_pipelined_query_without_a_process_group():
+    """One shard, no torch.distributed: the streaming path bench.py's end-to-end leg takes on one GPU.
+    Three batches (the second and third travel through the second buffer pair / come back through
+    on_result in the caller's tensors), hit lines equal the reference's."""
+    from miekki_b200 import sharded
+    from oracle import oracle as orc
+    d = os.path.join(H.GOLDEN, "caseA")
+    genomes = [H.genome_like_reference(os.path.join(d, f)) for f in H.load_list(d)]
+    eng = OracleEngine(genomes, 0, 31, 12, 33)
+    reads = H.reads_like_reference(os.path.join(d, "reads.fa"), 31)
+    per = len(reads) // 3
+    parts = [reads[i * per:(i + 1) * per] for i in range(3)]
+    heap = torch.zeros((per, 10 * 24), dtype=torch.uint8)
+    lens = torch.zeros(per, dtype=torch.int32)
+    lines, freed = {}, []
+
+    def on_result(i):
+        hn = heap.numpy()
+        lines[i] = "".join(orc.format_hit_line(hd, hn[j].view(orc.HIT_DTYPE)[: int(lens[j])])
+                           for j, (hd, _) in enumerate(parts[i]))
+    sharded.pipelined_query(eng, ([s for _, s in p] for p in parts), heap, lens, 10, 10, 100.0,
+                            on_result=on_result, after_chain=freed.append, tiles=2, last_tiles=3)
+    assert freed == [0, 1, 2]
+    want = open(os.path.join(d, "hits_s200.txt")).read().split("\n")
+    got = "".join(lines[i] for i in range(3)).split("\n")
+    assert got[:3 * per] == want[:3 * per] and 3 * per >= 54
+    # without on_result the last batch's lists are left in the caller's tensors
+    heap.zero_()
+    lens.zero_()
+    sharded.pipelined_query(eng, ([s for _, s in p] for p in parts[:2]), heap, lens, 10, 10, 100.0)
+    hn = heap.numpy()
+    last = "".join(orc.format_hit_line(hd, hn[j].view(orc.HIT_DTYPE)[: int(lens[j])]) for j, (hd, _) in enumerate(parts[1]))
+    assert last.split("\n")[:per] == want[per:2 * per]
