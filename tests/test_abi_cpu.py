@@ -111,3 +111,17 @@ def test_bloom_reach_bounds_every_canonical_kmer():
             for c in canon_of(s, k):
                 assert c < bound(k), (k, s)
                 assert ((c + 1023) >> 36) < L.mk_bloom_reach(k, 33)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/miekki_b200.h must compile as C99 on its own (what a cgo /
+    ctypes / JNI binding sees), with no C++ or CUDA types in it."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "miekki_b200.h")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
